@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Instant-NGP training throughput (rays/s) on the Lego-shaped synthetic
+workload (BASELINE.json configs[1]: 800x800x100 views, 8192-ray batch, scale 0.5, HashGrid T=2^19).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one training step of ngp_pl/train.py:144-170: ray generation from (img_idxs, pix_idxs), AABB,
+marcher, hash-grid encode + density/colour MLPs, compositing, NeRFLoss, backward, Adam on all parameters, and
+the density-grid update every 16 steps.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+SCALE, N_RAYS, W_IMG, H_IMG, N_IMG = 0.5, 8192, 800, 800, 100
+WORKLOAD = "NeRF-synthetic Lego-shaped 800x800x100 views, 8192-ray batch, scale 0.5, HashGrid L=16 F=2 T=2^19"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pretrain", type=int, default=512,
+                    help="untimed training steps before warm-up so that occupancy/density reach steady state")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per step of the bounded CPU-baseline sample")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel event timing table to stderr")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(n_rays, steps, warmup):
+    """The same training step as torch CPU ops (oracle/ngp_ref.py) on a bounded sample of the workload."""
+    from google_nerf_b200 import synthetic as syn
+    from oracle import ngp_ref as O
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+    ref = O.NGPRef(SCALE, seed=1337)
+    ref.density_bitfield = syn.bitfield_from_grid(syn.density_grid(SCALE, 1))
+    K = syn.intrinsics(W_IMG, H_IMG); dirs = syn.directions(W_IMG, H_IMG, K); poses = syn.hemisphere_poses(N_IMG)
+    opt = O.AdamRef([ref.xyz_params, ref.rgb_params], lr=1e-2, eps=1e-15)
+    times = []
+    for it in range(warmup + steps):
+        ii = torch.randint(N_IMG, (n_rays,), generator=g); pi = torch.randint(W_IMG * H_IMG, (n_rays,), generator=g)
+        t0 = time.perf_counter()
+        rays_o, rays_d = syn.get_rays(dirs[pi], poses[ii])
+        target = syn.shade(rays_o, rays_d, SCALE)
+        O.train_step(ref, opt, rays_o, rays_d, target, torch.rand(n_rays, generator=g))
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.median(times))
+    return dict(value=n_rays / sec, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+                sample=f"{steps} steps x {n_rays} rays of the same workload (oracle/ngp_ref.py train_step, torch CPU ops; "
+                       f"median step {sec:.2f} s; analytic occupancy, random-init weights)"), sec
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    cb, sec = cpu_baseline(args.cpu_rays, steps, warmup)
+    line = dict(impl="reference", metric="train_rays_per_s", value=cb["value"], unit="rays/s", n_gpus=args.gpus,
+                steps=steps, warmup=warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f16", data="synthetic", config=dict(workload=WORKLOAD),
+                cpu_baseline=cb, e2e=dict(value=cb["value"], unit="rays/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note="reference vren/tiny-cuda-nn kernels are CUDA-only and absent from the reference tree; this arm "
+                     "times the same render/train math as torch CPU ops on the host cores (BASELINE.json north_star)")
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ---------------------------------------------------------------------------------------------- kernel table
+# algorithmic bytes / flops per unit (DESIGN.md "Cost model")
+def kernel_costs(n_rays, n_samples, n_params_xyz, n_params_rgb):
+    s, r = n_samples, n_rays
+    return {
+        "b2n_ray_aabb_intersect": ("hbm", 32 * r),
+        "b2n_raymarching_train_count": ("hbm", 36 * r + 24 * r),
+        "b2n_raymarching_train_write": ("hbm", 60 * r + 32 * s),
+        "b2n_hashgrid_fw": ("hbm", 588 * s),
+        "b2n_hashgrid_bw": ("hbm", 1100 * s),
+        "b2n_mlp_fw": ("tensor", None),
+        "b2n_mlp_bw": ("tensor", None),
+        "b2n_sh4_fw": ("hbm", 44 * s),
+        "b2n_composite_train_fw": ("hbm", 24 * s + 48 * r),
+        "b2n_composite_train_bw": ("hbm", 40 * s + 96 * r),
+        "b2n_nerf_loss_fwbw": ("hbm", 56 * r),
+        "b2n_adam_step": ("hbm", None),
+    }
+
+
+def profile_kernels(tr, reps=5):
+    """CUDA-event duration of every libb2n launch inside real (eager) training steps."""
+    from google_nerf_b200 import _lib as L
+    orig = L.call
+    rec = []
+
+    def timed(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); orig(name, *a); e1.record()
+        rec.append((name, a, e0, e1))
+
+    import google_nerf_b200.trainer as T
+    L.call = timed
+    try:
+        for _ in range(reps):
+            tr.step_count += 1; tr._set_hyper(); tr._body()
+        torch.cuda.synchronize()
+    finally:
+        L.call = orig
+    out = {}
+    for name, a, e0, e1 in rec:
+        key = name
+        if name == "b2n_mlp_fw" or name == "b2n_mlp_bw":
+            key = f"{name}[{'rgb' if a[4 if name == 'b2n_mlp_fw' else 5] == 2 else 'sigma'}]"
+        if name == "b2n_adam_step":
+            key = f"{name}[{'xyz' if a[5] > 100000 else 'rgb'}]"
+        d = out.setdefault(key, [0.0, 0])
+        d[0] += e0.elapsed_time(e1); d[1] += 1
+    return {k: v[0] / v[1] for k, v in out.items()}, len(rec) // reps
+
+
+# ---------------------------------------------------------------------------------------------- main arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch.distributed as dist
+    from google_nerf_b200 import synthetic as syn
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.trainer import NGPTrainer
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic dataset (same on every rank), model replicated with identical seeds
+    torch.manual_seed(1337)
+    K = syn.intrinsics(W_IMG, H_IMG); dirs = syn.directions(W_IMG, H_IMG, K); poses = syn.hemisphere_poses(N_IMG)
+    model = NGP(SCALE, encoding="HashGrid").to(dev)
+    tr = NGPTrainer(model, n_rays=N_RAYS, use_graph=not args.no_graph, seed=1234 + rank, samples_per_ray=128)
+    tr.set_dataset(dirs, poses)
+    model.mark_invisible_cells(K.to(dev), poses.to(dev), (W_IMG, H_IMG))
+
+    total_steps = args.pretrain + args.warmup + 2 * args.steps + 8
+    g = torch.Generator().manual_seed(100 + rank)
+    img_all = torch.randint(N_IMG, (total_steps, N_RAYS), generator=g)
+    pix_all = torch.randint(W_IMG * H_IMG, (total_steps, N_RAYS), generator=g)
+    # ground truth of every batch, shaded on the GPU in chunks, kept in pinned host memory (the dataloader's
+    # `rays[img_idxs, pix_idxs]`, datasets/base.py:31)
+    rgb_all = torch.empty(total_steps, N_RAYS, 3).pin_memory()
+    dd, pp = dirs.to(dev), poses.to(dev)
+    for s0 in range(0, total_steps, 64):
+        ii = img_all[s0:s0 + 64].reshape(-1).to(dev); pi = pix_all[s0:s0 + 64].reshape(-1).to(dev)
+        ro, rd = syn.get_rays(dd[pi], pp[ii])
+        rgb_all[s0:s0 + 64] = syn.shade(ro, rd, SCALE).view(-1, N_RAYS, 3).cpu()
+    img_all, pix_all = img_all.pin_memory(), pix_all.pin_memory()
+    img_dev, pix_dev, rgb_dev = img_all.to(dev), pix_all.to(dev), rgb_all.to(dev)
+
+    it = [0]
+
+    def dev_step():                       # inputs already resident in HBM
+        i = it[0]; it[0] += 1
+        tr.set_batch_indices(img_dev[i], pix_dev[i], rgb_dev[i])
+        return tr.step()
+
+    def host_step():                      # the call a user makes: host batch in, loss out
+        i = it[0]; it[0] += 1
+        loss = tr.step_batch({"img_idxs": img_all[i], "pix_idxs": pix_all[i], "rgb": rgb_all[i]})
+        return float(loss.item())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- pretrain (untimed) to steady-state occupancy; grow the sample capacity if it overflows
+    for i in range(args.pretrain):
+        dev_step()
+        if i % 32 == 31 and tr.overflowed():
+            tr.grow(1.5)
+    for _ in range(max(args.warmup, 3)):
+        dev_step()
+    barrier()
+    if tr.overflowed():
+        tr.grow(1.5)
+        for _ in range(3):
+            dev_step()
+        barrier()
+
+    # ---- timed: device-resident inputs
+    clocks = ClockSampler(local); clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(); e0.record()
+    for _ in range(args.steps):
+        dev_step()
+    e1.record(); barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    samples = tr.samples_last_step()
+    # ---- timed: end to end through the public API with host batches (H2D + loss D2H inside)
+    barrier(); t0 = time.perf_counter(); e0.record()
+    for _ in range(args.steps):
+        last_loss = host_step()
+    e1.record(); barrier()
+    ms_e2e = torch.tensor([max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)], device=dev)
+    clk = clocks.stop()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX); dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(ms.item()), float(ms_e2e.item())
+
+    if rank == 0:
+        # ---- per-kernel table + roofline of the dominant kernel (eager replays of the same step)
+        tr.use_graph = False
+        table, launches_per_step = profile_kernels(tr)
+        tr.use_graph = not args.no_graph
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+            os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
+        hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+        tf_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
+        costs = kernel_costs(N_RAYS, samples, tr.p_xyz.numel(), tr.p_rgb.numel())
+        top = max(table, key=table.get)
+        base = top.split("[")[0]
+        bound = costs.get(base, ("hbm", None))[0]
+        if base == "b2n_adam_step":
+            alg = 34.0 * (tr.p_xyz.numel() if "xyz" in top else tr.p_rgb.numel())
+        elif base == "b2n_mlp_fw":
+            alg = samples * (2 * (32 * 64 + 64 * 16) if "sigma" in top else 2 * (32 * 64 + 64 * 64 + 64 * 16))
+        elif base == "b2n_mlp_bw":
+            alg = samples * 2 * (2 * (32 * 64 + 64 * 16) if "sigma" in top else 2 * (32 * 64 + 64 * 64 + 64 * 16))
+        else:
+            alg = costs.get(base, ("hbm", 0))[1]
+        dur_s = table[top] * 1e-3
+        if bound == "hbm":
+            ach, peak, unit = alg / dur_s / 1e9, hbm_peak, "GB/s"
+        else:
+            ach, peak, unit = alg / dur_s / 1e12, tf_peak, "TFLOP/s"
+        roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+                        peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
+                        ms_per_launch=table[top], share_of_step=table[top] / sum(table.values()),
+                        algorithmic_per_launch=alg)
+        if args.profile:
+            for k, v in sorted(table.items(), key=lambda kv: -kv[1]):
+                print(f"  {k:40s} {v * 1e3:9.1f} us", file=sys.stderr)
+        cb = None
+        if not args.skip_cpu:
+            cb, _ = cpu_baseline(args.cpu_rays, 2, 1)
+        rays = N_RAYS * world * args.steps
+        n_updates = sum(1 for s in range(args.steps) if s % tr.S == 0)
+        line = dict(metric="train_rays_per_s", value=rays / (ms * 1e-3), unit="rays/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f16", data="synthetic (analytic 3-sphere+box scene, random-init weights "
+                    f"trained {args.pretrain} untimed steps to steady-state occupancy)",
+                    config=dict(workload=WORKLOAD, rays_per_gpu=N_RAYS, samples_per_step=samples,
+                                samples_per_ray=samples / N_RAYS, cuda_graph=not args.no_graph,
+                                l2="per-step working set (206 MB optimiser state + sample buffers) exceeds the 126 MB "
+                                   "L2; no explicit flush", parallelism=f"dp{world}"),
+                    clocks=clk,
+                    e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
+                             d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
+                    gpu_launches=launches_per_step * args.steps + 12 * n_updates,
+                    roofline=roofline, cpu_baseline=cb,
+                    kernels_us={k: round(v * 1e3, 1) for k, v in table.items()})
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,204 @@
+// composite.cu -- front-to-back transmittance compositing (train fw/bw, test fw).
+// Replaces vren.composite_train_fw / composite_train_bw / composite_test_fw
+// (ngp_pl/models/custom_functions.py:140-142,153-158; ngp_pl/models/rendering.py:97-100).
+//
+// Design (DESIGN.md "Compositing"): one warp per ray; the ray's packed samples are contiguous, so the 32
+// lanes read 32 consecutive samples (coalesced 128 B lines for sigma/delta/t, 384 B for rgb) and a
+// shuffle product-scan gives each lane its transmittance.  HBM-bound: 24 B/sample + 48 B/ray forward,
+// 40 B/sample + 96 B/ray backward.
+#include "common.cuh"
+
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v *= u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float u = __shfl_up_sync(FULL, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(256) composite_train_fw_kernel(
+    const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+    const float *__restrict__ ts, const int64_t *__restrict__ rays_a, float T_threshold, int64_t n_rays,
+    float *__restrict__ opacity, float *__restrict__ depth, float *__restrict__ depth_sq,
+    float *__restrict__ rgb) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
+        const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
+        const int N = (int)rays_a[3 * n + 2];
+        float T_run = 1.0f, aO = 0.f, aD = 0.f, aD2 = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
+        for (int base = 0; base < N; base += 32) {
+            const int k = base + lane;
+            const bool active = k < N;
+            const int64_t s = start + k;
+            float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (active) {
+                a = 1.0f - expf(-__ldg(sigmas + s) * __ldg(deltas + s));
+                t = __ldg(ts + s);
+                cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
+            }
+            const float P = warp_scan_mul(1.0f - a, lane);   // prod_{i<=lane} (1-a_i)
+            float Pprev = __shfl_up_sync(FULL, P, 1);
+            if (lane == 0) Pprev = 1.0f;
+            const float T_after = T_run * P, T_before = T_run * Pprev;
+            const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
+            const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
+            if (active && lane <= first_dead) {
+                const float w = a * T_before;
+                aO += w; aD += w * t; aD2 += w * t * t;
+                aR += w * cr; aG += w * cg; aB += w * cb;
+            }
+            if (first_dead < 32) break;
+            T_run = __shfl_sync(FULL, T_after, 31);
+        }
+        aO = warp_sum(aO); aD = warp_sum(aD); aD2 = warp_sum(aD2);
+        aR = warp_sum(aR); aG = warp_sum(aG); aB = warp_sum(aB);
+        if (lane == 0) {
+            opacity[ray] = aO; depth[ray] = aD; depth_sq[ray] = aD2;
+            rgb[3 * ray] = aR; rgb[3 * ray + 1] = aG; rgb[3 * ray + 2] = aB;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) composite_train_bw_kernel(
+    const float *__restrict__ dL_dopacity, const float *__restrict__ dL_ddepth,
+    const float *__restrict__ dL_ddepth_sq, const float *__restrict__ dL_drgb,
+    const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+    const float *__restrict__ ts, const int64_t *__restrict__ rays_a, const float *__restrict__ opacity,
+    const float *__restrict__ depth, const float *__restrict__ depth_sq, const float *__restrict__ rgb,
+    float T_threshold, int64_t n_rays, float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
+        const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
+        const int N = (int)rays_a[3 * n + 2];
+        const float gR = __ldg(dL_drgb + 3 * ray), gG = __ldg(dL_drgb + 3 * ray + 1), gB = __ldg(dL_drgb + 3 * ray + 2);
+        const float gO = __ldg(dL_dopacity + ray), gD = __ldg(dL_ddepth + ray), gD2 = __ldg(dL_ddepth_sq + ray);
+        // sum_c g_c*(C_c - c_c) + gD*(D-d) + gD2*(D2-d2) = Q_total - q_prefix  (the reference's six terms,
+        // regrouped so that one sum-scan per chunk suffices)
+        const float Q_total = gR * __ldg(rgb + 3 * ray) + gG * __ldg(rgb + 3 * ray + 1) + gB * __ldg(rgb + 3 * ray + 2) +
+                              gD * __ldg(depth + ray) + gD2 * __ldg(depth_sq + ray);
+        const float opa_term = gO * (1.0f - __ldg(opacity + ray));
+        float T_run = 1.0f, q_run = 0.0f;
+        bool stopped = false;
+        for (int base = 0; base < N; base += 32) {
+            const int k = base + lane;
+            const bool active = k < N;
+            const int64_t s = start + k;
+            if (stopped) {  // samples after an early stop get zero gradient
+                if (active) { dL_dsigmas[s] = 0.f; dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; }
+                continue;
+            }
+            float a = 0.f, t = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            if (active) {
+                dl = __ldg(deltas + s);
+                a = 1.0f - expf(-__ldg(sigmas + s) * dl);
+                t = __ldg(ts + s);
+                cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
+            }
+            const float P = warp_scan_mul(1.0f - a, lane);
+            float Pprev = __shfl_up_sync(FULL, P, 1);
+            if (lane == 0) Pprev = 1.0f;
+            const float T_after = T_run * P, T_before = T_run * Pprev;
+            const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
+            const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
+            const bool incl = active && lane <= first_dead;
+            const float w = incl ? a * T_before : 0.0f;
+            const float gc = gR * cr + gG * cg + gB * cb + gD * t + gD2 * t * t;
+            const float q_incl = q_run + warp_scan_add(w * gc, lane);
+            if (active) {
+                float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+                if (incl) {
+                    dr = gR * w; dg = gG * w; db = gB * w;
+                    ds = dl * (gc * T_after - (Q_total - q_incl) + opa_term);
+                }
+                dL_dsigmas[s] = ds;
+                dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
+            }
+            if (first_dead < 32) stopped = true;
+            T_run = __shfl_sync(FULL, T_after, 31);
+            q_run = __shfl_sync(FULL, q_incl, 31);
+        }
+    }
+}
+
+// Test-time compositor: one thread per alive ray, serial over its <= 64 new samples (in place).
+__global__ void __launch_bounds__(256) composite_test_fw_kernel(
+    const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+    const float *__restrict__ ts, int64_t *alive_indices, float T_threshold,
+    const int32_t *__restrict__ n_eff, int n_samples, int64_t n_alive, float *opacity, float *depth,
+    float *rgb) {
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_alive) return;
+    const int ne = n_eff[n];
+    if (ne == 0) { alive_indices[n] = -1; return; }
+    const int64_t r = alive_indices[n];
+    float op = opacity[r], dp = depth[r], cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
+    float T = 1.0f - op;
+    for (int s = 0; s < ne; ++s) {
+        const int64_t k = n * n_samples + s;
+        const float a = 1.0f - expf(-__ldg(sigmas + k) * __ldg(deltas + k));
+        const float w = a * T;
+        cr += w * __ldg(rgbs + 3 * k); cg += w * __ldg(rgbs + 3 * k + 1); cb += w * __ldg(rgbs + 3 * k + 2);
+        dp += w * __ldg(ts + k);
+        op += w;
+        T *= 1.0f - a;
+        if (T <= T_threshold) { alive_indices[n] = -1; break; }
+    }
+    opacity[r] = op; depth[r] = dp; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+}
+
+static inline unsigned warp_grid(int64_t n_warps) { return b2n_grid((n_warps + 7) / 8, 8); }
+
+extern "C" int b2n_composite_train_fw(const float *sigmas, const float *rgbs, const float *deltas,
+                                      const float *ts, const int64_t *rays_a, float T_threshold,
+                                      int64_t n_rays, float *opacity, float *depth, float *depth_sq,
+                                      float *rgb, void *stream) {
+    if (n_rays <= 0) return 0;
+    composite_train_fw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, rays_a, T_threshold, n_rays, opacity, depth, depth_sq, rgb);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_ddepth,
+                                      const float *dL_ddepth_sq, const float *dL_drgb, const float *sigmas,
+                                      const float *rgbs, const float *deltas, const float *ts,
+                                      const int64_t *rays_a, const float *opacity, const float *depth,
+                                      const float *depth_sq, const float *rgb, float T_threshold,
+                                      int64_t n_rays, float *dL_dsigmas, float *dL_drgbs, void *stream) {
+    if (n_rays <= 0) return 0;
+    composite_train_bw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
+        dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb, sigmas, rgbs, deltas, ts, rays_a, opacity, depth,
+        depth_sq, rgb, T_threshold, n_rays, dL_dsigmas, dL_drgbs);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas,
+                                     const float *ts, const float *hits_t, int64_t *alive_indices,
+                                     float T_threshold, const int32_t *n_eff, int n_samples,
+                                     int64_t n_alive, float *opacity, float *depth, float *rgb, void *stream) {
+    (void)hits_t;
+    if (n_alive <= 0) return 0;
+    composite_test_fw_kernel<<<b2n_blocks(n_alive, 256), 256, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff, n_samples, n_alive, opacity, depth, rgb);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

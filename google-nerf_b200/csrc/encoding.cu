@@ -1,0 +1,252 @@
+// encoding.cu -- multiresolution hash grid (fw / table-bw), frequency and spherical-harmonics encodings.
+// Replaces the tiny-cuda-nn encodings NGP builds (ngp_pl/models/networks.py:34-53,63-70).
+//
+// Hash grid design (DESIGN.md "Hash grid"): gather-bound.  One thread owns one sample and walks all levels,
+// so the 32 lanes of a warp always gather from the SAME level's table (neighbouring samples of a ray hit
+// neighbouring entries) and every thread keeps 8 independent 4-byte gathers in flight per level; the
+// thread's 64-byte output row is written with 16-byte stores.  The fp16 table (21.8 MiB at T=2^19) stays
+// L2-resident on B200 (126 MB L2).  Backward accumulates straight into the fp32 gradient table with
+// vector red.global.add.v2.f32 (no fp16 underflow, no separate cast pass).
+// Algorithmic bytes per sample: 12 in + 16 levels x 8 corners x 4 B gathered + 64 out = 588 B.
+#include "common.cuh"
+
+struct GridLevels {
+    int n_levels;
+    float scale[B2N_MAX_LEVELS];
+    uint32_t resolution[B2N_MAX_LEVELS];
+    uint32_t size[B2N_MAX_LEVELS];
+    uint32_t offset[B2N_MAX_LEVELS];
+};
+
+static int to_levels(const b2n_grid_layout *l, GridLevels &g) {
+    B2N_CHECK_ARG(l != nullptr && l->n_features == 2 && l->n_levels >= 1 && l->n_levels <= B2N_MAX_LEVELS,
+                  "hash grid needs n_features == 2 and 1..32 levels");
+    g.n_levels = l->n_levels;
+    for (int i = 0; i < l->n_levels; ++i) {
+        g.scale[i] = l->scale[i]; g.resolution[i] = l->resolution[i];
+        g.size[i] = l->size[i]; g.offset[i] = l->offset[i];
+    }
+    return 0;
+}
+
+extern "C" int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                                   double per_level_scale, b2n_grid_layout *layout) {
+    B2N_CHECK_ARG(layout && n_levels >= 1 && n_levels <= B2N_MAX_LEVELS && n_features == 2 &&
+                  log2_hashmap_size >= 3 && log2_hashmap_size <= 30 && base_resolution >= 1, "bad hash grid config");
+    layout->n_levels = n_levels; layout->n_features = n_features;
+    uint64_t off = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        // b^l in double, snapped to an integer when within 1e-6 so that the intended resolutions
+        // (N_min ... 2048*scale) do not hinge on one ulp of exp2f/log2f (DESIGN.md "Hash grid").
+        double v = pow(per_level_scale, (double)l) * base_resolution;
+        if (fabs(v - nearbyint(v)) < 1e-6 * v) v = nearbyint(v);
+        const float s = (float)(v - 1.0);
+        const uint32_t res = (uint32_t)ceilf(s) + 1;
+        uint64_t n = (uint64_t)res * res * res;
+        if (n > 0x7fffffffull) n = 0x7fffffffull;
+        n = (n + 7) / 8 * 8;
+        if (n > (1ull << log2_hashmap_size)) n = 1ull << log2_hashmap_size;
+        layout->scale[l] = s; layout->resolution[l] = res; layout->size[l] = (uint32_t)n;
+        layout->offset[l] = (uint32_t)off;
+        off += n;
+        B2N_CHECK_ARG(off < 0xffffffffull, "hash table too large");
+    }
+    layout->offset[n_levels] = (uint32_t)off;
+    return 0;
+}
+
+// entry index of one corner (tiny-cuda-nn grid_index: dense x + y*res + z*res^2 while it fits, otherwise the
+// coherent prime hash), all in wrapping uint32 arithmetic
+__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size) {
+    uint32_t stride = 1, index = 0;
+    // unrolled over the 3 dims with the early exit of the reference loop
+    if (stride <= size) { index += x * stride; stride *= res; }
+    if (stride <= size) { index += y * stride; stride *= res; }
+    if (stride <= size) { index += z * stride; stride *= res; }
+    if (size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
+    return index % size;
+}
+
+struct Corner8 {
+    uint32_t idx[8];
+    float w[8];
+};
+
+__device__ __forceinline__ void level_corners(float px, float py, float pz, float scale, uint32_t res,
+                                              uint32_t size, uint32_t offset, Corner8 &c) {
+    const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
+    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
+    const uint32_t x0 = (uint32_t)gx, y0 = (uint32_t)gy, z0 = (uint32_t)gz;
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint32_t x = x0 + (k & 1), y = y0 + ((k >> 1) & 1), z = z0 + ((k >> 2) & 1);
+        float w = 1.0f;
+        w *= (k & 1) ? wx : 1.0f - wx;
+        w *= (k & 2) ? wy : 1.0f - wy;
+        w *= (k & 4) ? wz : 1.0f - wz;
+        c.idx[k] = offset + grid_index(x, y, z, res, size);
+        c.w[k] = w;
+    }
+}
+
+__global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restrict__ x,
+                                                          const __half2 *__restrict__ table,
+                                                          const __grid_constant__ GridLevels g, int64_t n,
+                                                          const int32_t *__restrict__ n_dev,
+                                                          __half *__restrict__ out, int out_stride) {
+    n = b2n_eff_n(n, n_dev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+        __half2 *row = reinterpret_cast<__half2 *>(out + i * out_stride);
+        #pragma unroll 4
+        for (int l = 0; l < g.n_levels; ++l) {
+            Corner8 c;
+            level_corners(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], c);
+            __half2 v[8];
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = __ldg(table + c.idx[k]);
+            float a0 = 0.f, a1 = 0.f;
+            #pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float2 f = __half22float2(v[k]);
+                a0 = fmaf(c.w[k], f.x, a0);
+                a1 = fmaf(c.w[k], f.y, a1);
+            }
+            row[l] = __floats2half2_rn(a0, a1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restrict__ x,
+                                                          const __half *__restrict__ dy, int dy_stride,
+                                                          const __grid_constant__ GridLevels g, int64_t n,
+                                                          const int32_t *__restrict__ n_dev, float grad_scale,
+                                                          float2 *__restrict__ grad_table) {
+    n = b2n_eff_n(n, n_dev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+        const __half2 *row = reinterpret_cast<const __half2 *>(dy + i * dy_stride);
+        #pragma unroll 2
+        for (int l = 0; l < g.n_levels; ++l) {
+            float2 gr = __half22float2(__ldg(row + l));
+            gr.x *= grad_scale; gr.y *= grad_scale;
+            if (gr.x == 0.0f && gr.y == 0.0f) continue;
+            Corner8 c;
+            level_corners(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], c);
+            #pragma unroll
+            for (int k = 0; k < 8; ++k)
+                atomicAdd(grad_table + c.idx[k], make_float2(gr.x * c.w[k], gr.y * c.w[k]));
+        }
+    }
+}
+
+extern "C" int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_grid_layout *layout, int64_t n,
+                               const int32_t *n_dev, b2n_half *out, int out_stride, void *stream) {
+    GridLevels g;
+    if (to_levels(layout, g)) return 1;
+    B2N_CHECK_ARG(out_stride >= 2 * g.n_levels && out_stride % 2 == 0, "out_stride too small / odd");
+    if (n <= 0) return 0;
+    hashgrid_fw_kernel<<<b2n_grid(b2n_blocks(n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
+        x, (const __half2 *)table, g, n, n_dev, (__half *)out, out_stride);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_stride,
+                               const b2n_grid_layout *layout, int64_t n, const int32_t *n_dev,
+                               float grad_scale, float *grad_table, void *stream) {
+    GridLevels g;
+    if (to_levels(layout, g)) return 1;
+    B2N_CHECK_ARG(dy_stride >= 2 * g.n_levels && dy_stride % 2 == 0, "dy_stride too small / odd");
+    if (n <= 0) return 0;
+    hashgrid_bw_kernel<<<b2n_grid(b2n_blocks(n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
+        x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Frequency encoding: column j of the 3*F*2 encoded columns is sin(2^f * pi * x_d + (j&1) * pi/2) with
+// d = j / (2F), f = (j/2) % F; the remaining columns up to a multiple of 16 are ones.
+__global__ void __launch_bounds__(256) frequency_fw_kernel(const float *__restrict__ x, int n_freq, int width,
+                                                           int64_t n, const int32_t *__restrict__ n_dev,
+                                                           __half *__restrict__ out, int out_stride) {
+    n = b2n_eff_n(n, n_dev);
+    const int enc = 3 * n_freq * 2;
+    const int64_t total = n * width;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = e / width;
+        const int j = (int)(e - i * width);
+        float v = 1.0f;
+        if (j < enc) {
+            const int d = j / (2 * n_freq), f = (j >> 1) % n_freq;
+            const float xs = scalbnf(__ldg(x + 3 * i + d), f);
+            v = sinf(__fadd_rn(__fmul_rn(xs, 3.14159265358979323846f), (j & 1) ? 1.57079632679489661923f : 0.0f));
+        }
+        out[i * out_stride + j] = __float2half_rn(v);
+    }
+}
+
+extern "C" int b2n_frequency_fw(const float *x, int n_frequencies, int64_t n, const int32_t *n_dev,
+                                b2n_half *out, int out_stride, void *stream) {
+    const int width = (3 * n_frequencies * 2 + 15) / 16 * 16;
+    B2N_CHECK_ARG(n_frequencies >= 1 && out_stride >= width, "bad frequency config");
+    if (n <= 0) return 0;
+    frequency_fw_kernel<<<b2n_grid(b2n_blocks(n * width, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        x, n_frequencies, width, n, n_dev, (__half *)out, out_stride);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Real spherical harmonics up to degree 4 (16 coefficients) of a unit vector.
+__device__ __forceinline__ void sh4_eval(float x, float y, float z, float *o) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__global__ void __launch_bounds__(256) sh4_fw_kernel(const float *__restrict__ d, int normalize, int64_t n,
+                                                     const int32_t *__restrict__ n_dev,
+                                                     __half *__restrict__ out, int out_stride) {
+    n = b2n_eff_n(n, n_dev);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = __ldg(d + 3 * i), y = __ldg(d + 3 * i + 1), z = __ldg(d + 3 * i + 2);
+        if (normalize) {
+            const float inv = 1.0f / sqrtf(x * x + y * y + z * z);
+            x *= inv; y *= inv; z *= inv;
+        } else {  // tcnn convention: input in [0,1] -> [-1,1]
+            x = x * 2.0f - 1.0f; y = y * 2.0f - 1.0f; z = z * 2.0f - 1.0f;
+        }
+        float o[16];
+        sh4_eval(x, y, z, o);
+        __half2 *row = reinterpret_cast<__half2 *>(out + i * out_stride);
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) row[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+    }
+}
+
+extern "C" int b2n_sh4_fw(const float *d, int normalize, int64_t n, const int32_t *n_dev, b2n_half *out,
+                          int out_stride, void *stream) {
+    B2N_CHECK_ARG(out_stride >= 16 && out_stride % 2 == 0, "out_stride must be even and >= 16");
+    if (n <= 0) return 0;
+    sh4_fw_kernel<<<b2n_grid(b2n_blocks(n, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        d, normalize, n, n_dev, (__half *)out, out_stride);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

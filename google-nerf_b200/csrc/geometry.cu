@@ -1,0 +1,211 @@
+// geometry.cu -- ray/AABB, ray/sphere, Morton codes, packbits.
+// Compiled with -fmad=false: the numerics contract for bit-exact geometry is one IEEE fp32 operation per
+// source operation, no fused multiply-add (DESIGN.md "Numerics"); the oracle is built the same way.
+// Replaces vren.ray_aabb_intersect / ray_sphere_intersect / morton3D / morton3D_invert / packbits
+// (ngp_pl/models/custom_functions.py:29,52; ngp_pl/models/networks.py:128,147,153,251-252).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+void b2n_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *b2n_last_error(void) { return g_err; }
+extern "C" int b2n_version(void) { return B2N_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// One thread per ray; boxes/spheres are looped (render() uses exactly one box, max_hits = 1, so this is
+// launch-latency bound: 32 B/ray of HBM traffic).  Hits are kept sorted near-to-far by stable insertion.
+__device__ __forceinline__ void insert_hit(float t1, float t2, int64_t v, int max_hits, int &cnt,
+                                           float *ht, int64_t *hv) {
+    int pos = cnt < max_hits ? cnt : max_hits;
+    while (pos > 0 && ht[2 * (pos - 1)] > t1) --pos;
+    if (pos >= max_hits) return;
+    int last = cnt < max_hits ? cnt : max_hits - 1;
+    for (int k = last; k > pos; --k) {
+        ht[2 * k] = ht[2 * (k - 1)];
+        ht[2 * k + 1] = ht[2 * (k - 1) + 1];
+        hv[k] = hv[k - 1];
+    }
+    ht[2 * pos] = t1;
+    ht[2 * pos + 1] = t2;
+    hv[pos] = v;
+    if (cnt < max_hits) ++cnt;
+}
+
+__global__ void __launch_bounds__(256) ray_aabb_kernel(const float *__restrict__ rays_o,
+                                                       const float *__restrict__ rays_d,
+                                                       const float *__restrict__ centers,
+                                                       const float *__restrict__ half_sizes,
+                                                       int64_t n_rays, int64_t n_voxels, int max_hits,
+                                                       int32_t *__restrict__ hits_cnt,
+                                                       float *__restrict__ hits_t,
+                                                       int64_t *__restrict__ hits_idx) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float *ht = hits_t + r * max_hits * 2;
+    int64_t *hv = hits_idx + r * max_hits;
+    for (int k = 0; k < max_hits; ++k) {
+        ht[2 * k] = -1.0f;
+        ht[2 * k + 1] = -1.0f;
+        hv[k] = -1;
+    }
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float ix = 1.0f / rays_d[3 * r], iy = 1.0f / rays_d[3 * r + 1], iz = 1.0f / rays_d[3 * r + 2];
+    int cnt = 0, total = 0;
+    for (int64_t v = 0; v < n_voxels; ++v) {
+        const float cx = __ldg(centers + 3 * v), cy = __ldg(centers + 3 * v + 1), cz = __ldg(centers + 3 * v + 2);
+        const float hx = __ldg(half_sizes + 3 * v), hy = __ldg(half_sizes + 3 * v + 1), hz = __ldg(half_sizes + 3 * v + 2);
+        const float ax = (cx - hx - ox) * ix, bx = (cx + hx - ox) * ix;
+        const float ay = (cy - hy - oy) * iy, by = (cy + hy - oy) * iy;
+        const float az = (cz - hz - oz) * iz, bz = (cz + hz - oz) * iz;
+        const float t1 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz));
+        const float t2 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz));
+        if (t1 > t2) continue;
+        if (t2 > 0.0f) {
+            ++total;
+            insert_hit(fmaxf(t1, 0.0f), t2, v, max_hits, cnt, ht, hv);
+        }
+    }
+    hits_cnt[r] = total;
+}
+
+__global__ void __launch_bounds__(256) ray_sphere_kernel(const float *__restrict__ rays_o,
+                                                         const float *__restrict__ rays_d,
+                                                         const float *__restrict__ centers,
+                                                         const float *__restrict__ radii, int64_t n_rays,
+                                                         int64_t n_spheres, int max_hits,
+                                                         int32_t *__restrict__ hits_cnt,
+                                                         float *__restrict__ hits_t,
+                                                         int64_t *__restrict__ hits_idx) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float *ht = hits_t + r * max_hits * 2;
+    int64_t *hv = hits_idx + r * max_hits;
+    for (int k = 0; k < max_hits; ++k) {
+        ht[2 * k] = -1.0f;
+        ht[2 * k + 1] = -1.0f;
+        hv[k] = -1;
+    }
+    const float ox = rays_o[3 * r], oy = rays_o[3 * r + 1], oz = rays_o[3 * r + 2];
+    const float dx = rays_d[3 * r], dy = rays_d[3 * r + 1], dz = rays_d[3 * r + 2];
+    const float a = dx * dx + dy * dy + dz * dz;
+    int cnt = 0, total = 0;
+    for (int64_t s = 0; s < n_spheres; ++s) {
+        const float px = ox - __ldg(centers + 3 * s), py = oy - __ldg(centers + 3 * s + 1),
+                    pz = oz - __ldg(centers + 3 * s + 2);
+        const float rad = __ldg(radii + s);
+        const float hb = px * dx + py * dy + pz * dz;
+        const float c = px * px + py * py + pz * pz - rad * rad;
+        const float disc = hb * hb - a * c;
+        if (disc < 0.0f) continue;
+        const float sq = sqrtf(disc);
+        const float t1 = (-hb - sq) / a, t2 = (-hb + sq) / a;
+        if (t2 > 0.0f) {
+            ++total;
+            insert_hit(fmaxf(t1, 0.0f), t2, s, max_hits, cnt, ht, hv);
+        }
+    }
+    hits_cnt[r] = total;
+}
+
+__global__ void clamp_near_kernel(float *hits_t, int64_t n_rays, float near_distance) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    const float t1 = hits_t[2 * r];
+    if (t1 >= 0.0f && t1 < near_distance) hits_t[2 * r] = near_distance;
+}
+
+extern "C" int b2n_ray_aabb_intersect(const float *rays_o, const float *rays_d, const float *centers,
+                                      const float *half_sizes, int64_t n_rays, int64_t n_voxels,
+                                      int max_hits, int32_t *hits_cnt, float *hits_t,
+                                      int64_t *hits_voxel_idx, void *stream) {
+    B2N_CHECK_ARG(max_hits >= 1 && n_rays >= 0 && n_voxels >= 0, "bad sizes");
+    if (n_rays == 0) return 0;
+    ray_aabb_kernel<<<b2n_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, centers, half_sizes, n_rays, n_voxels, max_hits, hits_cnt, hits_t, hits_voxel_idx);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_ray_sphere_intersect(const float *rays_o, const float *rays_d, const float *centers,
+                                        const float *radii, int64_t n_rays, int64_t n_spheres,
+                                        int max_hits, int32_t *hits_cnt, float *hits_t,
+                                        int64_t *hits_sphere_idx, void *stream) {
+    B2N_CHECK_ARG(max_hits >= 1 && n_rays >= 0 && n_spheres >= 0, "bad sizes");
+    if (n_rays == 0) return 0;
+    ray_sphere_kernel<<<b2n_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        rays_o, rays_d, centers, radii, n_rays, n_spheres, max_hits, hits_cnt, hits_t, hits_sphere_idx);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_clamp_near(float *hits_t, int64_t n_rays, float near_distance, void *stream) {
+    if (n_rays <= 0) return 0;
+    clamp_near_kernel<<<b2n_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(hits_t, n_rays, near_distance);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void morton3D_kernel(const int32_t *__restrict__ coords, int64_t n, int32_t *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (int32_t)b2n_morton3D((uint32_t)coords[3 * i], (uint32_t)coords[3 * i + 1], (uint32_t)coords[3 * i + 2]);
+}
+__global__ void morton3D_invert_kernel(const int32_t *__restrict__ idx, int64_t n, int32_t *__restrict__ coords) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t v = (uint32_t)idx[i];
+    coords[3 * i + 0] = (int32_t)b2n_compact_bits(v);
+    coords[3 * i + 1] = (int32_t)b2n_compact_bits(v >> 1);
+    coords[3 * i + 2] = (int32_t)b2n_compact_bits(v >> 2);
+}
+
+extern "C" int b2n_morton3D(const int32_t *coords, int64_t n, int32_t *indices, void *stream) {
+    if (n <= 0) return 0;
+    morton3D_kernel<<<b2n_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(coords, n, indices);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b2n_morton3D_invert(const int32_t *indices, int64_t n, int32_t *coords, void *stream) {
+    if (n <= 0) return 0;
+    morton3D_invert_kernel<<<b2n_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(indices, n, coords);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// packbits: one thread per output byte reads 32 B (two float4) and writes 1 B; HBM-bound, 33 B/byte.
+__global__ void __launch_bounds__(256) packbits_kernel(const float4 *__restrict__ grid, int64_t n_bytes,
+                                                       float threshold, const float *__restrict__ threshold_dev,
+                                                       uint8_t *__restrict__ bitfield) {
+    const float thr = threshold_dev ? __ldg(threshold_dev) : threshold;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_bytes;
+         n += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(grid + 2 * n), b = __ldg(grid + 2 * n + 1);
+        uint32_t bits = 0;
+        bits |= (a.x > thr) ? 1u : 0u;
+        bits |= (a.y > thr) ? 2u : 0u;
+        bits |= (a.z > thr) ? 4u : 0u;
+        bits |= (a.w > thr) ? 8u : 0u;
+        bits |= (b.x > thr) ? 16u : 0u;
+        bits |= (b.y > thr) ? 32u : 0u;
+        bits |= (b.z > thr) ? 64u : 0u;
+        bits |= (b.w > thr) ? 128u : 0u;
+        bitfield[n] = (uint8_t)bits;
+    }
+}
+
+extern "C" int b2n_packbits(const float *density_grid, int64_t n_bytes, float threshold,
+                            const float *threshold_dev, uint8_t *density_bitfield, void *stream) {
+    if (n_bytes <= 0) return 0;
+    B2N_CHECK_ARG(((uintptr_t)density_grid & 15) == 0, "density_grid must be 16-byte aligned");
+    packbits_kernel<<<b2n_grid(b2n_blocks(n_bytes, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        (const float4 *)density_grid, n_bytes, threshold, threshold_dev, density_bitfield);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

@@ -1,0 +1,227 @@
+// optim.cu -- optimiser step, occupancy-grid maintenance and the fused NeRF loss.
+// Replaces apex FusedAdam as used at ngp_pl/train.py:112, the torch ops of NGP.update_density_grid
+// (ngp_pl/models/networks.py:225-252) and NeRFLoss + background blend
+// (ngp_pl/losses.py:26-40, ngp_pl/models/rendering.py:159-164).  All streaming, HBM-bound kernels:
+// 128-bit accesses, grid-stride loops on a grid sized to the 148 SMs.
+#include "common.cuh"
+
+#define FULL 0xffffffffu
+
+// ------------------------------------------------------------------------------------------------ Adam
+// Per parameter: read p, g, m, v (16 B), write p, m, v (12 B), zero g (4 B), write fp16 copy (2 B) = 34 B.
+__global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g,
+                                                   float4 *__restrict__ m, float4 *__restrict__ v,
+                                                   __half2 *__restrict__ h, int64_t n4, float lr, float b1,
+                                                   float b2, float eps, float inv_scale, int step,
+                                                   const void *__restrict__ hyper) {
+    if (hyper != nullptr) {
+        lr = *reinterpret_cast<const float *>(hyper);
+        step = reinterpret_cast<const int *>(hyper)[1];
+    }
+    const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+        float *P = &pp.x, *G = &gg.x, *M = &mm.x, *V = &vv.x;
+        #pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = G[k] * inv_scale;
+            M[k] = b1 * M[k] + (1.0f - b1) * gr;
+            V[k] = b2 * V[k] + (1.0f - b2) * gr * gr;
+            P[k] -= lr * (M[k] / c1) / (sqrtf(V[k] / c2) + eps);
+        }
+        p[i] = pp; m[i] = mm; v[i] = vv;
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (h != nullptr) {
+            h[2 * i] = __floats2half2_rn(pp.x, pp.y);
+            h[2 * i + 1] = __floats2half2_rn(pp.z, pp.w);
+        }
+    }
+}
+
+extern "C" int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
+                             int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale,
+                             int step, const void *hyper_dev, void *stream) {
+    B2N_CHECK_ARG(n % 4 == 0, "parameter count must be a multiple of 4");
+    B2N_CHECK_ARG(step >= 1 || hyper_dev != nullptr, "step is 1-based");
+    if (n == 0) return 0;
+    adam_kernel<<<b2n_grid(b2n_blocks(n / 4, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        (float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, (__half2 *)half_copy, n / 4,
+        lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) cast_half_kernel(const float4 *__restrict__ src, __half2 *__restrict__ dst,
+                                                        int64_t n4, const float *__restrict__ tail_src,
+                                                        __half *__restrict__ tail_dst, int n_tail) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        dst[2 * i] = __floats2half2_rn(v.x, v.y);
+        dst[2 * i + 1] = __floats2half2_rn(v.z, v.w);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n_tail) tail_dst[threadIdx.x] = __float2half_rn(tail_src[threadIdx.x]);
+}
+
+extern "C" int b2n_cast_half(const float *src, b2n_half *dst, int64_t n, void *stream) {
+    if (n <= 0) return 0;
+    B2N_CHECK_ARG(((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 3) == 0, "misaligned buffers");
+    const int64_t n4 = n / 4;
+    cast_half_kernel<<<b2n_grid(b2n_blocks(n4 > 0 ? n4 : 1, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        (const float4 *)src, (__half2 *)dst, n4, src + 4 * n4, (__half *)dst + 4 * n4, (int)(n - 4 * n4));
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ grid
+__global__ void __launch_bounds__(256) cell_positions_kernel(const int32_t *__restrict__ coords,
+                                                             const float *__restrict__ noise, int64_t n,
+                                                             float gm1_inv2, float span, float half, float xyz_min,
+                                                             float inv_extent, int unit_cube,
+                                                             float *__restrict__ xyz) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < 3 * n; e += (int64_t)gridDim.x * blockDim.x) {
+        // (coords/(G-1)*2-1)*(s-s/G) + (noise*2-1)*s/G      (networks.py:227-231)
+        float v = ((float)__ldg(coords + e) * gm1_inv2 - 1.0f) * span + (__ldg(noise + e) * 2.0f - 1.0f) * half;
+        if (unit_cube) v = (v - xyz_min) * inv_extent;     // networks.py:96
+        xyz[e] = v;
+    }
+}
+
+extern "C" int b2n_grid_cell_positions(const int32_t *coords, const float *noise, int64_t n, int grid_size, float s,
+                                       float xyz_min, float xyz_max, int unit_cube, float *xyz, void *stream) {
+    B2N_CHECK_ARG(grid_size >= 2, "grid_size < 2");
+    if (n <= 0) return 0;
+    const float half = s / grid_size;
+    cell_positions_kernel<<<b2n_grid(b2n_blocks(3 * n, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        coords, noise, n, 2.0f / (grid_size - 1), s - half, half, xyz_min, 1.0f / (xyz_max - xyz_min), unit_cube, xyz);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const int64_t *__restrict__ indices,
+                                                           const float *__restrict__ sigmas, int64_t n,
+                                                           float *__restrict__ tmp) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        tmp[indices[i]] = sigmas[i];
+}
+extern "C" int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, void *stream) {
+    if (n <= 0) return 0;
+    grid_scatter_kernel<<<b2n_grid(b2n_blocks(n, 256), 8), 256, 0, (cudaStream_t)stream>>>(indices, sigmas, n, tmp);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) grid_ema_kernel(float *__restrict__ grid, const float *__restrict__ tmp,
+                                                       int64_t n, float decay) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = grid[i];
+        grid[i] = (g < 0.0f) ? g : fmaxf(g * decay, tmp[i]);   // networks.py:234-237
+    }
+}
+extern "C" int b2n_grid_ema(float *density_grid, const float *tmp, int64_t n_cells, float decay, void *stream) {
+    if (n_cells <= 0) return 0;
+    grid_ema_kernel<<<b2n_grid(b2n_blocks(n_cells, 256), 8), 256, 0, (cudaStream_t)stream>>>(density_grid, tmp, n_cells, decay);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// mean over grid > 0 (networks.py:249) kept on the device: block partial sums in double, one atomic per
+// CTA, and the last CTA to finish publishes min(mean, threshold).
+__global__ void __launch_bounds__(256) grid_threshold_kernel(const float *__restrict__ grid, int64_t n,
+                                                             float density_threshold, double *ws,
+                                                             unsigned int *ticket, float *stats) {
+    double sum = 0.0, cnt = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float g = __ldg(grid + i);
+        if (g > 0.0f) { sum += g; cnt += 1.0; }
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum += __shfl_xor_sync(FULL, sum, o);
+        cnt += __shfl_xor_sync(FULL, cnt, o);
+    }
+    __shared__ double ss[8], sc[8];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) { ss[wid] = sum; sc[wid] = cnt; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0, c = 0;
+        for (int k = 0; k < 8; ++k) { s += ss[k]; c += sc[k]; }
+        atomicAdd(ws, s);
+        atomicAdd(ws + 1, c);
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        const double s = atomicAdd(ws, 0.0), c = atomicAdd(ws + 1, 0.0);
+        const float mean = (float)(s / c);          // NaN when no cell is positive, like torch's empty mean
+        stats[0] = fminf(mean, density_threshold);  // python min(nan, thr) would keep nan; fminf keeps thr
+        stats[1] = mean;
+        stats[2] = (float)c;
+    }
+}
+
+__global__ void grid_threshold_init_kernel(double *ws) {
+    ws[0] = 0.0; ws[1] = 0.0;
+    reinterpret_cast<unsigned int *>(ws + 2)[0] = 0u;
+}
+
+extern "C" int b2n_grid_threshold(const float *density_grid, int64_t n_cells, float density_threshold,
+                                  double *workspace, float *stats_dev, void *stream) {
+    B2N_CHECK_ARG(n_cells > 0 && workspace && stats_dev, "bad arguments (workspace = 3 doubles)");
+    cudaStream_t st = (cudaStream_t)stream;
+    grid_threshold_init_kernel<<<1, 1, 0, st>>>(workspace);
+    grid_threshold_kernel<<<b2n_grid(b2n_blocks(n_cells, 256), 4), 256, 0, st>>>(
+        density_grid, n_cells, density_threshold, workspace, reinterpret_cast<unsigned int *>(workspace + 2), stats_dev);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+__global__ void __launch_bounds__(256) nerf_loss_kernel(const float *__restrict__ rgb, const float *__restrict__ opacity,
+                                                        const float *__restrict__ target, int64_t n, float bg,
+                                                        float lambda_opa, float loss_scale, float *__restrict__ rgb_out,
+                                                        float *loss, float *__restrict__ d_rgb,
+                                                        float *__restrict__ d_opacity) {
+    float part = 0.f;
+    const float inv3n = 1.0f / (3.0f * (float)n), invn = 1.0f / (float)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float op = opacity[i];
+        float dsum = 0.f;
+        #pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = rgb[3 * i + c] + bg * (1.0f - op);      // rendering.py:163-164
+            const float e = v - target[3 * i + c];
+            if (rgb_out) rgb_out[3 * i + c] = v;
+            part += e * e * inv3n;                                   // losses.py:34 + .mean()
+            const float gr = 2.0f * e * inv3n * loss_scale;
+            d_rgb[3 * i + c] = gr;
+            dsum += gr;
+        }
+        const float o = op + 1e-10f;                                 // losses.py:36-38
+        part += lambda_opa * (-o * logf(o)) * invn;
+        d_opacity[i] = -bg * dsum + lambda_opa * (-(logf(o) + 1.0f)) * invn * loss_scale;
+    }
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+    __shared__ float sp[8];
+    if ((threadIdx.x & 31) == 0) sp[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += sp[k];
+        atomicAdd(loss, s);
+    }
+}
+
+extern "C" int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const float *target, int64_t n_rays,
+                                  float bg, float lambda_opa, float loss_scale, float *rgb_out, float *loss_dev,
+                                  float *dL_drgb, float *dL_dopacity, void *stream) {
+    if (n_rays <= 0) return 0;
+    nerf_loss_kernel<<<b2n_grid(b2n_blocks(n_rays, 256), 2), 256, 0, (cudaStream_t)stream>>>(
+        rgb, opacity, target, n_rays, bg, lambda_opa, loss_scale, rgb_out, loss_dev, dL_drgb, dL_dopacity);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

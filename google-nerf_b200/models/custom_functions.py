@@ -1,0 +1,100 @@
+"""Autograd wrappers with the names, argument order and return arity of
+ngp_pl/models/custom_functions.py (RayAABBIntersector :8-29, RaySphereIntersector :32-52, RayMarcher :55-113,
+VolumeRenderer :116-159, TruncExp :162-173), bound to libb2n through the `vren` drop-in."""
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from .. import vren
+
+_fwd32 = custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+_bwd = custom_bwd(device_type="cuda")
+
+
+class RayAABBIntersector(torch.autograd.Function):
+    """rays_o, rays_d (N_rays,3); centers, half_sizes (N_voxels,3); max_hits ->
+    hits_cnt (N_rays), hits_t (N_rays,max_hits,2) near-to-far (-1 = no hit), hits_voxel_idx (N_rays,max_hits)."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, center, half_size, max_hits):
+        return vren.ray_aabb_intersect(rays_o, rays_d, center, half_size, max_hits)
+
+
+class RaySphereIntersector(torch.autograd.Function):
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, center, radii, max_hits):
+        return vren.ray_sphere_intersect(rays_o, rays_d, center, radii, max_hits)
+
+
+class RayMarcher(torch.autograd.Function):
+    """-> rays_a (N_rays,3) [ray_idx, start_idx, N_samples], xyzs, dirs (N,3), deltas, ts (N), total_samples.
+
+    ``RayMarcher.noise`` may be set to a (N_rays) tensor to fix the per-ray jitter (parity tests share it with
+    the oracle); otherwise it is drawn with torch.rand_like as at custom_functions.py:84."""
+    noise = None
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, grid_size,
+                max_samples):
+        noise = RayMarcher.noise if RayMarcher.noise is not None else torch.rand_like(rays_o[:, 0])
+        rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(
+            rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples)
+        total_samples = counter[0]
+        ctx.save_for_backward(rays_a, ts)
+        return rays_a, xyzs, dirs, deltas, ts, total_samples
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dL_drays_a, dL_dxyzs, dL_ddirs, dL_ddeltas, dL_dts, dL_dtotal_samples):
+        # per-ray segmented sums (the reference uses torch_scatter.segment_csr, custom_functions.py:108-111);
+        # the deterministic packing makes the segments contiguous and ordered, so index_add suffices
+        rays_a, ts = ctx.saved_tensors
+        n_rays = rays_a.shape[0]
+        seg = torch.repeat_interleave(torch.arange(n_rays, device=ts.device), rays_a[:, 2])
+        zero = lambda: torch.zeros(n_rays, 3, dtype=dL_dxyzs.dtype, device=ts.device)
+        dL_drays_o = zero().index_add_(0, seg, dL_dxyzs)
+        g_d = dL_dxyzs * ts[:, None]
+        if dL_ddirs is not None:
+            g_d = g_d + dL_ddirs
+        dL_drays_d = zero().index_add_(0, seg, g_d)
+        return dL_drays_o, dL_drays_d, None, None, None, None, None, None, None
+
+
+class VolumeRenderer(torch.autograd.Function):
+    """sigmas (N), rgbs (N,3), deltas, ts (N), rays_a (N_rays,3), T_threshold ->
+    opacity, depth, depth_sq (N_rays), rgb (N_rays,3)."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, sigmas, rgbs, deltas, ts, rays_a, T_threshold):
+        opacity, depth, depth_sq, rgb = vren.composite_train_fw(sigmas, rgbs, deltas, ts, rays_a, T_threshold)
+        ctx.save_for_backward(sigmas, rgbs, deltas, ts, rays_a, opacity, depth, depth_sq, rgb)
+        ctx.T_threshold = T_threshold
+        return opacity, depth, depth_sq, rgb
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb):
+        sigmas, rgbs, deltas, ts, rays_a, opacity, depth, depth_sq, rgb = ctx.saved_tensors
+        dL_dsigmas, dL_drgbs = vren.composite_train_bw(
+            dL_dopacity.contiguous(), dL_ddepth.contiguous(), dL_ddepth_sq.contiguous(), dL_drgb.contiguous(),
+            sigmas, rgbs, deltas, ts, rays_a, opacity, depth, depth_sq, rgb, ctx.T_threshold)
+        return dL_dsigmas, dL_drgbs, None, None, None, None
+
+
+class TruncExp(torch.autograd.Function):
+    """exp forward; backward uses exp(clamp(x, -15, 15))  (custom_functions.py:162-173)."""
+
+    @staticmethod
+    @_fwd32
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, dL_dout):
+        x = ctx.saved_tensors[0]
+        return dL_dout * torch.exp(x.clamp(-15, 15))

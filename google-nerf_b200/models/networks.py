@@ -1,0 +1,168 @@
+"""NGP: the field + occupancy-grid state holder with the attribute names, method signatures and
+checkpoint keys of ngp_pl/models/networks.py:12-252.
+
+state_dict keys: center, xyz_min, xyz_max, half_size (1,3); density_bitfield
+(cascades*G^3/8) uint8; xyz_encoder.params, dir_encoder.params (0 elements), rgb_net.params (flat fp32);
+`density_grid` (cascades, G^3) and `grid_coords` (G^3, 3) int32 are registered by the training system
+(ngp_pl/train.py:73-77) -- or by ``init_grid_buffers()`` here -- and are dropped by utils.slim_ckpt.
+
+Extra keyword arguments (reference constants as defaults):
+  encoding: "Frequency" is what this fork's NGP builds (networks.py:49-53); "HashGrid" is the Instant-NGP
+            configuration left commented at networks.py:39-47 and the one north_star names.
+  log2_T, grid_size: networks.py:25,30.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .. import tinycudann as tcnn
+from .. import vren
+from .custom_functions import TruncExp
+from .rendering import NEAR_DISTANCE
+
+
+class NGP(nn.Module):
+    def __init__(self, scale, num_levels=16, encoding="HashGrid", log2_T=19, grid_size=128):
+        super().__init__()
+        self.scale = scale
+        self.register_buffer("center", torch.zeros(1, 3))
+        self.register_buffer("xyz_min", -torch.ones(1, 3) * scale)
+        self.register_buffer("xyz_max", torch.ones(1, 3) * scale)
+        self.register_buffer("half_size", (self.xyz_max - self.xyz_min) / 2)
+
+        # cascade k of the occupancy grid covers [-2^(k-1), 2^(k-1)]^3 (clipped to the scene box)
+        self.cascades = max(1 + int(np.ceil(np.log2(2 * scale))), 1)
+        self.grid_size = grid_size
+        self.register_buffer("density_bitfield", torch.zeros(self.cascades * grid_size ** 3 // 8, dtype=torch.uint8))
+
+        L_, F_, N_min = num_levels, 2, 16
+        b = np.exp(np.log(2048 * scale / N_min) / (L_ - 1))
+        self.encoding = encoding
+        if encoding == "HashGrid":
+            enc_cfg = {"otype": "HashGrid", "n_levels": L_, "n_features_per_level": F_,
+                       "log2_hashmap_size": log2_T, "base_resolution": N_min, "per_level_scale": b}
+        elif encoding == "Frequency":
+            enc_cfg = {"otype": "Frequency", "n_frequencies": 12}
+        else:
+            raise ValueError(f"unknown encoding {encoding!r}")
+        self.xyz_encoder = tcnn.NetworkWithInputEncoding(
+            n_input_dims=3, n_output_dims=16, encoding_config=enc_cfg,
+            network_config={"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                            "n_neurons": 64, "n_hidden_layers": 1})
+        self.dir_encoder = tcnn.Encoding(n_input_dims=3, encoding_config={"otype": "SphericalHarmonics", "degree": 4})
+        self.rgb_net = tcnn.Network(
+            n_input_dims=32, n_output_dims=3,
+            network_config={"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid",
+                            "n_neurons": 64, "n_hidden_layers": 2})
+        self.sigma_act = TruncExp.apply
+
+    # ------------------------------------------------------------------ field
+    def density(self, x, return_feat=False):
+        """x (N,3) in [-scale, scale] -> sigmas (N) fp32 [, h (N,16) fp16]."""
+        x = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
+        h = self.xyz_encoder(x)
+        sigmas = self.sigma_act(h[:, 0]).float()
+        if return_feat:
+            return sigmas, h
+        return sigmas
+
+    def forward(self, x, d):
+        """x (N,3) positions, d (N,3) directions (normalised IN PLACE like the reference, networks.py:113)
+        -> sigmas (N) fp32, rgbs (N,3) fp16."""
+        sigmas, h = self.density(x, return_feat=True)
+        d /= torch.norm(d, dim=-1, keepdim=True)
+        d = self.dir_encoder((d + 1) / 2)
+        rgbs = self.rgb_net(torch.cat([d, h], 1))
+        return sigmas, rgbs
+
+    # ------------------------------------------------------------------ occupancy grid
+    def init_grid_buffers(self):
+        """What ngp_pl/train.py:73-77 does from outside: density_grid zeros and the (G^3,3) cell coordinates."""
+        G, dev = self.grid_size, self.center.device
+        if not hasattr(self, "density_grid"):
+            self.register_buffer("density_grid", torch.zeros(self.cascades, G ** 3, device=dev))
+        if not hasattr(self, "grid_coords"):
+            r = torch.arange(G, dtype=torch.int32, device=dev)
+            z, y, x = torch.meshgrid(r, r, r, indexing="ij")
+            self.register_buffer("grid_coords", torch.stack([x, y, z], -1).reshape(-1, 3).contiguous())
+        return self
+
+    @torch.no_grad()
+    def get_all_cells(self):
+        """[(morton indices (G^3) i64, coords (G^3,3) i32)] * cascades."""
+        indices = vren.morton3D(self.grid_coords).long()
+        return [(indices, self.grid_coords)] * self.cascades
+
+    @torch.no_grad()
+    def sample_uniform_and_occupied_cells(self, M):
+        """Per cascade: M uniformly random cells and M cells drawn from the currently occupied ones."""
+        cells = []
+        dev = self.density_grid.device
+        for c in range(self.cascades):
+            coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=dev)
+            indices1 = vren.morton3D(coords1).long()
+            indices2 = torch.nonzero(self.density_grid[c] > 0)[:, 0]
+            pick = torch.randint(len(indices2), (M,), device=dev)
+            indices2 = indices2[pick]
+            coords2 = vren.morton3D_invert(indices2.int())
+            cells.append((torch.cat([indices1, indices2]), torch.cat([coords1, coords2])))
+        return cells
+
+    @torch.no_grad()
+    def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
+        """Cells no training camera sees (or that sit closer than NEAR_DISTANCE to one) get density -1 and are
+        never updated (networks.py:159-214).  One-time torch ops."""
+        w2c_R = poses[:, :3, :3].transpose(1, 2)                       # (N,3,3)
+        w2c_T = -torch.bmm(w2c_R, poses[:, :3, 3:])                    # (N,3,1)
+        cells = self.get_all_cells()
+        G = self.grid_size
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            half_grid_size = s / G
+            for i in range(0, len(indices), chunk):
+                xyzs = coords[i:i + chunk] / (G - 1) * 2 - 1
+                xyzs_w = (xyzs * (s - half_grid_size)).T               # (3,chunk)
+                xyzs_c = w2c_R @ xyzs_w[None] + w2c_T                  # (N,3,chunk)
+                uvd = K @ xyzs_c
+                uv = uvd[:, :2] / uvd[:, 2:]
+                in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & \
+                           (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
+                covered = ((uvd[:, 2] >= NEAR_DISTANCE) & in_image).any(0)
+                too_near = ((uvd[:, 2] < NEAR_DISTANCE) & in_image).any(0)
+                valid = covered & ~too_near
+                self.density_grid[c, indices[i:i + chunk]] = torch.where(valid, 0., -1.)
+
+    @torch.no_grad()
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+        """EMA-max update of the cascaded density grid from fresh field samples, then re-pack the bitfield
+        (networks.py:216-252).  The mean/threshold stays on the device (no .item() sync)."""
+        G = self.grid_size
+        tmp = torch.zeros_like(self.density_grid)
+        cells = self.get_all_cells() if warmup else self.sample_uniform_and_occupied_cells(G ** 3 // 4)
+        lo, hi = -float(self.scale), float(self.scale)
+        for c in range(self.cascades):
+            indices, coords = cells[c]
+            s = min(2 ** (c - 1), self.scale)
+            noise = torch.rand(coords.shape[0], 3, device=coords.device)
+            xyz01 = torch.empty(coords.shape[0], 3, device=coords.device)
+            L.call("b2n_grid_cell_positions", L.ptr(coords.contiguous()), L.ptr(noise), coords.shape[0], G, float(s),
+                   lo, hi, 1, L.ptr(xyz01))
+            h = self.xyz_encoder(xyz01)
+            sigmas = torch.exp(h[:, 0].float())
+            L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]))
+        if not self.density_grid.is_contiguous():
+            self.density_grid = self.density_grid.contiguous()
+        L.call("b2n_grid_ema", L.ptr(self.density_grid), L.ptr(tmp), self.density_grid.numel(), float(decay))
+        if erode:
+            grid = self.density_grid.view(self.cascades, G, G, G)
+            maxpool = torch.nn.functional.max_pool3d(grid, kernel_size=3, stride=1, padding=1)
+            local_max = (grid == maxpool) & (maxpool > 0)
+            self.density_grid[local_max.view(self.cascades, -1)] *= decay
+        ws = torch.empty(3, dtype=torch.float64, device=tmp.device)
+        stats = torch.empty(3, dtype=torch.float32, device=tmp.device)
+        L.call("b2n_grid_threshold", L.ptr(self.density_grid), self.density_grid.numel(), float(density_threshold),
+               L.ptr(ws), L.ptr(stats))
+        vren.packbits(self.density_grid, float(density_threshold), self.density_bitfield, threshold_dev=stats)
+        self._grid_stats = stats                                        # [threshold used, mean, #positive]

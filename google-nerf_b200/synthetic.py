@@ -1,0 +1,137 @@
+"""Synthetic NeRF-synthetic- / ScanNet-shaped workloads (datasets are unavailable offline).
+
+Shapes follow the reference datasets: ``directions (H*W,3)`` un-normalised ``((u-cx+.5)/fx, (v-cy+.5)/fy, 1)``
+(ngp_pl/datasets/ray_utils.py:33-35), ``poses (N,3,4)`` camera-to-world with positions divided by
+``2*scale`` (ngp_pl/datasets/nsvf.py:86-87), batches ``{img_idxs, pix_idxs, rgb}`` (ngp_pl/datasets/base.py:24-40).
+The scene is an analytic union of three spheres and a box so that ground-truth colours and the
+occupancy grid are both closed-form.
+"""
+import math
+
+import numpy as np
+import torch
+
+# primitives in units of `scale` (so the same scene fits any bounding box)
+_SPHERES = [((0.00, 0.05, -0.10), 0.42, (0.85, 0.25, 0.20)),
+            ((0.45, -0.30, 0.25), 0.24, (0.20, 0.65, 0.30)),
+            ((-0.40, 0.35, 0.30), 0.20, (0.25, 0.35, 0.85))]
+_BOX = ((0.0, 0.0, -0.62), (0.75, 0.75, 0.08), (0.80, 0.75, 0.55))   # centre, half size, albedo
+
+
+def inside(xyz, scale):
+    """(N,3) world positions -> bool occupancy of the analytic scene."""
+    p = xyz / scale
+    occ = torch.zeros(p.shape[0], dtype=torch.bool, device=p.device)
+    for c, r, _ in _SPHERES:
+        occ |= ((p - torch.tensor(c, device=p.device)) ** 2).sum(-1) <= r * r
+    c, h, _ = _BOX
+    occ |= ((p - torch.tensor(c, device=p.device)).abs() <= torch.tensor(h, device=p.device)).all(-1)
+    return occ
+
+
+def _morton(coords):
+    def expand(v):
+        v = (v * 0x00010001) & 0xFF0000FF
+        v = (v * 0x00000101) & 0x0F00F00F
+        v = (v * 0x00000011) & 0xC30C30C3
+        v = (v * 0x00000005) & 0x49249249
+        return v
+    c = coords.to(torch.int64)
+    return expand(c[:, 0]) | (expand(c[:, 1]) << 1) | (expand(c[:, 2]) << 2)
+
+
+def grid_coords(G, device="cpu"):
+    """(G^3,3) int32 cell coordinates, same content as kornia.create_meshgrid3d(G,G,G,False).reshape(-1,3)
+    as registered at ngp_pl/train.py:76-77 (x fastest)."""
+    r = torch.arange(G, dtype=torch.int32, device=device)
+    z, y, x = torch.meshgrid(r, r, r, indexing="ij")
+    return torch.stack([x, y, z], -1).reshape(-1, 3)
+
+
+def density_grid(scale, cascades, G=128, occupied_value=10.0, coarse=None, device="cpu"):
+    """(cascades, G^3) fp32 grid in Morton order; cell centres as in ngp_pl/models/networks.py:227-229.
+    ``coarse=64`` rasterises at 64^3 and replicates 2x per axis."""
+    coords = grid_coords(G, device)
+    idx = _morton(coords)
+    out = torch.zeros(cascades, G ** 3, device=device)
+    for c in range(cascades):
+        s = min(2 ** (c - 1), scale)
+        cc = coords if coarse is None else (coords // (G // coarse)) * (G // coarse) + (G // coarse - 1) / 2
+        xyz = (cc.float() / (G - 1) * 2 - 1) * (s - s / G)
+        out[c, idx] = inside(xyz, scale).float() * occupied_value
+    return out
+
+
+def bitfield_from_grid(grid, thr=0.0):
+    bits = (grid.reshape(-1, 8) > thr).to(torch.uint8)
+    w = (2 ** torch.arange(8, device=grid.device)).to(torch.uint8)
+    return (bits * w).sum(1).to(torch.uint8)
+
+
+def intrinsics(W, H, fx=None):
+    fx = 1111.1 * (W / 800.0) if fx is None else fx
+    K = torch.tensor([[fx, 0, W / 2], [0, fx, H / 2], [0, 0, 1]], dtype=torch.float32)
+    return K
+
+
+def directions(W, H, K):
+    v, u = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    d = torch.stack([(u - K[0, 2] + 0.5) / K[0, 0], (v - K[1, 2] + 0.5) / K[1, 1], torch.ones_like(u)], -1)
+    return d.reshape(-1, 3)
+
+
+def hemisphere_poses(n, radius=4.0, dataset_scale=1.15, seed=0):
+    """(n,3,4) c2w poses looking at the origin from the upper hemisphere ([right down front] camera frame).
+    Positions are divided by 2*dataset_scale like ngp_pl/datasets/nsvf.py:86-87, which puts a radius-4 Lego rig
+    at ~1.74 from the centre of a scene bounded by [-0.5,0.5]^3."""
+    g = torch.Generator().manual_seed(seed)
+    phi = torch.rand(n, generator=g) * 2 * math.pi
+    theta = torch.rand(n, generator=g) * (0.45 * math.pi) + 0.05 * math.pi   # elevation above the horizon
+    pos = radius * torch.stack([torch.cos(theta) * torch.cos(phi), torch.cos(theta) * torch.sin(phi), torch.sin(theta)], -1)
+    fwd = -pos / pos.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd)
+    right = torch.cross(fwd, up, dim=-1); right = right / right.norm(dim=-1, keepdim=True)
+    down = torch.cross(fwd, right, dim=-1)
+    return torch.stack([right, down, fwd, pos / (2 * dataset_scale)], -1).contiguous()   # (n,3,4)
+
+
+def get_rays(dirs_cam, c2w):
+    """ngp_pl/datasets/ray_utils.py:152-175 as plain torch (the per-step bmm)."""
+    if c2w.ndim == 2:
+        rays_d = dirs_cam @ c2w[:, :3].T
+    else:
+        rays_d = torch.bmm(dirs_cam[:, None], c2w[..., :3].transpose(1, 2))[:, 0]
+    rays_o = c2w[..., 3].expand_as(rays_d)
+    return rays_o.contiguous(), rays_d.contiguous()
+
+
+def shade(rays_o, rays_d, scale, bg=1.0):
+    """Closed-form ground-truth colour of the analytic scene (nearest primitive, Lambert + ambient)."""
+    dev = rays_o.device
+    o = rays_o / scale; d = rays_d / scale                           # primitives are in units of scale
+    N = o.shape[0]
+    best_t = torch.full((N,), float("inf"), device=dev)
+    colour = torch.full((N, 3), bg, device=dev)
+    light = torch.tensor([0.4, 0.3, 0.85], device=dev); light = light / light.norm()
+    a = (d * d).sum(-1)
+    for c, r, alb in _SPHERES:
+        oc = o - torch.tensor(c, device=dev)
+        hb = (oc * d).sum(-1); cc = (oc * oc).sum(-1) - r * r
+        disc = hb * hb - a * cc
+        t = (-hb - disc.clamp(min=0).sqrt()) / a
+        hit = (disc >= 0) & (t > 0) & (t < best_t)
+        n = (oc + t[:, None] * d) / r
+        lam = (n * light).sum(-1).clamp(min=0) * 0.7 + 0.3
+        colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
+        best_t = torch.where(hit, t, best_t)
+    c, h, alb = _BOX
+    c = torch.tensor(c, device=dev); h = torch.tensor(h, device=dev)
+    inv = 1.0 / d
+    lo, hi = (c - h - o) * inv, (c + h - o) * inv
+    tmin, tmax = torch.minimum(lo, hi), torch.maximum(lo, hi)
+    t1, axis = tmin.max(-1); t2 = tmax.min(-1)[0]
+    hit = (t1 <= t2) & (t1 > 0) & (t1 < best_t)
+    n = torch.zeros(N, 3, device=dev); n.scatter_(1, axis[:, None], -torch.sign(d.gather(1, axis[:, None])))
+    lam = (n * light).sum(-1).clamp(min=0) * 0.7 + 0.3
+    colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
+    return colour

@@ -1,0 +1,189 @@
+/*
+ * b2n.h -- C ABI of libb2n.so, the B200 (sm_100a) implementation of the Instant-NGP hot path that
+ * mikacuy/google-nerf's ngp_pl runs through its `vren` extension and tiny-cuda-nn.
+ *
+ * Boundary rules:
+ *   - plain pointers and sizes only; every pointer is a CUDA device pointer unless marked HOST;
+ *   - the caller allocates every output; the library owns no persistent memory;
+ *   - every entry point takes the CUDA stream to launch on (`void*` = cudaStream_t) and is asynchronous;
+ *   - return value 0 = ok, non-zero = error (message via b2n_last_error(), thread-local); never exits;
+ *   - tensors are contiguous, row-major, shapes written as (rows, cols).
+ *
+ * Each declaration cites the reference interface it replaces (paths under /root/reference/ngp_pl).
+ */
+#ifndef B2N_H
+#define B2N_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2N_VERSION 100
+#if defined(__GNUC__)
+#define B2N_API __attribute__((visibility("default")))
+#else
+#define B2N_API
+#endif
+typedef uint16_t b2n_half; /* IEEE binary16 bit pattern */
+
+B2N_API int b2n_version(void);
+B2N_API const char *b2n_last_error(void);
+
+/* ---------------------------------------------------------------- vren: intersection ----------------- */
+/* vren.ray_aabb_intersect  (models/custom_functions.py:29; used by models/rendering.py:27-28).
+ * hits_cnt (n_rays) i32, hits_t (n_rays,max_hits,2) f32 (-1 = miss), hits_voxel_idx (n_rays,max_hits) i64. */
+B2N_API int b2n_ray_aabb_intersect(const float *rays_o, const float *rays_d, const float *centers,
+                           const float *half_sizes, int64_t n_rays, int64_t n_voxels, int max_hits,
+                           int32_t *hits_cnt, float *hits_t, int64_t *hits_voxel_idx, void *stream);
+/* vren.ray_sphere_intersect  (models/custom_functions.py:52).  radii (n_spheres). */
+B2N_API int b2n_ray_sphere_intersect(const float *rays_o, const float *rays_d, const float *centers,
+                             const float *radii, int64_t n_rays, int64_t n_spheres, int max_hits,
+                             int32_t *hits_cnt, float *hits_t, int64_t *hits_sphere_idx, void *stream);
+/* rendering.py:29 -- hits_t[(t1>=0)&(t1<near)] = near, in place on hits_t (n_rays,1,2). */
+B2N_API int b2n_clamp_near(float *hits_t, int64_t n_rays, float near_distance, void *stream);
+
+/* ---------------------------------------------------------------- vren: Morton / bitfield ------------ */
+/* vren.morton3D (models/networks.py:128,147): coords (n,3) i32 -> indices (n) i32. */
+B2N_API int b2n_morton3D(const int32_t *coords, int64_t n, int32_t *indices, void *stream);
+/* vren.morton3D_invert (models/networks.py:153): indices (n) i32 -> coords (n,3) i32. */
+B2N_API int b2n_morton3D_invert(const int32_t *indices, int64_t n, int32_t *coords, void *stream);
+/* vren.packbits (models/networks.py:251-252): bit i of byte n = grid[8n+i] > threshold.
+ * threshold_dev, if non-NULL, is a device float that overrides `threshold` (min(mean, thr) computed on
+ * the device by b2n_density_grid_update, removing the .item() sync at networks.py:249). */
+B2N_API int b2n_packbits(const float *density_grid, int64_t n_bytes, float threshold, const float *threshold_dev,
+                 uint8_t *density_bitfield, void *stream);
+
+/* ---------------------------------------------------------------- vren: ray marching ----------------- */
+/* vren.raymarching_train (models/custom_functions.py:86-90), split in two so that the caller can size the
+ * sample buffers: _count fills rays_a (n_rays,3) i64 = [ray_idx, start_idx, N] with start_idx the exclusive
+ * prefix sum of N in ray order, and counter (4) i32 = [total, n_rays, overflow, unclamped_total]; _write
+ * re-marches and writes xyzs, dirs (total,3), deltas, ts (total).
+ * capacity >= 0 clamps: rays whose samples would pass `capacity` rows are truncated (N reduced) and
+ * counter[2] is set; capacity < 0 = unbounded.  hits_t (n_rays,2); noise (n_rays) in [0,1). */
+B2N_API int b2n_raymarching_train_count(const float *rays_o, const float *rays_d, const float *hits_t,
+                                const uint8_t *density_bitfield, int cascades, float scale,
+                                float exp_step_factor, const float *noise, int grid_size,
+                                int max_samples, int64_t n_rays, int64_t capacity, int64_t *rays_a,
+                                int32_t *counter, void *stream);
+B2N_API int b2n_raymarching_train_write(const float *rays_o, const float *rays_d, const float *hits_t,
+                                const uint8_t *density_bitfield, int cascades, float scale,
+                                float exp_step_factor, const float *noise, int grid_size,
+                                int max_samples, int64_t n_rays, const int64_t *rays_a, float *xyzs,
+                                float *dirs, float *deltas, float *ts, void *stream);
+/* vren.raymarching_test (models/rendering.py:79-83).  hits_t (n_rays,2) is advanced IN PLACE;
+ * outputs (n_alive,n_samples[,3]) are fully written (unused slots zero); n_eff (n_alive) i32. */
+B2N_API int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,
+                         const int64_t *alive_indices, const uint8_t *density_bitfield, int cascades,
+                         float scale, float exp_step_factor, int grid_size, int max_samples,
+                         int n_samples, int64_t n_alive, float *xyzs, float *dirs, float *deltas,
+                         float *ts, int32_t *n_eff, void *stream);
+
+/* ---------------------------------------------------------------- vren: compositing ------------------ */
+/* vren.composite_train_fw (models/custom_functions.py:140-142).  n_total_dev (device i32, may be NULL)
+ * is unused by the math; rays_a drives everything.  Outputs indexed by rays_a[:,0]. */
+B2N_API int b2n_composite_train_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                           const int64_t *rays_a, float T_threshold, int64_t n_rays, float *opacity,
+                           float *depth, float *depth_sq, float *rgb, void *stream);
+/* vren.composite_train_bw (models/custom_functions.py:153-158).  Writes every sample owned by a ray
+ * (zeros after an early stop), so dL_dsigmas/dL_drgbs need no pre-zeroing. */
+B2N_API int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_ddepth, const float *dL_ddepth_sq,
+                           const float *dL_drgb, const float *sigmas, const float *rgbs,
+                           const float *deltas, const float *ts, const int64_t *rays_a,
+                           const float *opacity, const float *depth, const float *depth_sq,
+                           const float *rgb, float T_threshold, int64_t n_rays, float *dL_dsigmas,
+                           float *dL_drgbs, void *stream);
+/* vren.composite_test_fw (models/rendering.py:97-100).  In place on alive_indices/opacity/depth/rgb. */
+B2N_API int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                          const float *hits_t, int64_t *alive_indices, float T_threshold,
+                          const int32_t *n_eff, int n_samples, int64_t n_alive, float *opacity,
+                          float *depth, float *rgb, void *stream);
+
+/* ---------------------------------------------------------------- tiny-cuda-nn: encodings ------------ */
+#define B2N_MAX_LEVELS 32
+typedef struct {
+    int32_t n_levels, n_features;        /* n_features must be 2 */
+    float scale[B2N_MAX_LEVELS];         /* pos = fma(scale, x, 0.5) */
+    uint32_t resolution[B2N_MAX_LEVELS];
+    uint32_t size[B2N_MAX_LEVELS];       /* entries in the level (hashed iff res^3 does not fit) */
+    uint32_t offset[B2N_MAX_LEVELS + 1]; /* entry offsets into the flat table */
+} b2n_grid_layout;                       /* HOST struct, passed by pointer, copied at launch */
+
+/* GridEncoding sizing of tcnn's "HashGrid" config (models/networks.py:39-47).  Fills *layout (HOST);
+ * returns 0.  n_params = layout->offset[n_levels] * n_features. */
+B2N_API int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
+                        double per_level_scale, b2n_grid_layout *layout);
+/* HashGrid forward: x (n,3) f32 in [0,1], table fp16 (entries, 2) -> out (n, out_stride) fp16 columns
+ * [0, 2*n_levels).  n_dev (device i32, may be NULL) overrides n with min(n, *n_dev). */
+B2N_API int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_grid_layout *layout, int64_t n,
+                    const int32_t *n_dev, b2n_half *out, int out_stride, void *stream);
+/* HashGrid backward w.r.t. the table: dL_dout (n, dy_stride) fp16, accumulated (+=) into
+ * grad_table fp32 (entries,2) as  grad += dL_dout * weight * grad_scale. */
+B2N_API int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_stride, const b2n_grid_layout *layout,
+                    int64_t n, const int32_t *n_dev, float grad_scale, float *grad_table, void *stream);
+/* Frequency encoding (models/networks.py:49-53): x (n,3) -> out (n, out_stride) fp16, 3*n_freq*2 columns
+ * then ones up to the next multiple of 16. */
+B2N_API int b2n_frequency_fw(const float *x, int n_frequencies, int64_t n, const int32_t *n_dev, b2n_half *out,
+                     int out_stride, void *stream);
+/* SphericalHarmonics degree 4 (models/networks.py:63-70): d01 (n,3) f32 in [0,1] -> out (n,out_stride)
+ * fp16 columns [0,16).  If normalize != 0 the input is a raw direction d and the kernel computes
+ * d/|d| first (the fused form of networks.py:113-114; (d+1)/2 then *2-1 is folded away exactly). */
+B2N_API int b2n_sh4_fw(const float *d, int normalize, int64_t n, const int32_t *n_dev, b2n_half *out,
+               int out_stride, void *stream);
+
+/* ---------------------------------------------------------------- tiny-cuda-nn: FullyFusedMLP -------- */
+/* FullyFusedMLP, 64 neurons, ReLU, no bias (models/networks.py:54-60,76-82).
+ * weights: fp16, layers concatenated, each row-major (out,in): (64,in_width), (64,64)*(n_hidden-1),
+ * (16,64).  in (n,in_stride) fp16 [in_width columns used, in_width in {16,32,48,64,80}];
+ * hidden (n_hidden, n, 64) fp16 post-ReLU activations saved for backward (may be NULL);
+ * out (n,16) fp16.  output_activation: 0 none, 1 sigmoid. */
+B2N_API int b2n_mlp_fw(const b2n_half *in, int in_stride, int in_width, const b2n_half *weights, int n_hidden,
+               int output_activation, int64_t n, const int32_t *n_dev, b2n_half *hidden, b2n_half *out,
+               void *stream);
+/* Backward.  dL_dout (n,16) fp16 (w.r.t. the activated output), out = forward output (for sigmoid').
+ * dL_din (n,in_stride) fp16 or NULL; grad_weights fp32, same layout as weights, accumulated (+=) as
+ * grad += g * grad_scale. */
+B2N_API int b2n_mlp_bw(const b2n_half *dL_dout, const b2n_half *in, int in_stride, int in_width,
+               const b2n_half *weights, int n_hidden, int output_activation, int64_t n,
+               const int32_t *n_dev, const b2n_half *hidden, const b2n_half *out, float grad_scale,
+               b2n_half *dL_din, float *grad_weights, void *stream);
+
+/* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
+/* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
+ * over one flat fp32 parameter; grad is multiplied by inv_scale, then ZEROED; half_copy (may be NULL)
+ * receives the fp16 copy of the updated parameter.  hyper_dev (may be NULL): device struct
+ * {float lr; int32 step;} that overrides `lr` / `step` (1-based) so that a captured CUDA graph can be
+ * replayed while the schedule advances. */
+B2N_API int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
+                  int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale, int step,
+                  const void *hyper_dev, void *stream);
+/* fp32 -> fp16 parameter copy (what tcnn does before each forward). */
+B2N_API int b2n_cast_half(const float *src, b2n_half *dst, int64_t n, void *stream);
+
+/* NGP.update_density_grid pieces (models/networks.py:225-252).
+ * cells -> world positions: xyz = (coords/(G-1)*2-1)*(s - s/G) + (noise*2-1)*s/G, normalised to [0,1]
+ * with (x - xyz_min)/(xyz_max - xyz_min) when unit_cube != 0 (networks.py:96,227-231). */
+B2N_API int b2n_grid_cell_positions(const int32_t *coords, const float *noise, int64_t n, int grid_size, float s,
+                            float xyz_min, float xyz_max, int unit_cube, float *xyz, void *stream);
+/* grid[idx[i]] update: tmp scatter + EMA-max: grid = grid<0 ? grid : max(grid*decay, tmp)  (:232-237)
+ * done in two launches: scatter (tmp[indices[i]] = sigma[i]) and ema over the whole cascade set. */
+B2N_API int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, void *stream);
+B2N_API int b2n_grid_ema(float *density_grid, const float *tmp, int64_t n_cells, float decay, void *stream);
+/* mean of grid[grid>0] -> stats_dev[0] = min(mean, density_threshold), stats_dev[1] = mean, stats_dev[2]
+ * = count (networks.py:249-251), no host sync.  workspace: 3 doubles (24 B), initialised by the call. */
+B2N_API int b2n_grid_threshold(const float *density_grid, int64_t n_cells, float density_threshold,
+                       double *workspace, float *stats_dev, void *stream);
+
+/* ---------------------------------------------------------------- loss (losses.py:26-40) ------------- */
+/* NeRFLoss + background blend fused: rgb_out = rgb + bg*(1-opacity) (rendering.py:159-164);
+ * loss = mean((rgb_out-target)^2) + lambda_opa*mean(-o log o), o = opacity+1e-10 (train.py:160).
+ * Writes loss_dev[0] += loss (caller zeroes) and the gradients dL_drgb (n,3), dL_dopacity (n) of
+ * loss*loss_scale with respect to the composited rgb / opacity. */
+B2N_API int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const float *target, int64_t n_rays,
+                       float bg, float lambda_opa, float loss_scale, float *rgb_out, float *loss_dev,
+                       float *dL_drgb, float *dL_dopacity, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2N_H */
