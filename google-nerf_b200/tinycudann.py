@@ -176,7 +176,7 @@ class _ModuleFn(torch.autograd.Function):
             ctx.mod = mod
             ctx.save_for_backward(x32)
             return feat
-        need = torch.is_grad_enabled() and (params.requires_grad or x.requires_grad)
+        need = any(ctx.needs_input_grad[:2])      # (grad mode is off inside Function.forward; ask the ctx)
         out, hidden = mlp_fw(feat, p16, mlp.in_width, mlp.n_hidden, mlp.out_act, save_hidden=need)
         ctx.mod = mod
         ctx.x_dtype, ctx.x_cols = x.dtype, x.shape[1]

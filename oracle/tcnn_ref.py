@@ -103,7 +103,7 @@ def frequency_forward(x, n_frequencies=12, out_dtype=torch.float16, pad_to=16):
     output is padded with ones to a multiple of 16 (3*12*2 = 72 -> 80)."""
     N, D = x.shape
     f = torch.arange(n_frequencies, dtype=torch.int32)
-    xs = torch.ldexp(x.to(torch.float32)[:, :, None], f[None, None])            # scalbnf
+    xs = torch.ldexp(x.to(torch.float32)[:, :, None].expand(N, D, n_frequencies), f[None, None].expand(N, D, n_frequencies))  # scalbnf
     phase = torch.tensor([0.0, math.pi / 2], dtype=torch.float32)
     arg = xs[..., None] * torch.tensor(math.pi, dtype=torch.float32) + phase     # (N,D,F,2)
     out = torch.sin(arg).reshape(N, D * n_frequencies * 2)

@@ -224,6 +224,8 @@ def _padded(rays_a, *arrs):
     k = torch.arange(max(maxN, 1))
     mask = k[None] < N[:, None]
     idx = torch.where(mask, start[:, None] + k[None], torch.zeros_like(k[None]))
+    if arrs and arrs[0].shape[0] == 0:                              # no samples at all: gather from one dummy row
+        arrs = [torch.zeros((1,) + tuple(a.shape[1:]), dtype=a.dtype) for a in arrs]
     return mask, idx, [a[idx] for a in arrs]
 
 

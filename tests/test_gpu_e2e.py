@@ -136,8 +136,8 @@ def test_trainer_graph_equals_eager_and_learns(pair):
     from google_nerf_b200.models.networks import NGP
     from google_nerf_b200.trainer import NGPTrainer
     _, _, s = pair
-    n = 1024
-    ro, rd = s["rays_o"][:n].to(DEV).repeat(2, 1)[:n], s["rays_d"][:n].to(DEV).repeat(2, 1)[:n]
+    n = 768
+    ro, rd = s["rays_o"][:n].to(DEV), s["rays_d"][:n].to(DEV)
     tgt = syn.shade(ro, rd, 0.5)
     losses = {}
     for use_graph in (False, True):

@@ -196,7 +196,7 @@ def test_composite_train_fw_bw(mods, scene05, sigma_max, thr):
     # the sigma gradient is a difference of large terms: compare against its own scale
     scale_s = rb[0].abs().max().item() + 1e-12
     assert (gb[0].cpu() - rb[0]).abs().max().item() <= 2e-5 * scale_s
-    torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-6 * rb[1].abs().max().item())
 
 
 def test_composite_uniform_slab_closed_form(mods):
@@ -336,8 +336,9 @@ def test_grid_threshold_and_loss(mods):
     loss.backward()
     out = torch.empty(n, 3, device=DEV); lossd = torch.zeros(1, device=DEV)
     drgb = torch.empty(n, 3, device=DEV); dop = torch.empty(n, device=DEV)
-    L.call("b2n_nerf_loss_fwbw", L.ptr(rgb.detach().to(DEV)), L.ptr(op.detach().to(DEV)), L.ptr(tgt.to(DEV)), n, 1.0,
-           1e-3, 1.0, L.ptr(out), L.ptr(lossd), L.ptr(drgb), L.ptr(dop))
+    rgb_d, op_d, tgt_d = rgb.detach().to(DEV), op.detach().to(DEV), tgt.to(DEV)      # keep the buffers alive
+    L.call("b2n_nerf_loss_fwbw", L.ptr(rgb_d), L.ptr(op_d), L.ptr(tgt_d), n, 1.0, 1e-3, 1.0, L.ptr(out), L.ptr(lossd),
+           L.ptr(drgb), L.ptr(dop))
     assert abs(lossd.item() - loss.item()) < 1e-5 * abs(loss.item())
     torch.testing.assert_close(drgb.cpu(), rgb.grad, rtol=1e-4, atol=1e-9)
     torch.testing.assert_close(dop.cpu(), op.grad, rtol=1e-4, atol=1e-9)
