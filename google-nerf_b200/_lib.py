@@ -17,7 +17,8 @@ class GridLayout(C.Structure):
     """b2n_grid_layout (include/b2n.h)."""
     _fields_ = [("n_levels", C.c_int32), ("n_features", C.c_int32),
                 ("scale", C.c_float * MAX_LEVELS), ("resolution", C.c_uint32 * MAX_LEVELS),
-                ("size", C.c_uint32 * MAX_LEVELS), ("offset", C.c_uint32 * (MAX_LEVELS + 1))]
+                ("size", C.c_uint32 * MAX_LEVELS), ("offset", C.c_uint32 * (MAX_LEVELS + 1)),
+                ("x_offset", C.c_float), ("x_scale", C.c_float)]
 
     @property
     def n_entries(self):
@@ -49,6 +50,9 @@ _SIGS = {
     "b2n_sh4_fw": [_P, _I, _L, _P, _P, _I, _P],
     "b2n_mlp_fw": [_P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _P],
     "b2n_mlp_bw": [_P, _P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _F, _P, _P, _P],
+    "b2n_field_pack_weights": [_P, _P, _P, _P],
+    "b2n_field_mlp_fw": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P],
+    "b2n_field_mlp_bw": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P],
     "b2n_cast_half": [_P, _P, _L, _P],
     "b2n_grid_cell_positions": [_P, _P, _L, _I, _F, _F, _F, _I, _P, _P],

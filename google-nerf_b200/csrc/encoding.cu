@@ -16,12 +16,14 @@ struct GridLevels {
     uint32_t resolution[B2N_MAX_LEVELS];
     uint32_t size[B2N_MAX_LEVELS];
     uint32_t offset[B2N_MAX_LEVELS];
+    float x_offset, x_scale;
 };
 
 static int to_levels(const b2n_grid_layout *l, GridLevels &g) {
     B2N_CHECK_ARG(l != nullptr && l->n_features == 2 && l->n_levels >= 1 && l->n_levels <= B2N_MAX_LEVELS,
                   "hash grid needs n_features == 2 and 1..32 levels");
     g.n_levels = l->n_levels;
+    g.x_offset = l->x_offset; g.x_scale = l->x_scale;
     for (int i = 0; i < l->n_levels; ++i) {
         g.scale[i] = l->scale[i]; g.resolution[i] = l->resolution[i];
         g.size[i] = l->size[i]; g.offset[i] = l->offset[i];
@@ -52,6 +54,7 @@ extern "C" int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashma
         B2N_CHECK_ARG(off < 0xffffffffull, "hash table too large");
     }
     layout->offset[n_levels] = (uint32_t)off;
+    layout->x_offset = 0.0f; layout->x_scale = 1.0f;
     return 0;
 }
 
@@ -97,7 +100,8 @@ __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restric
                                                           __half *__restrict__ out, int out_stride) {
     n = b2n_eff_n(n, n_dev);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+        const float px = (__ldg(x + 3 * i) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * i + 1) - g.x_offset) * g.x_scale,
+                    pz = (__ldg(x + 3 * i + 2) - g.x_offset) * g.x_scale;
         __half2 *row = reinterpret_cast<__half2 *>(out + i * out_stride);
         #pragma unroll 4
         for (int l = 0; l < g.n_levels; ++l) {
@@ -125,7 +129,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
                                                           float2 *__restrict__ grad_table) {
     n = b2n_eff_n(n, n_dev);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float px = __ldg(x + 3 * i), py = __ldg(x + 3 * i + 1), pz = __ldg(x + 3 * i + 2);
+        const float px = (__ldg(x + 3 * i) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * i + 1) - g.x_offset) * g.x_scale,
+                    pz = (__ldg(x + 3 * i + 2) - g.x_offset) * g.x_scale;
         const __half2 *row = reinterpret_cast<const __half2 *>(dy + i * dy_stride);
         #pragma unroll 2
         for (int l = 0; l < g.n_levels; ++l) {

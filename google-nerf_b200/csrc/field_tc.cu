@@ -1,0 +1,573 @@
+// field_tc.cu -- the NGP field's dense part on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Replaces, for the HashGrid NGP hot path, the chain
+//     xyz_encoder's FullyFusedMLP (32 -> 64 -> 16)  ->  TruncExp  ->  SH-4(dir)  ->  cat  ->  rgb_net (32 -> 64 -> 64 -> 3)
+// of ngp_pl/models/networks.py:96-115 (five tcnn/torch launches plus casts in the reference) with ONE kernel
+// forward and ONE kernel backward.  Layer activations never leave the SM between layers: each layer is one
+// tcgen05.mma group (M = 128 samples, N = layer width, K = 16 per instruction) whose fp32 accumulator lives in
+// TMEM; the epilogue threads pull their row with tcgen05.ld, apply ReLU / exp / sigmoid, and write the fp16
+// row straight back into the shared-memory operand tile of the next layer.  Weights (20 KB fp16, laid out
+// once in the UMMA canonical layout by field_pack_weights) arrive with one TMA bulk copy per CTA.
+//
+// Work decomposition: CTA = 128 threads = 128 samples (thread r <-> sample row r <-> TMEM lane r); CTAs are
+// persistent over tiles; several CTAs per SM (52 KB smem, 64 TMEM columns each) overlap one CTA's epilogue
+// with another's MMA.  The arithmetic (20.5 kFLOP/sample) is far below the tensor roofline; the kernel is
+// bound by the activation bytes it has to save for the backward pass (DESIGN.md "Field MLP").
+#include "common.cuh"
+#include "tc_common.cuh"
+
+using namespace tc;
+
+// canonical weight image (halves): [W1 64x32][W2 16x64][W3 64x32][W4 64x64][W5 16x64]
+#define IMG_W1 0
+#define IMG_W2 2048
+#define IMG_W3 3072
+#define IMG_W4 5120
+#define IMG_W5 9216
+#define IMG_HALVES 10240
+
+__global__ void __launch_bounds__(256) field_pack_weights_kernel(const __half *__restrict__ sigma_w,
+                                                                 const __half *__restrict__ rgb_w,
+                                                                 __half *__restrict__ image) {
+    // flat row-major (out,in) matrices -> canonical K-major no-swizzle images
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < IMG_HALVES; e += gridDim.x * blockDim.x) {
+        const __half *src; int base, N, K, idx;
+        if (e < 2048)      { src = sigma_w;        base = IMG_W1; N = 64; K = 32; idx = e; }
+        else if (e < 3072) { src = sigma_w + 2048; base = IMG_W2; N = 16; K = 64; idx = e - 2048; }
+        else if (e < 5120) { src = rgb_w;          base = IMG_W3; N = 64; K = 32; idx = e - 3072; }
+        else if (e < 9216) { src = rgb_w + 2048;   base = IMG_W4; N = 64; K = 64; idx = e - 5120; }
+        else               { src = rgb_w + 6144;   base = IMG_W5; N = 16; K = 64; idx = e - 9216; }
+        const int n = idx / K, k = idx - n * K;
+        image[base + w_off_halves(n, k, N)] = src[idx];
+    }
+}
+
+extern "C" int b2n_field_pack_weights(const b2n_half *sigma_w, const b2n_half *rgb_w, b2n_half *image, void *stream) {
+    field_pack_weights_kernel<<<10, 256, 0, (cudaStream_t)stream>>>((const __half *)sigma_w, (const __half *)rgb_w,
+                                                                    (__half *)image);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sh4_eval_dev(float x, float y, float z, float *o) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+__device__ __forceinline__ uint4 pack8(const float *v) {
+    uint4 p;
+    __half2 *h = reinterpret_cast<__half2 *>(&p);
+    h[0] = __floats2half2_rn(v[0], v[1]); h[1] = __floats2half2_rn(v[2], v[3]);
+    h[2] = __floats2half2_rn(v[4], v[5]); h[3] = __floats2half2_rn(v[6], v[7]);
+    return p;
+}
+
+// issue the K-loop of one layer: D[128 x N] = A[128 x K] (K-major tile) * W[N x K]^T (K-major image)
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int N, int K,
+                                            uint64_t *bar) {
+    const uint32_t idesc = make_idesc(128, N, 0, 0);
+    const uint32_t w_lbo = (uint32_t)(N >> 3) * 128;
+    for (int k = 0; k < K / 16; ++k) {
+        const uint64_t da = make_desc(a_addr + (uint32_t)k * 2 * ACT_LBO, ACT_LBO, ACT_SBO);
+        const uint64_t db = make_desc(w_addr + (uint32_t)k * 2 * w_lbo, w_lbo, 128);
+        mma_f16_ss(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+    mma_commit(bar);
+}
+
+struct FieldFwSmem {
+    __half w[IMG_HALVES];          // 20480 B  canonical weight images
+    __half a0[128 * 32];           //  8192 B  encoded input tile  [128 x 32]
+    __half a1[128 * 64];           // 16384 B  hidden tile         [128 x 64]
+    __half a3[128 * 32];           //  8192 B  colour-net input    [128 x 32] = [SH16 | h16]
+    uint64_t bar_w, bar_mma;
+    uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__restrict__ enc,
+                                                              const float *__restrict__ dirs,
+                                                              const __half *__restrict__ image, int64_t n,
+                                                              const int32_t *__restrict__ n_dev,
+                                                              float *__restrict__ sigmas, float *__restrict__ rgbs,
+                                                              __half *__restrict__ hid_s, __half *__restrict__ h_out,
+                                                              __half *__restrict__ hid_r) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FieldFwSmem &S = *reinterpret_cast<FieldFwSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int64_t n_alloc = n;
+    n = b2n_eff_n(n, n_dev);
+    const int64_t n_tiles = (n + 127) / 128;
+    if ((int64_t)blockIdx.x >= n_tiles) return;     // uniform per CTA: nothing allocated yet
+
+    if (tid == 0) {
+        mbar_init(&S.bar_w, 1);
+        mbar_init(&S.bar_mma, 1);
+        mbar_init_fence();
+    }
+    if (warp == 0) tmem_alloc<64>(&S.tmem_base);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes
+    if (tid == 0) {
+        mbar_expect_tx(&S.bar_w, IMG_HALVES * 2);
+        bulk_g2s(S.w, image, IMG_HALVES * 2, &S.bar_w);
+    }
+    mbar_wait(&S.bar_w, 0);
+
+    const uint32_t w_addr = smem_u32(S.w), a0 = smem_u32(S.a0), a1 = smem_u32(S.a1), a3 = smem_u32(S.a3);
+    unsigned char *A0 = reinterpret_cast<unsigned char *>(S.a0);
+    unsigned char *A1 = reinterpret_cast<unsigned char *>(S.a1);
+    unsigned char *A3 = reinterpret_cast<unsigned char *>(S.a3);
+    uint32_t phase = 0;
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * 128 + tid;
+        const bool live = row < n;
+        // ---- stage 0: encoded features and SH(dir) into the operand tiles
+        {
+            uint4 e[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+            float dx = 0.f, dy = 0.f, dz = 1.f;
+            if (live) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(enc + row * 32);
+                e[0] = __ldg(src); e[1] = __ldg(src + 1); e[2] = __ldg(src + 2); e[3] = __ldg(src + 3);
+                dx = __ldg(dirs + 3 * row); dy = __ldg(dirs + 3 * row + 1); dz = __ldg(dirs + 3 * row + 2);
+            }
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(A0 + act_off(tid, c)) = e[c];
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float sh[16];
+            sh4_eval_dev(dx * inv, dy * inv, dz * inv, sh);
+            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 0)) = pack8(sh);
+            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 1)) = pack8(sh + 8);
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        // ---- layer 1: enc(32) -> 64, ReLU
+        if (tid == 0) issue_layer(tmem, a0, w_addr + IMG_W1 * 2, 64, 32, &S.bar_mma);
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        #pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+            float v[16];
+            tmem_ld16(tmem_row + c16 * 16, v);
+            #pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+            *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16)) = p0;
+            *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16 + 1)) = p1;
+            if (hid_s != nullptr && live) {
+                uint4 *dst = reinterpret_cast<uint4 *>(hid_s + row * 64 + c16 * 16);
+                dst[0] = p0; dst[1] = p1;
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        // ---- layer 2: 64 -> 16 (h); sigma = exp(h[0])   (TruncExp forward, custom_functions.py:165-167)
+        if (tid == 0) issue_layer(tmem, a1, w_addr + IMG_W2 * 2, 16, 64, &S.bar_mma);
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float v[16];
+            tmem_ld16(tmem_row, v);
+            const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 2)) = p0;
+            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 3)) = p1;
+            if (live) {
+                const float h0 = __low2float(*reinterpret_cast<const __half2 *>(&p0));   // fp16-rounded like the reference
+                sigmas[row] = expf(h0);
+                if (h_out != nullptr) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(h_out + row * 16);
+                    dst[0] = p0; dst[1] = p1;
+                }
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+        // ---- layers 3, 4: [SH16 | h16] -> 64 -> 64, ReLU
+        #pragma unroll 1
+        for (int l = 0; l < 2; ++l) {
+            if (tid == 0) {
+                if (l == 0) issue_layer(tmem, a3, w_addr + IMG_W3 * 2, 64, 32, &S.bar_mma);
+                else        issue_layer(tmem, a1, w_addr + IMG_W4 * 2, 64, 64, &S.bar_mma);
+            }
+            mbar_wait(&S.bar_mma, phase); phase ^= 1;
+            fence_after_sync();
+            #pragma unroll
+            for (int c16 = 0; c16 < 4; ++c16) {
+                float v[16];
+                tmem_ld16(tmem_row + c16 * 16, v);
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+                const uint4 p0 = pack8(v), p1 = pack8(v + 8);
+                *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16)) = p0;
+                *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16 + 1)) = p1;
+                if (hid_r != nullptr && live) {
+                    uint4 *dst = reinterpret_cast<uint4 *>(hid_r + ((int64_t)l * n_alloc + row) * 64 + c16 * 16);
+                    dst[0] = p0; dst[1] = p1;
+                }
+            }
+            fence_async_smem();
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+        }
+        // ---- layer 5: 64 -> 3 (padded 16), sigmoid
+        if (tid == 0) issue_layer(tmem, a1, w_addr + IMG_W5 * 2, 16, 64, &S.bar_mma);
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float v[16];
+            tmem_ld16(tmem_row, v);
+            if (live) {
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    // the reference's rgb_net returns fp16: round the sigmoid like it does
+                    const float y = 1.0f / (1.0f + __expf(-v[c]));
+                    rgbs[3 * row + c] = __half2float(__float2half_rn(y));
+                }
+            }
+        }
+        fence_before_sync();
+        __syncthreads();       // all TMEM reads of this tile are done before the next tile's first MMA
+        fence_after_sync();
+    }
+    if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+extern "C" int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2n_half *image, int64_t n,
+                                const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *hid_s, b2n_half *h,
+                                b2n_half *hid_r, void *stream) {
+    B2N_CHECK_ARG(((uintptr_t)enc & 15) == 0 && ((uintptr_t)image & 15) == 0, "enc / image must be 16-byte aligned");
+    if (n <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(field_mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldFwSmem) + 1024);
+        attr_set = true;
+    }
+    field_mlp_fw_kernel<<<b2n_grid((n + 127) / 128, 4), 128, sizeof(FieldFwSmem) + 1024, (cudaStream_t)stream>>>(
+        (const __half *)enc, dirs, (const __half *)image, n, n_dev, sigmas, rgbs, (__half *)hid_s, (__half *)h,
+        (__half *)hid_r);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ================================================================================================
+// Backward.  Per 128-sample tile, five steps (layer 5 .. layer 1); each step issues, back to back,
+//   wgrad:  dW (+)= g^T . act     (M = 64, K = 128 samples; both operands are the SAME shared-memory tiles the
+//                                  forward/dgrad MMAs use, read MN-major; accumulators persist in TMEM across
+//                                  all tiles of the CTA and are flushed once with red.global.add)
+//   dgrad:  g_prev = g . W        (M = 128 samples; W read MN-major from the canonical weight image)
+// then the epilogue threads apply ReLU' / TruncExp' and write the fp16 gradient tile of the next step.
+// Activation rows of the next step are fetched from global memory while the current step's MMAs run.
+// TMEM columns: [0,64) dgrad work | [64,80) dW5^T | [80,144) dW4 | [144,176) dW3 | [176,192) dW2^T | [192,224) dW1.
+struct FieldBwSmem {
+    __half w[IMG_HALVES];          // 20480 B
+    __half act[2][128 * 64];       // 32768 B  activation tiles (ping-pong)
+    __half g[2][128 * 64];         // 32768 B  gradient tiles   (ping-pong)
+    uint64_t bar_w, bar_mma;
+    uint32_t tmem_base;
+};
+
+#define TM_WORK 0
+#define TM_DW5T 64
+#define TM_DW4 80
+#define TM_DW3 144
+#define TM_DW2T 176
+#define TM_DW1 192
+
+// wgrad: D[64 x N] (+)= A_tile^T[64 x 128] * B_tile[128 x N]; A/B tiles are [128 samples x features]
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, int N, bool accumulate) {
+    const uint32_t idesc = make_idesc(64, N, 1, 1);
+    #pragma unroll
+    for (int k = 0; k < 8; ++k) {                    // 16 samples per instruction = two 8-sample groups
+        const uint64_t da = make_desc(a_tile + (uint32_t)k * 2 * ACT_SBO, ACT_SBO, ACT_LBO);
+        const uint64_t db = make_desc(b_tile + (uint32_t)k * 2 * ACT_SBO, ACT_SBO, ACT_LBO);
+        mma_f16_ss(tmem_d, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+    }
+}
+// dgrad: D[128 x N_in] = G_tile[128 x K_out] (K-major) * W[K_out x N_in] (W image has K_out rows: MN-major B)
+__device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t g_tile, uint32_t w_img, int N_in, int K_out) {
+    const uint32_t idesc = make_idesc(128, N_in, 0, 1);
+    const uint32_t w_lbo = (uint32_t)(K_out >> 3) * 128;          // byte stride between in-chunks of the image
+    for (int k = 0; k < K_out / 16; ++k) {
+        const uint64_t da = make_desc(g_tile + (uint32_t)k * 2 * ACT_LBO, ACT_LBO, ACT_SBO);
+        const uint64_t db = make_desc(w_img + (uint32_t)k * 2 * 128, 128, w_lbo);
+        mma_f16_ss(tmem_d, da, db, idesc, k > 0 ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void load_row64(const __half *src, bool live, unsigned char *tile, int r) {
+    #pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (live) v = __ldg(reinterpret_cast<const uint4 *>(src) + c);
+        *reinterpret_cast<uint4 *>(tile + act_off(r, c)) = v;
+    }
+}
+
+// masked = (act > 0) ? g : 0 for 16 columns starting at c16*16, packed to fp16 into tile chunks 2*c16, 2*c16+1
+__device__ __forceinline__ void relu_bw_store(const float *v, const unsigned char *act_tile, unsigned char *g_tile,
+                                              int r, int c16) {
+    float o[16];
+    #pragma unroll
+    for (int half8 = 0; half8 < 2; ++half8) {
+        const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, 2 * c16 + half8));
+        const __half *ah = reinterpret_cast<const __half *>(&a);
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) o[half8 * 8 + j] = (__half2float(ah[j]) > 0.f) ? v[half8 * 8 + j] : 0.f;
+    }
+    *reinterpret_cast<uint4 *>(g_tile + act_off(r, 2 * c16)) = pack8(o);
+    *reinterpret_cast<uint4 *>(g_tile + act_off(r, 2 * c16 + 1)) = pack8(o + 8);
+}
+
+#define STEP_SYNC()            \
+    do {                       \
+        fence_async_smem();    \
+        fence_before_sync();   \
+        __syncthreads();       \
+        fence_after_sync();    \
+    } while (0)
+
+__global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
+    const float *__restrict__ dL_dsigmas, const float *__restrict__ dL_drgbs, const __half *__restrict__ enc,
+    const float *__restrict__ dirs, const __half *__restrict__ image, int64_t n, const int32_t *__restrict__ n_dev,
+    const float *__restrict__ rgbs, const __half *__restrict__ hid_s, const __half *__restrict__ h_in,
+    const __half *__restrict__ hid_r, float grad_scale, __half *__restrict__ dL_denc,
+    float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    FieldBwSmem &S = *reinterpret_cast<FieldBwSmem *>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n_alloc = n;
+    n = b2n_eff_n(n, n_dev);
+    const int64_t n_tiles = (n + 127) / 128;
+    if ((int64_t)blockIdx.x >= n_tiles) return;
+
+    if (tid == 0) {
+        mbar_init(&S.bar_w, 1);
+        mbar_init(&S.bar_mma, 1);
+        mbar_init_fence();
+    }
+    if (warp == 0) tmem_alloc<256>(&S.tmem_base);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = S.tmem_base;
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
+    if (tid == 0) {
+        mbar_expect_tx(&S.bar_w, IMG_HALVES * 2);
+        bulk_g2s(S.w, image, IMG_HALVES * 2, &S.bar_w);
+    }
+    mbar_wait(&S.bar_w, 0);
+
+    const uint32_t w_addr = smem_u32(S.w);
+    const uint32_t act_a[2] = {smem_u32(S.act[0]), smem_u32(S.act[1])};
+    const uint32_t g_a[2] = {smem_u32(S.g[0]), smem_u32(S.g[1])};
+    unsigned char *ACT[2] = {reinterpret_cast<unsigned char *>(S.act[0]), reinterpret_cast<unsigned char *>(S.act[1])};
+    unsigned char *G[2] = {reinterpret_cast<unsigned char *>(S.g[0]), reinterpret_cast<unsigned char *>(S.g[1])};
+    uint32_t phase = 0;
+    bool acc = false;          // wgrad accumulators hold data from an earlier tile
+
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row = tile * 128 + tid;
+        const bool live = row < n;
+        // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G0 [128x16]; hid_r2 -> ACT0; hid_r1 -> ACT1
+        {
+            float g5[16];
+            #pragma unroll
+            for (int i = 0; i < 16; ++i) g5[i] = 0.f;
+            if (live) {
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float y = __ldg(rgbs + 3 * row + c);
+                    g5[c] = __ldg(dL_drgbs + 3 * row + c) * y * (1.0f - y);
+                }
+            }
+            *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 0)) = pack8(g5);
+            *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 1)) = pack8(g5 + 8);
+            load_row64(hid_r + ((int64_t)1 * n_alloc + row) * 64, live, ACT[0], tid);
+            load_row64(hid_r + row * 64, live, ACT[1], tid);
+        }
+        STEP_SYNC();
+        // ---- step A: layer 5 (64 -> 16)
+        if (tid == 0) {
+            issue_wgrad(tmem + TM_DW5T, act_a[0], g_a[0], 16, acc);          // dW5^T[in][out] += hid_r2^T . g5
+            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W5 * 2, 64, 16);  // g4 = g5 . W5
+            mma_commit(&S.bar_mma);
+        }
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        #pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+            float v[16];
+            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
+            relu_bw_store(v, ACT[0], G[1], tid, c16);                        // g4 = . * (hid_r2 > 0)
+        }
+        STEP_SYNC();
+        // ---- step B: layer 4 (64 -> 64)
+        if (tid == 0) {
+            issue_wgrad(tmem + TM_DW4, g_a[1], act_a[1], 64, acc);            // dW4[out][in] += g4^T . hid_r1
+            issue_dgrad(tmem + TM_WORK, g_a[1], w_addr + IMG_W4 * 2, 64, 64);  // g3 = g4 . W4
+            mma_commit(&S.bar_mma);
+        }
+        {   // while the MMAs run: colour-net input [SH16 | h16] -> ACT0 (its last readers finished in step A)
+            float dx = 0.f, dy = 0.f, dz = 1.f;
+            uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+            if (live) {
+                dx = __ldg(dirs + 3 * row); dy = __ldg(dirs + 3 * row + 1); dz = __ldg(dirs + 3 * row + 2);
+                h0 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16));
+                h1 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16) + 1);
+            }
+            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+            float sh[16];
+            sh4_eval_dev(dx * inv, dy * inv, dz * inv, sh);
+            if (!live) {
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+            }
+            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 0)) = pack8(sh);
+            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 1)) = pack8(sh + 8);
+            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 2)) = h0;
+            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 3)) = h1;
+        }
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        #pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+            float v[16];
+            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
+            relu_bw_store(v, ACT[1], G[0], tid, c16);                        // g3 = . * (hid_r1 > 0)
+        }
+        STEP_SYNC();
+        // ---- step C: layer 3 (32 -> 64)
+        if (tid == 0) {
+            issue_wgrad(tmem + TM_DW3, g_a[0], act_a[0], 32, acc);            // dW3[out][in] += g3^T . [SH|h]
+            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W3 * 2, 32, 64);  // g_in3 = g3 . W3
+            mma_commit(&S.bar_mma);
+        }
+        load_row64(hid_s + row * 64, live, ACT[1], tid);                      // prefetch hid_s
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        {
+            float v[16];
+            tmem_ld16(tmem_row + TM_WORK + 16, v);                           // columns 16..31 = dL/dh from the colour net
+            // TruncExp backward (custom_functions.py:171-173) joins on channel 0
+            const __half2 hh = *reinterpret_cast<const __half2 *>(ACT[0] + act_off(tid, 2));
+            const float h0 = __low2float(hh);
+            if (live) v[0] += __ldg(dL_dsigmas + row) * expf(fminf(fmaxf(h0, -15.f), 15.f));
+            *reinterpret_cast<uint4 *>(G[1] + act_off(tid, 0)) = pack8(v);
+            *reinterpret_cast<uint4 *>(G[1] + act_off(tid, 1)) = pack8(v + 8);
+        }
+        STEP_SYNC();
+        // ---- step D: layer 2 (64 -> 16)
+        if (tid == 0) {
+            issue_wgrad(tmem + TM_DW2T, act_a[1], g_a[1], 16, acc);           // dW2^T[in][out] += hid_s^T . g2
+            issue_dgrad(tmem + TM_WORK, g_a[1], w_addr + IMG_W2 * 2, 64, 16);  // g1 = g2 . W2
+            mma_commit(&S.bar_mma);
+        }
+        {   // prefetch enc -> ACT0 [128x32]
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (live) v = __ldg(reinterpret_cast<const uint4 *>(enc + row * 32) + c);
+                *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, c)) = v;
+            }
+        }
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        #pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+            float v[16];
+            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
+            relu_bw_store(v, ACT[1], G[0], tid, c16);                        // g1 = . * (hid_s > 0)
+        }
+        STEP_SYNC();
+        // ---- step E: layer 1 (32 -> 64)
+        if (tid == 0) {
+            issue_wgrad(tmem + TM_DW1, g_a[0], act_a[0], 32, acc);            // dW1[out][in] += g1^T . enc
+            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W1 * 2, 32, 64);  // g_enc = g1 . W1
+            mma_commit(&S.bar_mma);
+        }
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        fence_after_sync();
+        #pragma unroll
+        for (int c16 = 0; c16 < 2; ++c16) {
+            float v[16];
+            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
+            if (live) {
+                uint4 *dst = reinterpret_cast<uint4 *>(dL_denc + row * 32 + c16 * 16);
+                dst[0] = pack8(v); dst[1] = pack8(v + 8);
+            }
+        }
+        acc = true;
+        fence_before_sync();
+        __syncthreads();
+        fence_after_sync();
+    }
+    // ---- flush the weight gradients: M = 64 accumulators sit in lanes 32*w + (0..15) <-> rows 16*w + lane
+    {
+        const int m = warp * 16 + lane;      // valid for lane < 16
+        #pragma unroll 1
+        for (int c16 = 0; c16 < 10; ++c16) {  // columns 64 .. 223 in groups of 16
+            float v[16];
+            tmem_ld16(tmem_row + 64 + c16 * 16, v);
+            if (lane < 16) {
+                #pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = 64 + c16 * 16 + j;
+                    const float val = v[j] * grad_scale;
+                    if (val == 0.f) continue;
+                    if (col < TM_DW4)       atomicAdd(grad_rgb_w + 6144 + (col - TM_DW5T) * 64 + m, val);   // dW5^T[in=m][out]
+                    else if (col < TM_DW3)  atomicAdd(grad_rgb_w + 2048 + m * 64 + (col - TM_DW4), val);    // dW4[out=m][in]
+                    else if (col < TM_DW2T) atomicAdd(grad_rgb_w + m * 32 + (col - TM_DW3), val);           // dW3[out=m][in]
+                    else if (col < TM_DW1)  atomicAdd(grad_sigma_w + 2048 + (col - TM_DW2T) * 64 + m, val); // dW2^T[in=m][out]
+                    else                    atomicAdd(grad_sigma_w + m * 32 + (col - TM_DW1), val);         // dW1[out=m][in]
+                }
+            }
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
+                                const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs,
+                                const b2n_half *hid_s, const b2n_half *h, const b2n_half *hid_r, float grad_scale,
+                                b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, void *stream) {
+    B2N_CHECK_ARG(hid_s && h && hid_r && rgbs && dL_denc && grad_sigma_w && grad_rgb_w, "saved activations and outputs are required");
+    if (n <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(field_mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldBwSmem) + 1024);
+        attr_set = true;
+    }
+    field_mlp_bw_kernel<<<b2n_grid((n + 127) / 128, 2), 128, sizeof(FieldBwSmem) + 1024, (cudaStream_t)stream>>>(
+        dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)hid_s,
+        (const __half *)h, (const __half *)hid_r, grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

@@ -45,7 +45,6 @@ class NGPTrainer:
         self._from_indices = False
 
         xe, rn = model.xyz_encoder, model.rgb_net
-        self.layout = xe.enc.layout
         self.n_mlp = xe.mlp.n_params
         self.p_xyz, self.p_rgb = xe.params.data, rn.params.data
         z = lambda t: torch.zeros_like(t)
@@ -54,6 +53,12 @@ class NGPTrainer:
         self.h_xyz = tc.cast_half(self.p_xyz)
         self.h_rgb = tc.cast_half(self.p_rgb)
         self.hyper = torch.zeros(2, dtype=torch.int32, device=self.dev)        # {float lr; int32 step}
+        self.w_image = torch.empty(10240, dtype=_f16, device=self.dev)
+        self._pack_weights()
+        # fold NGP.density's box normalisation (networks.py:96) into the hash-grid kernels
+        self.layout = L.GridLayout.from_buffer_copy(xe.enc.layout)
+        self.layout.x_offset = -float(model.scale)
+        self.layout.x_scale = 1.0 / (2.0 * float(model.scale))
         self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -65,17 +70,15 @@ class NGPTrainer:
         self.noise = e(n)
         self.rays_a = e(n, 3, dt=torch.int64); self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
         self.xyzs, self.dirs, self.deltas, self.ts = e(cap, 3), e(cap, 3), e(cap), e(cap)
-        self.x01 = e(cap, 3)
-        self.enc = e(cap, 32, dt=_f16); self.hid_s = e(1, cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
-        self.rgb_in = e(cap, 32, dt=_f16); self.hid_r = e(2, cap, 64, dt=_f16); self.rgb16 = e(cap, 16, dt=_f16)
+        self.enc = e(cap, 32, dt=_f16); self.hid_s = e(cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
+        self.hid_r = e(2, cap, 64, dt=_f16)
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
         self.opacity, self.depth, self.depth_sq, self.rgb = e(n), e(n), e(n), e(n, 3)
         self.rgb_out, self.loss = e(n, 3), torch.zeros(1, device=dev)
         self.dL_drgb, self.dL_dopacity = e(n, 3), e(n)
         self.zeros_n = torch.zeros(n, device=dev)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
-        self.dy_rgb = torch.zeros(cap, 16, dtype=_f16, device=dev); self.din_rgb = e(cap, 32, dt=_f16)
-        self.dy_sig = e(cap, 16, dt=_f16); self.din_enc = e(cap, 32, dt=_f16)
+        self.din_enc = e(cap, 32, dt=_f16)
         self.graph = None
 
     # ------------------------------------------------------------------ the step body (all on the device)
@@ -96,15 +99,10 @@ class NGPTrainer:
                  float(self.esf), P(self.noise), m.grid_size, MAX_SAMPLES, n)
         call("b2n_raymarching_train_count", *march, cap, P(self.rays_a), P(self.counter))
         call("b2n_raymarching_train_write", *march, P(self.rays_a), P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts))
-        # field forward
-        torch.sub(self.xyzs, m.xyz_min, out=self.x01); self.x01.div_(m.xyz_max - m.xyz_min)
-        call("b2n_hashgrid_fw", P(self.x01), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
-        call("b2n_mlp_fw", P(self.enc), 32, 32, P(self.h_xyz), 1, 0, cap, P(nd), P(self.hid_s), P(self.h))
-        torch.exp(self.h[:, 0].float(), out=self.sigmas)
-        call("b2n_sh4_fw", P(self.dirs), 1, cap, P(nd), P(self.rgb_in), 32)
-        self.rgb_in[:, 16:].copy_(self.h)
-        call("b2n_mlp_fw", P(self.rgb_in), 32, 32, P(self.h_rgb), 2, 1, cap, P(nd), P(self.hid_r), P(self.rgb16))
-        self.rgbs.copy_(self.rgb16[:, :3])
+        # field forward: hash-grid gather, then the fused tcgen05 MLP chain (sigma + colour)
+        call("b2n_hashgrid_fw", P(self.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
+        call("b2n_field_mlp_fw", P(self.enc), P(self.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),
+             P(self.hid_s), P(self.h), P(self.hid_r))
         # compositing + loss
         call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.rays_a),
              self.T_threshold, n, P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb))
@@ -115,15 +113,10 @@ class NGPTrainer:
              P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.rays_a), P(self.opacity), P(self.depth),
              P(self.depth_sq), P(self.rgb), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs))
         # field backward (gradients carry loss_scale; parameter gradients are unscaled inside Adam)
-        self.dy_rgb[:, :3].copy_(self.dL_drgbs)
-        call("b2n_mlp_bw", P(self.dy_rgb), P(self.rgb_in), 32, 32, P(self.h_rgb), 2, 1, cap, P(nd), P(self.hid_r),
-             P(self.rgb16), 1.0, P(self.din_rgb), P(self.g_rgb))
-        self.dy_sig.copy_(self.din_rgb[:, 16:])
-        # TruncExp backward (custom_functions.py:171-173) joins the colour branch's gradient on channel 0
-        self.dy_sig[:, 0] += (self.dL_dsigmas * torch.exp(self.h[:, 0].float().clamp(-15, 15))).to(_f16)
-        call("b2n_mlp_bw", P(self.dy_sig), P(self.enc), 32, 32, P(self.h_xyz), 1, 0, cap, P(nd), P(self.hid_s),
-             P(self.h), 1.0, P(self.din_enc), P(self.g_xyz))
-        call("b2n_hashgrid_bw", P(self.x01), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
+        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), P(self.dirs), P(self.w_image), cap,
+             P(nd), P(self.rgbs), P(self.hid_s), P(self.h), P(self.hid_r), 1.0, P(self.din_enc), P(self.g_xyz),
+             P(self.g_rgb))
+        call("b2n_hashgrid_bw", P(self.xyzs), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
              P(self.g_xyz[self.n_mlp:]))
 
     def _allreduce(self):
@@ -139,6 +132,11 @@ class NGPTrainer:
                               (self.p_rgb, self.g_rgb, self.m_rgb, self.v_rgb, self.h_rgb)):
             call("b2n_adam_step", P(p), P(g), P(m), P(v), P(h), p.numel(), self.lr, b1, b2, self.eps, inv, 1,
                  P(self.hyper))
+        self._pack_weights()
+
+    def _pack_weights(self):
+        """fp16 MLP weights -> UMMA canonical shared-memory image for the fused field kernels."""
+        L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image))
 
     # ------------------------------------------------------------------ ray generation (train.py:150-157)
     def set_dataset(self, directions, poses):
@@ -222,6 +220,7 @@ class NGPTrainer:
                           self.h_rgb), state):
             t.copy_(sv)                                   # the warm-up must not count as a training step
         self.g_xyz.zero_(); self.g_rgb.zero_()
+        self._pack_weights()
         if self.world == 1:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):

@@ -107,6 +107,8 @@ typedef struct {
     uint32_t resolution[B2N_MAX_LEVELS];
     uint32_t size[B2N_MAX_LEVELS];       /* entries in the level (hashed iff res^3 does not fit) */
     uint32_t offset[B2N_MAX_LEVELS + 1]; /* entry offsets into the flat table */
+    float x_offset, x_scale;             /* input affine x01 = (x - x_offset) * x_scale, (0,1) by default: folds
+                                            NGP.density's box normalisation (networks.py:96) into the kernel */
 } b2n_grid_layout;                       /* HOST struct, passed by pointer, copied at launch */
 
 /* GridEncoding sizing of tcnn's "HashGrid" config (models/networks.py:39-47).  Fills *layout (HOST);
@@ -147,6 +149,26 @@ B2N_API int b2n_mlp_bw(const b2n_half *dL_dout, const b2n_half *in, int in_strid
                const b2n_half *weights, int n_hidden, int output_activation, int64_t n,
                const int32_t *n_dev, const b2n_half *hidden, const b2n_half *out, float grad_scale,
                b2n_half *dL_din, float *grad_weights, void *stream);
+
+/* ---------------------------------------------------------------- fused field MLPs (tcgen05) --------- */
+/* The dense half of NGP.forward (models/networks.py:96-115) for the HashGrid configuration in one kernel:
+ * enc(32) -> 64 -> 16 = h, sigma = exp(h[0]) (TruncExp), [SH4(dir/|dir|) | h] -> 64 -> 64 -> 3, sigmoid.
+ * image: the two FullyFusedMLP weight sets repacked by b2n_field_pack_weights (10240 halves).
+ * enc (n,32) fp16 (b2n_hashgrid_fw output), dirs (n,3) fp32 raw directions -> sigmas (n) fp32,
+ * rgbs (n,3) fp32 (fp16-rounded).  Optional saves for the backward pass (NULL to skip):
+ * hid_s (n,64), h (n,16), hid_r (2,n,64), all fp16. */
+B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights /*3072*/, const b2n_half *rgb_weights /*7168*/,
+                                   b2n_half *image /*10240*/, void *stream);
+B2N_API int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2n_half *image, int64_t n,
+                             const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *hid_s, b2n_half *h,
+                             b2n_half *hid_r, void *stream);
+/* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale);
+ * writes dL_denc (n,32) fp16 for b2n_hashgrid_bw and accumulates (+=) grad_sigma_w (3072) / grad_rgb_w (7168)
+ * fp32 in the flat row-major (out,in) layout of the weights, times grad_scale. */
+B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
+                             const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs,
+                             const b2n_half *hid_s, const b2n_half *h, const b2n_half *hid_r, float grad_scale,
+                             b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, void *stream);
 
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
