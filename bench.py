@@ -129,6 +129,11 @@ def kernel_costs(n_rays, n_samples, n_params_xyz, n_params_rgb):
         "b2n_hashgrid_bw": ("hbm", 1100 * s),
         "b2n_mlp_fw": ("tensor", None),
         "b2n_mlp_bw": ("tensor", None),
+        # fused tcgen05 field MLPs: 20.5 / 41 kFLOP per sample are ~1% of the tensor roofline; what bounds them is
+        # the activation traffic (enc 64 + dirs 12 + sigma 4 + rgb 12 + saved hid_s 128, h 32, hid_r 256 B/sample)
+        "b2n_field_mlp_fw": ("hbm", 508 * s),
+        "b2n_field_mlp_bw": ("hbm", 584 * s),
+        "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_sh4_fw": ("hbm", 44 * s),
         "b2n_composite_train_fw": ("hbm", 24 * s + 48 * r),
         "b2n_composite_train_bw": ("hbm", 40 * s + 96 * r),

@@ -127,21 +127,66 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
                                                           const __grid_constant__ GridLevels g, int64_t n,
                                                           const int32_t *__restrict__ n_dev, float grad_scale,
                                                           float2 *__restrict__ grad_table) {
+    // Warp-aggregated scatter.  The 32 lanes of a warp hold 32 CONSECUTIVE packed samples, i.e. neighbours on a ray
+    // (0.0017 apart), so on the coarse levels most lanes fall into the same cell and would hit the same 8 table
+    // entries: L2 serialises atomics per address.  For levels whose cells are wide enough (resolution <= AGG_RES)
+    // runs of lanes with the same cell are summed with a segmented shuffle reduction and only the run's head lane
+    // issues the 8 vector reds; fine levels (one sample per cell) go straight to red.global.add.v2.f32.
+    const uint32_t AGG_RES = 320;
+    const uint32_t FULLM = 0xffffffffu;
     n = b2n_eff_n(n, n_dev);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float px = (__ldg(x + 3 * i) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * i + 1) - g.x_offset) * g.x_scale,
-                    pz = (__ldg(x + 3 * i + 2) - g.x_offset) * g.x_scale;
-        const __half2 *row = reinterpret_cast<const __half2 *>(dy + i * dy_stride);
-        #pragma unroll 2
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {  // warp-uniform
+        const int64_t i = base + lane;
+        const bool live = i < n;
+        const int64_t ii = live ? i : n - 1;
+        const float px = (__ldg(x + 3 * ii) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * ii + 1) - g.x_offset) * g.x_scale,
+                    pz = (__ldg(x + 3 * ii + 2) - g.x_offset) * g.x_scale;
+        const __half2 *row = reinterpret_cast<const __half2 *>(dy + ii * dy_stride);
+        #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
             float2 gr = __half22float2(__ldg(row + l));
-            gr.x *= grad_scale; gr.y *= grad_scale;
-            if (gr.x == 0.0f && gr.y == 0.0f) continue;
+            gr.x = live ? gr.x * grad_scale : 0.f;
+            gr.y = live ? gr.y * grad_scale : 0.f;
+            const uint32_t res = g.resolution[l];
             Corner8 c;
-            level_corners(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], c);
+            level_corners(px, py, pz, g.scale[l], res, g.size[l], g.offset[l], c);
+            if (res > AGG_RES) {
+                if (gr.x != 0.0f || gr.y != 0.0f) {
+                    #pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        atomicAdd(grad_table + c.idx[k], make_float2(gr.x * c.w[k], gr.y * c.w[k]));
+                }
+                continue;
+            }
+            // cell key: the integer lattice position (10 bits per axis is enough for res <= 320)
+            const float s = g.scale[l];
+            const uint32_t kx = (uint32_t)floorf(fmaf(s, px, 0.5f)), ky = (uint32_t)floorf(fmaf(s, py, 0.5f)),
+                           kz = (uint32_t)floorf(fmaf(s, pz, 0.5f));
+            const uint32_t key = live ? (kx | (ky << 10) | (kz << 20)) : (0xC0000000u | (uint32_t)lane);
+            const uint32_t prev = __shfl_up_sync(FULLM, key, 1);
+            const bool head = (lane == 0) || (key != prev);
+            const uint32_t heads = __ballot_sync(FULLM, head);
+            const uint32_t above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));   // heads at positions > lane
+            const int seg_end = above ? (__ffs(above) - 2) : 31;
+            float vx[8], vy[8];
             #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                atomicAdd(grad_table + c.idx[k], make_float2(gr.x * c.w[k], gr.y * c.w[k]));
+            for (int k = 0; k < 8; ++k) { vx[k] = gr.x * c.w[k]; vy[k] = gr.y * c.w[k]; }
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const bool take = lane + d <= seg_end;
+                #pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float ox = __shfl_down_sync(FULLM, vx[k], d), oy = __shfl_down_sync(FULLM, vy[k], d);
+                    if (take) { vx[k] += ox; vy[k] += oy; }
+                }
+            }
+            if (head && live) {
+                #pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (vx[k] != 0.0f || vy[k] != 0.0f) atomicAdd(grad_table + c.idx[k], make_float2(vx[k], vy[k]));
+            }
         }
     }
 }

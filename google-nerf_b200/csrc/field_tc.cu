@@ -10,13 +10,15 @@
 // once in the UMMA canonical layout by field_pack_weights) arrive with one TMA bulk copy per CTA.
 //
 // Work decomposition: CTA = 128 threads = 128 samples (thread r <-> sample row r <-> TMEM lane r); CTAs are
-// persistent over tiles; several CTAs per SM (52 KB smem, 64 TMEM columns each) overlap one CTA's epilogue
-// with another's MMA.  The arithmetic (20.5 kFLOP/sample) is far below the tensor roofline; the kernel is
-// bound by the activation bytes it has to save for the backward pass (DESIGN.md "Field MLP").
+// persistent over tiles; several CTAs per SM overlap one CTA's epilogue with another's MMA.  Activations that
+// the backward pass needs are copied out of the operand tiles with fully coalesced 16-byte stores while the next
+// layer's MMA is in flight.  The arithmetic (20.5 kFLOP/sample) is far below the tensor roofline; the kernels are
+// bound by the activation bytes saved / re-read for the backward pass (DESIGN.md "Field MLP").
 #include "common.cuh"
 #include "tc_common.cuh"
 
 using namespace tc;
+static_assert(ACT_LBO == 2064, "tile_load/tile_store hard-code the padded chunk stride");
 
 // canonical weight image (halves): [W1 64x32][W2 16x64][W3 64x32][W4 64x64][W5 16x64]
 #define IMG_W1 0
@@ -78,6 +80,33 @@ __device__ __forceinline__ uint4 pack8(const float *v) {
     return p;
 }
 
+// SH-4 of the normalised direction of this thread's row -> chunks 0,1 of a [128 x 32] tile
+__device__ __forceinline__ void sh_to_tile(const float *__restrict__ dirs, int64_t row, bool live, unsigned char *tile,
+                                           int r) {
+    float dx = 0.f, dy = 0.f, dz = 1.f;
+    if (live) { dx = __ldg(dirs + 3 * row); dy = __ldg(dirs + 3 * row + 1); dz = __ldg(dirs + 3 * row + 2); }
+    const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
+    float sh[16];
+    sh4_eval_dev(dx * inv, dy * inv, dz * inv, sh);
+    if (!live) {
+        #pragma unroll
+        for (int i = 0; i < 16; ++i) sh[i] = 0.f;
+    }
+    *reinterpret_cast<uint4 *>(tile + act_off(r, 0)) = pack8(sh);
+    *reinterpret_cast<uint4 *>(tile + act_off(r, 1)) = pack8(sh + 8);
+}
+
+// ReLU + fp16 pack of this thread's 64 accumulator columns into its row of a [128 x 64] tile
+__device__ __forceinline__ void relu_to_tile(const float *v, unsigned char *tile, int r) {
+    #pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        float o[8];
+        #pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[8 * c + j], 0.f);
+        *reinterpret_cast<uint4 *>(tile + act_off(r, c)) = pack8(o);
+    }
+}
+
 // issue the K-loop of one layer: D[128 x N] = A[128 x K] (K-major tile) * W[N x K]^T (K-major image)
 __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int N, int K,
                                             uint64_t *bar) {
@@ -91,11 +120,19 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
     mma_commit(bar);
 }
 
+#define STEP_SYNC()            \
+    do {                       \
+        fence_async_smem();    \
+        fence_before_sync();   \
+        __syncthreads();       \
+        fence_after_sync();    \
+    } while (0)
+
 struct FieldFwSmem {
-    __half w[IMG_HALVES];          // 20480 B  canonical weight images
-    __half a0[128 * 32];           //  8192 B  encoded input tile  [128 x 32]
-    __half a1[128 * 64];           // 16384 B  hidden tile         [128 x 64]
-    __half a3[128 * 32];           //  8192 B  colour-net input    [128 x 32] = [SH16 | h16]
+    __half w[IMG_HALVES];                      // 20480 B  canonical weight images
+    unsigned char a0[TILE32_BYTES];            //  8256 B  encoded input tile  [128 x 32]
+    unsigned char a1[TILE64_BYTES];            // 16512 B  hidden tile         [128 x 64]
+    unsigned char a3[TILE32_BYTES];            //  8256 B  colour-net input    [128 x 32] = [SH16 | h16]
     uint64_t bar_w, bar_mma;
     uint32_t tmem_base;
 };
@@ -133,67 +170,36 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
     mbar_wait(&S.bar_w, 0);
 
     const uint32_t w_addr = smem_u32(S.w), a0 = smem_u32(S.a0), a1 = smem_u32(S.a1), a3 = smem_u32(S.a3);
-    unsigned char *A0 = reinterpret_cast<unsigned char *>(S.a0);
-    unsigned char *A1 = reinterpret_cast<unsigned char *>(S.a1);
-    unsigned char *A3 = reinterpret_cast<unsigned char *>(S.a3);
     uint32_t phase = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * 128 + tid;
+        const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
-        // ---- stage 0: encoded features and SH(dir) into the operand tiles
-        {
-            uint4 e[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-            float dx = 0.f, dy = 0.f, dz = 1.f;
-            if (live) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(enc + row * 32);
-                e[0] = __ldg(src); e[1] = __ldg(src + 1); e[2] = __ldg(src + 2); e[3] = __ldg(src + 3);
-                dx = __ldg(dirs + 3 * row); dy = __ldg(dirs + 3 * row + 1); dz = __ldg(dirs + 3 * row + 2);
-            }
-            #pragma unroll
-            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(A0 + act_off(tid, c)) = e[c];
-            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            float sh[16];
-            sh4_eval_dev(dx * inv, dy * inv, dz * inv, sh);
-            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 0)) = pack8(sh);
-            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 1)) = pack8(sh + 8);
-        }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
+        // ---- stage 0: encoded features (coalesced) and SH(dir) into the operand tiles
+        tile_load<4>(S.a0, enc + row0 * 32, rows_valid, tid);
+        sh_to_tile(dirs, row, live, S.a3, tid);
+        STEP_SYNC();
         // ---- layer 1: enc(32) -> 64, ReLU
         if (tid == 0) issue_layer(tmem, a0, w_addr + IMG_W1 * 2, 64, 32, &S.bar_mma);
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-            float v[16];
-            tmem_ld16(tmem_row + c16 * 16, v);
-            #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-            const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-            *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16)) = p0;
-            *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16 + 1)) = p1;
-            if (hid_s != nullptr && live) {
-                uint4 *dst = reinterpret_cast<uint4 *>(hid_s + row * 64 + c16 * 16);
-                dst[0] = p0; dst[1] = p1;
-            }
+        {
+            float v[64];
+            tmem_ld64(tmem_row, v);
+            relu_to_tile(v, S.a1, tid);
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
-        fence_after_sync();
+        STEP_SYNC();
         // ---- layer 2: 64 -> 16 (h); sigma = exp(h[0])   (TruncExp forward, custom_functions.py:165-167)
         if (tid == 0) issue_layer(tmem, a1, w_addr + IMG_W2 * 2, 16, 64, &S.bar_mma);
+        if (hid_s != nullptr) tile_store<8>(S.a1, hid_s + row0 * 64, rows_valid, tid);   // overlaps the MMA
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
         {
             float v[16];
             tmem_ld16(tmem_row, v);
             const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 2)) = p0;
-            *reinterpret_cast<uint4 *>(A3 + act_off(tid, 3)) = p1;
+            *reinterpret_cast<uint4 *>(S.a3 + act_off(tid, 2)) = p0;
+            *reinterpret_cast<uint4 *>(S.a3 + act_off(tid, 3)) = p1;
             if (live) {
                 const float h0 = __low2float(*reinterpret_cast<const __half2 *>(&p0));   // fp16-rounded like the reference
                 sigmas[row] = expf(h0);
@@ -203,40 +209,32 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
                 }
             }
         }
-        fence_async_smem();
-        fence_before_sync();
-        __syncthreads();
+        STEP_SYNC();
+        // ---- layer 3: [SH16 | h16] -> 64, ReLU
+        if (tid == 0) issue_layer(tmem, a3, w_addr + IMG_W3 * 2, 64, 32, &S.bar_mma);
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        // ---- layers 3, 4: [SH16 | h16] -> 64 -> 64, ReLU
-        #pragma unroll 1
-        for (int l = 0; l < 2; ++l) {
-            if (tid == 0) {
-                if (l == 0) issue_layer(tmem, a3, w_addr + IMG_W3 * 2, 64, 32, &S.bar_mma);
-                else        issue_layer(tmem, a1, w_addr + IMG_W4 * 2, 64, 64, &S.bar_mma);
-            }
-            mbar_wait(&S.bar_mma, phase); phase ^= 1;
-            fence_after_sync();
-            #pragma unroll
-            for (int c16 = 0; c16 < 4; ++c16) {
-                float v[16];
-                tmem_ld16(tmem_row + c16 * 16, v);
-                #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
-                const uint4 p0 = pack8(v), p1 = pack8(v + 8);
-                *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16)) = p0;
-                *reinterpret_cast<uint4 *>(A1 + act_off(tid, 2 * c16 + 1)) = p1;
-                if (hid_r != nullptr && live) {
-                    uint4 *dst = reinterpret_cast<uint4 *>(hid_r + ((int64_t)l * n_alloc + row) * 64 + c16 * 16);
-                    dst[0] = p0; dst[1] = p1;
-                }
-            }
-            fence_async_smem();
-            fence_before_sync();
-            __syncthreads();
-            fence_after_sync();
+        {
+            float v[64];
+            tmem_ld64(tmem_row, v);
+            relu_to_tile(v, S.a1, tid);
         }
+        STEP_SYNC();
+        // ---- layer 4: 64 -> 64, ReLU
+        if (tid == 0) issue_layer(tmem, a1, w_addr + IMG_W4 * 2, 64, 64, &S.bar_mma);
+        if (hid_r != nullptr) tile_store<8>(S.a1, hid_r + row0 * 64, rows_valid, tid);
+        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        __syncthreads();       // every thread's copy-out of a1 is done before anyone overwrites its row below
+        fence_after_sync();
+        {
+            float v[64];
+            tmem_ld64(tmem_row, v);
+            relu_to_tile(v, S.a1, tid);
+        }
+        STEP_SYNC();
         // ---- layer 5: 64 -> 3 (padded 16), sigmoid
         if (tid == 0) issue_layer(tmem, a1, w_addr + IMG_W5 * 2, 16, 64, &S.bar_mma);
+        if (hid_r != nullptr) tile_store<8>(S.a1, hid_r + (n_alloc + row0) * 64, rows_valid, tid);
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
         {
@@ -265,10 +263,10 @@ extern "C" int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2
     if (n <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(field_mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldFwSmem) + 1024);
+        cudaFuncSetAttribute(field_mlp_fw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldFwSmem) + 256);
         attr_set = true;
     }
-    field_mlp_fw_kernel<<<b2n_grid((n + 127) / 128, 4), 128, sizeof(FieldFwSmem) + 1024, (cudaStream_t)stream>>>(
+    field_mlp_fw_kernel<<<b2n_grid((n + 127) / 128, 4), 128, sizeof(FieldFwSmem) + 256, (cudaStream_t)stream>>>(
         (const __half *)enc, dirs, (const __half *)image, n, n_dev, sigmas, rgbs, (__half *)hid_s, (__half *)h,
         (__half *)hid_r);
     B2N_LAUNCH_CHECK();
@@ -282,12 +280,12 @@ extern "C" int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2
 //                                  all tiles of the CTA and are flushed once with red.global.add)
 //   dgrad:  g_prev = g . W        (M = 128 samples; W read MN-major from the canonical weight image)
 // then the epilogue threads apply ReLU' / TruncExp' and write the fp16 gradient tile of the next step.
-// Activation rows of the next step are fetched from global memory while the current step's MMAs run.
+// Activation tiles of the next step are fetched from global memory (coalesced) while the current MMAs run.
 // TMEM columns: [0,64) dgrad work | [64,80) dW5^T | [80,144) dW4 | [144,176) dW3 | [176,192) dW2^T | [192,224) dW1.
 struct FieldBwSmem {
-    __half w[IMG_HALVES];          // 20480 B
-    __half act[2][128 * 64];       // 32768 B  activation tiles (ping-pong)
-    __half g[2][128 * 64];         // 32768 B  gradient tiles   (ping-pong)
+    __half w[IMG_HALVES];                      // 20480 B
+    unsigned char act[2][TILE64_BYTES];        // 33024 B  activation tiles (ping-pong)
+    unsigned char g[2][TILE64_BYTES];          // 33024 B  gradient tiles   (ping-pong)
     uint64_t bar_w, bar_mma;
     uint32_t tmem_base;
 };
@@ -320,37 +318,18 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t g_tile, ui
     }
 }
 
-__device__ __forceinline__ void load_row64(const __half *src, bool live, unsigned char *tile, int r) {
+// g_next = (act > 0) ? v : 0 for this thread's 64 columns, packed to fp16 into its row of g_tile
+__device__ __forceinline__ void relu_bw_to_tile(const float *v, const unsigned char *act_tile, unsigned char *g_tile, int r) {
     #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (live) v = __ldg(reinterpret_cast<const uint4 *>(src) + c);
-        *reinterpret_cast<uint4 *>(tile + act_off(r, c)) = v;
-    }
-}
-
-// masked = (act > 0) ? g : 0 for 16 columns starting at c16*16, packed to fp16 into tile chunks 2*c16, 2*c16+1
-__device__ __forceinline__ void relu_bw_store(const float *v, const unsigned char *act_tile, unsigned char *g_tile,
-                                              int r, int c16) {
-    float o[16];
-    #pragma unroll
-    for (int half8 = 0; half8 < 2; ++half8) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, 2 * c16 + half8));
+        const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, c));
         const __half *ah = reinterpret_cast<const __half *>(&a);
+        float o[8];
         #pragma unroll
-        for (int j = 0; j < 8; ++j) o[half8 * 8 + j] = (__half2float(ah[j]) > 0.f) ? v[half8 * 8 + j] : 0.f;
+        for (int j = 0; j < 8; ++j) o[j] = (__half2float(ah[j]) > 0.f) ? v[8 * c + j] : 0.f;
+        *reinterpret_cast<uint4 *>(g_tile + act_off(r, c)) = pack8(o);
     }
-    *reinterpret_cast<uint4 *>(g_tile + act_off(r, 2 * c16)) = pack8(o);
-    *reinterpret_cast<uint4 *>(g_tile + act_off(r, 2 * c16 + 1)) = pack8(o + 8);
 }
-
-#define STEP_SYNC()            \
-    do {                       \
-        fence_async_smem();    \
-        fence_before_sync();   \
-        __syncthreads();       \
-        fence_after_sync();    \
-    } while (0)
 
 __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
     const float *__restrict__ dL_dsigmas, const float *__restrict__ dL_drgbs, const __half *__restrict__ enc,
@@ -386,13 +365,13 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
     const uint32_t w_addr = smem_u32(S.w);
     const uint32_t act_a[2] = {smem_u32(S.act[0]), smem_u32(S.act[1])};
     const uint32_t g_a[2] = {smem_u32(S.g[0]), smem_u32(S.g[1])};
-    unsigned char *ACT[2] = {reinterpret_cast<unsigned char *>(S.act[0]), reinterpret_cast<unsigned char *>(S.act[1])};
-    unsigned char *G[2] = {reinterpret_cast<unsigned char *>(S.g[0]), reinterpret_cast<unsigned char *>(S.g[1])};
+    unsigned char *ACT[2] = {S.act[0], S.act[1]};
+    unsigned char *G[2] = {S.g[0], S.g[1]};
     uint32_t phase = 0;
     bool acc = false;          // wgrad accumulators hold data from an earlier tile
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t row = tile * 128 + tid;
+        const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
         // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G0 [128x16]; hid_r2 -> ACT0; hid_r1 -> ACT1
         {
@@ -408,8 +387,8 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
             }
             *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 0)) = pack8(g5);
             *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 1)) = pack8(g5 + 8);
-            load_row64(hid_r + ((int64_t)1 * n_alloc + row) * 64, live, ACT[0], tid);
-            load_row64(hid_r + row * 64, live, ACT[1], tid);
+            tile_load<8>(ACT[0], hid_r + (n_alloc + row0) * 64, rows_valid, tid);
+            tile_load<8>(ACT[1], hid_r + row0 * 64, rows_valid, tid);
         }
         STEP_SYNC();
         // ---- step A: layer 5 (64 -> 16)
@@ -420,11 +399,10 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
         }
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-            float v[16];
-            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
-            relu_bw_store(v, ACT[0], G[1], tid, c16);                        // g4 = . * (hid_r2 > 0)
+        {
+            float v[64];
+            tmem_ld64(tmem_row + TM_WORK, v);
+            relu_bw_to_tile(v, ACT[0], G[1], tid);                           // g4 = . * (hid_r2 > 0)
         }
         STEP_SYNC();
         // ---- step B: layer 4 (64 -> 64)
@@ -434,32 +412,21 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
             mma_commit(&S.bar_mma);
         }
         {   // while the MMAs run: colour-net input [SH16 | h16] -> ACT0 (its last readers finished in step A)
-            float dx = 0.f, dy = 0.f, dz = 1.f;
+            sh_to_tile(dirs, row, live, ACT[0], tid);
             uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
             if (live) {
-                dx = __ldg(dirs + 3 * row); dy = __ldg(dirs + 3 * row + 1); dz = __ldg(dirs + 3 * row + 2);
                 h0 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16));
                 h1 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16) + 1);
             }
-            const float inv = 1.0f / sqrtf(dx * dx + dy * dy + dz * dz);
-            float sh[16];
-            sh4_eval_dev(dx * inv, dy * inv, dz * inv, sh);
-            if (!live) {
-                #pragma unroll
-                for (int i = 0; i < 16; ++i) sh[i] = 0.f;
-            }
-            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 0)) = pack8(sh);
-            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 1)) = pack8(sh + 8);
             *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 2)) = h0;
             *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 3)) = h1;
         }
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-            float v[16];
-            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
-            relu_bw_store(v, ACT[1], G[0], tid, c16);                        // g3 = . * (hid_r1 > 0)
+        {
+            float v[64];
+            tmem_ld64(tmem_row + TM_WORK, v);
+            relu_bw_to_tile(v, ACT[1], G[0], tid);                           // g3 = . * (hid_r1 > 0)
         }
         STEP_SYNC();
         // ---- step C: layer 3 (32 -> 64)
@@ -468,7 +435,7 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
             issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W3 * 2, 32, 64);  // g_in3 = g3 . W3
             mma_commit(&S.bar_mma);
         }
-        load_row64(hid_s + row * 64, live, ACT[1], tid);                      // prefetch hid_s
+        tile_load<8>(ACT[1], hid_s + row0 * 64, rows_valid, tid);             // prefetch hid_s
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
         {
@@ -488,21 +455,13 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
             issue_dgrad(tmem + TM_WORK, g_a[1], w_addr + IMG_W2 * 2, 64, 16);  // g1 = g2 . W2
             mma_commit(&S.bar_mma);
         }
-        {   // prefetch enc -> ACT0 [128x32]
-            #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (live) v = __ldg(reinterpret_cast<const uint4 *>(enc + row * 32) + c);
-                *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, c)) = v;
-            }
-        }
+        tile_load<4>(ACT[0], enc + row0 * 32, rows_valid, tid);               // prefetch enc -> ACT0 [128x32]
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-            float v[16];
-            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
-            relu_bw_store(v, ACT[1], G[0], tid, c16);                        // g1 = . * (hid_s > 0)
+        {
+            float v[64];
+            tmem_ld64(tmem_row + TM_WORK, v);
+            relu_bw_to_tile(v, ACT[1], G[0], tid);                           // g1 = . * (hid_s > 0)
         }
         STEP_SYNC();
         // ---- step E: layer 1 (32 -> 64)
@@ -513,19 +472,18 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
         }
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
-        #pragma unroll
-        for (int c16 = 0; c16 < 2; ++c16) {
-            float v[16];
-            tmem_ld16(tmem_row + TM_WORK + c16 * 16, v);
-            if (live) {
-                uint4 *dst = reinterpret_cast<uint4 *>(dL_denc + row * 32 + c16 * 16);
-                dst[0] = pack8(v); dst[1] = pack8(v + 8);
-            }
+        {   // dL/denc: own row -> G1 tile, then one coalesced copy to global
+            float v[32];
+            tmem_ld16(tmem_row + TM_WORK, v);
+            tmem_ld16(tmem_row + TM_WORK + 16, v + 16);
+            #pragma unroll
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(G[1] + act_off(tid, c)) = pack8(v + 8 * c);
         }
         acc = true;
         fence_before_sync();
         __syncthreads();
         fence_after_sync();
+        tile_store<4>(G[1], dL_denc + row0 * 32, rows_valid, tid);
     }
     // ---- flush the weight gradients: M = 64 accumulators sit in lanes 32*w + (0..15) <-> rows 16*w + lane
     {
@@ -562,10 +520,10 @@ extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, 
     if (n <= 0) return 0;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(field_mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldBwSmem) + 1024);
+        cudaFuncSetAttribute(field_mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldBwSmem) + 256);
         attr_set = true;
     }
-    field_mlp_bw_kernel<<<b2n_grid((n + 127) / 128, 2), 128, sizeof(FieldBwSmem) + 1024, (cudaStream_t)stream>>>(
+    field_mlp_bw_kernel<<<b2n_grid((n + 127) / 128, 2), 128, sizeof(FieldBwSmem) + 256, (cudaStream_t)stream>>>(
         dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)hid_s,
         (const __half *)h, (const __half *)hid_r, grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w);
     B2N_LAUNCH_CHECK();

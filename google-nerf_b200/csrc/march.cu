@@ -10,16 +10,27 @@
 // parallel (one L2-latency per 32 rungs instead of one per rung), then resolve which rungs the serial
 // loop would have visited with ballots and a short uniform walk over the empty rungs; emitted samples are
 // compacted with a popcount rank.  Results are bit-identical to the serial loop (oracle cross-check).
+//
+// The ladder itself is a serial fp32 recurrence, but where the step is constant (exp_step_factor == 0, or the
+// clamped ends of the exponential schedule) and the 32 rungs stay inside one binade, repeated rounding adds
+// a constant increment q = fl(t + dt) - t, so rung j = t + j*q exactly and every lane computes its rung in
+// O(1); chunks that cross a binade, hit a rounding tie or sit in the geometric part fall back to the serial
+// recurrence.  The count pass records each chunk's emission mask (64 words per ray) so that the write pass
+// replays the ladder without touching the bitfield again.
 #include "common.cuh"
 
 #define SQRT3 1.73205080757f
 #define FULL 0xffffffffu
+#define MAX_MIPS 16
+#define WS_WORDS 64          // workspace words per ray: [0] = n_chunks | overflow << 31, [1..63] = chunk masks
+#define MAX_CHUNKS (WS_WORDS - 1)
 
 struct MarchParams {
     const uint8_t *bitfield;
     int cascades, grid_size, max_samples;
     float scale, esf, dt_lo, dt_hi, dt0, g_inv;  // dt0 = calc_dt for esf == 0 (constant step)
     uint32_t g3;
+    float mip_bound[MAX_MIPS], mip_bound_inv[MAX_MIPS];   // min(2^(mip-1), scale) and its IEEE reciprocal
 };
 
 __device__ __forceinline__ float calc_dt(float t, const MarchParams &p) {
@@ -38,13 +49,16 @@ __device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &
     y = r.oy + t * r.dy;
     z = r.oz + t * r.dz;
     dt = calc_dt(t, p);
-    int e;
-    frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e);
-    int mip = min(p.cascades - 1, max(0, e + 1));
-    frexpf(dt * G, &e);
-    mip = max(mip, min(p.cascades - 1, max(0, e)));
-    const float mip_bound = fminf(__int_as_float((126 + mip) << 23), p.scale);  // scalbnf(1, mip-1)
-    const float mip_bound_inv = 1.0f / mip_bound;
+    int mip = 0;
+    if (p.cascades > 1) {
+        int e;
+        frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e);
+        mip = min(p.cascades - 1, max(0, e + 1));
+        frexpf(dt * G, &e);
+        mip = max(mip, min(p.cascades - 1, max(0, e)));
+    }
+    const float mip_bound = p.mip_bound[mip];
+    const float mip_bound_inv = p.mip_bound_inv[mip];
     const int nx = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (x * mip_bound_inv + 1) * G)));
     const int ny = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (y * mip_bound_inv + 1) * G)));
     const int nz = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (z * mip_bound_inv + 1) * G)));
@@ -57,15 +71,44 @@ __device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &
     return occ;
 }
 
-// Sample sink interfaces: count only / packed train output / (n_alive, n_samples) test output.
+// 32 rungs of the ladder starting at t_base: lane j gets f^j(t_base), t_next = f^32(t_base).
+template <bool ESF_ZERO>
+__device__ __forceinline__ void ladder(float t_base, const MarchParams &p, int lane, float &tj, float &t_next) {
+    const float dt_c = ESF_ZERO ? p.dt0 : calc_dt(t_base, p);
+    // constant-step regime over the whole chunk?  (calc_dt is monotone in t)
+    const bool constant = ESF_ZERO || (calc_dt(t_base + 33.0f * dt_c, p) == dt_c);
+    const float q = (t_base + dt_c) - t_base;             // the increment rounding actually applies
+    const float t_end = t_base + 32.0f * q;
+    const uint32_t b0 = __float_as_uint(t_base), b1 = __float_as_uint(t_end);
+    // same binade for all 33 rungs; t_base > dt_c keeps ulp(t) >= ulp(dt) (and excludes zero / negative t)
+    const bool same_binade = ((b0 ^ b1) >> 23) == 0 && (b0 >> 23) > 24 && t_base > dt_c;
+    // ulp(t_base) = 2^(e-23); a residual of exactly half an ulp is a round-to-even tie whose outcome depends on t
+    const float ulp = __uint_as_float((b0 & 0x7f800000u) - (23u << 23));
+    const bool tie = fabsf(dt_c - q) * 2.0f == ulp;
+    if (constant && same_binade && !tie) {
+        tj = t_base + (float)lane * q;                    // both the product and the sum are exact
+        t_next = t_end;
+        return;
+    }
+    float t = t_base;
+    tj = t_base;
+    #pragma unroll 8
+    for (int i = 0; i < 32; ++i) {
+        t = t + (ESF_ZERO ? p.dt0 : calc_dt(t, p));
+        if (i < lane) tj = t;
+    }
+    t_next = t;
+}
+
+// Sample sinks: count only / packed train output / (n_alive, n_samples) test output.
 struct CountSink {
     __device__ __forceinline__ void put(int, float, float, float, float, float, const Ray &) const {}
 };
-struct TrainSink {
+struct PackedSink {
     float *xyzs, *dirs, *deltas, *ts;
-    int64_t start;
+    int64_t base;
     __device__ __forceinline__ void put(int k, float x, float y, float z, float t, float dt, const Ray &r) const {
-        const int64_t s = start + k;
+        const int64_t s = base + k;
         xyzs[3 * s] = x; xyzs[3 * s + 1] = y; xyzs[3 * s + 2] = z;
         dirs[3 * s] = r.dx; dirs[3 * s + 1] = r.dy; dirs[3 * s + 2] = r.dz;
         ts[s] = t; deltas[s] = dt;
@@ -74,23 +117,20 @@ struct TrainSink {
 
 // Marches one ray with the whole warp.  Emits at most `limit` samples.  Returns the number emitted;
 // t_after_last = parameter after the last emitted sample (test marcher state), unchanged if none.
+// ws (optional): per-ray workspace that receives the emission mask of every chunk.
 template <bool ESF_ZERO, class Sink>
 __device__ __forceinline__ int march_ray(const Ray &r, float t_start, float t2, int limit,
-                                         const MarchParams &p, const Sink &sink, float &t_after_last) {
+                                         const MarchParams &p, const Sink &sink, float &t_after_last,
+                                         uint32_t *ws) {
     const int lane = threadIdx.x & 31;
     const float NEG_INF = __int_as_float(0xff800000);
     float t_base = t_start;
     float pending = NEG_INF;  // skip target carried over from the previous chunk
-    int n = 0;
+    int n = 0, chunk = 0;
+    bool ws_overflow = false;
     while (true) {
-        // ---- ladder: lane j gets t_j = f^j(t_base); lane 31 also produces the next chunk's base
-        float t = t_base, tj = t_base, t_next;
-        #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            t = t + (ESF_ZERO ? p.dt0 : calc_dt(t, p));
-            if (i < lane) tj = t;
-        }
-        t_next = t;  // f^32(t_base), identical on every lane
+        float tj, t_next;
+        ladder<ESF_ZERO>(t_base, p, lane, tj, t_next);
         // ---- probe all 32 rungs in parallel
         const bool valid = tj < t2;
         float dt = 0.f, x = 0.f, y = 0.f, z = 0.f, target = NEG_INF;
@@ -98,52 +138,89 @@ __device__ __forceinline__ int march_ray(const Ray &r, float t_start, float t2, 
         if (valid) occ = probe(r, tj, p, dt, x, y, z, target);
         const uint32_t valid_m = __ballot_sync(FULL, valid);
         const uint32_t occ_m = __ballot_sync(FULL, occ) & valid_m;
-        // next rung the serial loop probes after an empty rung j: first k > j with t_k >= target_j
-        int lo = 0, hi = 32;
-        #pragma unroll
-        for (int s = 0; s < 5; ++s) {
-            const int mid = (lo + hi) >> 1;
-            const float tm = __shfl_sync(FULL, tj, mid);
-            if (tm < target) lo = mid + 1; else hi = mid;
-        }
-        const int next = max(lane + 1, lo);
-        // ---- which rungs does the serial loop visit?  (uniform walk; one iteration per visited empty rung)
-        const uint32_t reach_m = __ballot_sync(FULL, tj >= pending);
-        int cur = reach_m ? (__ffs(reach_m) - 1) : 32;
         uint32_t emit_m = 0;
-        bool done = false, carried = (cur == 32);
-        while (cur < 32) {
-            if (!((valid_m >> cur) & 1)) { done = true; break; }
-            // run of occupied rungs starting at cur
-            const uint32_t stop_m = (~occ_m) & (FULL << cur);   // first non-occupied (or invalid) rung >= cur
-            const int run_end = stop_m ? (__ffs(stop_m) - 1) : 32;
-            if (run_end > cur) emit_m |= (run_end == 32 ? FULL : ((1u << run_end) - 1)) & (FULL << cur);
-            cur = run_end;
-            if (cur == 32) break;
-            if (!((valid_m >> cur) & 1)) { done = true; break; }
-            const int nx = __shfl_sync(FULL, next, cur);
-            if (nx >= 32) { pending = __shfl_sync(FULL, target, cur); carried = true; cur = 32; }
-            else cur = nx;
+        bool done = false;
+        if (occ_m == valid_m && pending == NEG_INF) {
+            // every live rung is occupied and nothing is being skipped: the serial loop emits them all
+            emit_m = valid_m;
+            done = valid_m != FULL;
+        } else {
+            // next rung the serial loop probes after an empty rung j: first k > j with t_k >= target_j
+            int lo = 0, hi = 32;
+            #pragma unroll
+            for (int s = 0; s < 5; ++s) {
+                const int mid = (lo + hi) >> 1;
+                const float tm = __shfl_sync(FULL, tj, mid);
+                if (tm < target) lo = mid + 1; else hi = mid;
+            }
+            const int next = max(lane + 1, lo);
+            // which rungs does the serial loop visit?  (uniform walk; one iteration per visited empty rung)
+            const uint32_t reach_m = __ballot_sync(FULL, tj >= pending);
+            int cur = reach_m ? (__ffs(reach_m) - 1) : 32;
+            bool carried = (cur == 32);
+            while (cur < 32) {
+                if (!((valid_m >> cur) & 1)) { done = true; break; }
+                const uint32_t stop_m = (~occ_m) & (FULL << cur);   // first non-occupied (or invalid) rung >= cur
+                const int run_end = stop_m ? (__ffs(stop_m) - 1) : 32;
+                if (run_end > cur) emit_m |= (run_end == 32 ? FULL : ((1u << run_end) - 1)) & (FULL << cur);
+                cur = run_end;
+                if (cur == 32) break;
+                if (!((valid_m >> cur) & 1)) { done = true; break; }
+                const int nx = __shfl_sync(FULL, next, cur);
+                if (nx >= 32) { pending = __shfl_sync(FULL, target, cur); carried = true; cur = 32; }
+                else cur = nx;
+            }
+            if (!carried) pending = NEG_INF;
         }
-        if (!carried) pending = NEG_INF;
         // ---- compaction: rank among emitted rungs, honour the per-ray limit
         const int rank = __popc(emit_m & ((1u << lane) - 1));
         const int room = limit - n;
-        const int cnt = __popc(emit_m);
         const bool mine = ((emit_m >> lane) & 1) && rank < room;
         if (mine) sink.put(n + rank, x, y, z, tj, dt, r);
-        const int took = min(cnt, room);
+        const int took = min(__popc(emit_m), room);
         if (took > 0) {
-            // parameter after the last emitted sample: the lane holding rank == took-1
             const uint32_t last_m = __ballot_sync(FULL, mine && rank == took - 1);
             t_after_last = __shfl_sync(FULL, tj + dt, __ffs(last_m) - 1);
         }
+        if (ws != nullptr) {
+            if (chunk < MAX_CHUNKS) {
+                const uint32_t took_m = __ballot_sync(FULL, mine);
+                if (lane == 0) ws[1 + chunk] = took_m;
+            } else {
+                ws_overflow = true;
+            }
+        }
+        ++chunk;
         n += took;
         if (done || n >= limit) break;
         t_base = t_next;
         if (!(t_base < t2)) break;  // the next chunk's first rung already fails the loop test
     }
+    if (ws != nullptr && lane == 0) ws[0] = (uint32_t)min(chunk, MAX_CHUNKS) | (ws_overflow ? 0x80000000u : 0u);
     return n;
+}
+
+// Write pass from recorded masks: recompute the ladder, no bitfield access.
+template <bool ESF_ZERO>
+__device__ __forceinline__ void replay_ray(const Ray &r, float t_start, int n_chunks, int limit,
+                                           const MarchParams &p, const PackedSink &sink, const uint32_t *ws) {
+    const int lane = threadIdx.x & 31;
+    float t_base = t_start;
+    int n = 0;
+    for (int c = 0; c < n_chunks && n < limit; ++c) {
+        float tj, t_next;
+        ladder<ESF_ZERO>(t_base, p, lane, tj, t_next);
+        const uint32_t m = __ldg(ws + 1 + c);
+        if (m != 0) {
+            const int rank = __popc(m & ((1u << lane) - 1));
+            if (((m >> lane) & 1) && n + rank < limit) {
+                const float x = r.ox + tj * r.dx, y = r.oy + tj * r.dy, z = r.oz + tj * r.dz;
+                sink.put(n + rank, x, y, z, tj, calc_dt(tj, p), r);
+            }
+            n += __popc(m);
+        }
+        t_base = t_next;
+    }
 }
 
 __device__ __forceinline__ Ray load_ray(const float *rays_o, const float *rays_d, int64_t r) {
@@ -160,31 +237,39 @@ template <bool ESF_ZERO, bool WRITE>
 __global__ void __launch_bounds__(256) march_train_kernel(const float *__restrict__ rays_o,
                                                           const float *__restrict__ rays_d,
                                                           const float *__restrict__ hits_t,
-                                                          const float *__restrict__ noise, MarchParams p,
+                                                          const float *__restrict__ noise, const __grid_constant__ MarchParams p,
                                                           int64_t n_rays, int64_t *rays_a, float *xyzs,
-                                                          float *dirs, float *deltas, float *ts) {
+                                                          float *dirs, float *deltas, float *ts, uint32_t *workspace) {
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_rays; r += warps) {
         const Ray q = load_ray(rays_o, rays_d, r);
         float t1 = __ldg(hits_t + 2 * r);
         const float t2 = __ldg(hits_t + 2 * r + 1);
+        uint32_t *ws = workspace ? workspace + r * WS_WORDS : nullptr;
         int n = 0;
+        bool marched = false;
         if (t1 >= 0.0f) {  // the reference loop needs 0 <= t; a miss (-1) emits nothing
             t1 += calc_dt(t1, p) * __ldg(noise + r);
             float unused;
             if (t1 < t2) {
                 if (WRITE) {
                     const int limit = (int)rays_a[3 * r + 2];
-                    TrainSink sink{xyzs, dirs, deltas, ts, rays_a[3 * r + 1]};
-                    if (limit > 0) n = march_ray<ESF_ZERO>(q, t1, t2, limit, p, sink, unused);
+                    PackedSink sink{xyzs, dirs, deltas, ts, rays_a[3 * r + 1]};
+                    if (limit > 0) {
+                        const uint32_t head = ws ? __ldg(ws) : 0x80000000u;
+                        if (head & 0x80000000u) march_ray<ESF_ZERO>(q, t1, t2, limit, p, sink, unused, nullptr);
+                        else replay_ray<ESF_ZERO>(q, t1, (int)head, limit, p, sink, ws);
+                    }
                 } else {
-                    n = march_ray<ESF_ZERO>(q, t1, t2, p.max_samples, p, CountSink{}, unused);
+                    n = march_ray<ESF_ZERO>(q, t1, t2, p.max_samples, p, CountSink{}, unused, ws);
+                    marched = true;
                 }
             }
         }
         if (!WRITE && (threadIdx.x & 31) == 0) {
             rays_a[3 * r] = r;
             rays_a[3 * r + 2] = n;
+            if (ws && !marched) ws[0] = 0;
         }
     }
 }
@@ -244,7 +329,8 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(int64_t *rays_a, int64
 
 static int fill_params(MarchParams &p, const uint8_t *bitfield, int cascades, float scale, float esf,
                        int grid_size, int max_samples) {
-    B2N_CHECK_ARG(cascades >= 1 && grid_size >= 1 && grid_size <= 1024 && max_samples >= 1, "bad marcher config");
+    B2N_CHECK_ARG(cascades >= 1 && cascades <= MAX_MIPS && grid_size >= 1 && grid_size <= 1024 && max_samples >= 1,
+                  "bad marcher config");
     p.bitfield = bitfield; p.cascades = cascades; p.grid_size = grid_size; p.max_samples = max_samples;
     p.scale = scale; p.esf = esf;
     p.dt_lo = SQRT3 / max_samples;
@@ -252,6 +338,11 @@ static int fill_params(MarchParams &p, const uint8_t *bitfield, int cascades, fl
     p.dt0 = fminf(p.dt_hi, fmaxf(p.dt_lo, 0.0f));
     p.g_inv = 1.0f / grid_size;
     p.g3 = (uint32_t)grid_size * grid_size * grid_size;
+    for (int m = 0; m < MAX_MIPS; ++m) {
+        const float b = fminf(scalbnf(1.0f, m - 1), scale);   // host fp32 = IEEE, same values as the device would compute
+        p.mip_bound[m] = b;
+        p.mip_bound_inv[m] = 1.0f / b;
+    }
     return 0;
 }
 
@@ -264,7 +355,7 @@ extern "C" int b2n_raymarching_train_count(const float *rays_o, const float *ray
                                            const uint8_t *density_bitfield, int cascades, float scale,
                                            float exp_step_factor, const float *noise, int grid_size,
                                            int max_samples, int64_t n_rays, int64_t capacity,
-                                           int64_t *rays_a, int32_t *counter, void *stream) {
+                                           int64_t *rays_a, int32_t *counter, uint32_t *workspace, void *stream) {
     MarchParams p;
     if (fill_params(p, density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples)) return 1;
     B2N_CHECK_ARG(n_rays >= 0, "n_rays < 0");
@@ -272,10 +363,10 @@ extern "C" int b2n_raymarching_train_count(const float *rays_o, const float *ray
     if (n_rays > 0) {
         if (exp_step_factor == 0.0f)
             march_train_kernel<true, false><<<march_grid(n_rays), 256, 0, st>>>(
-                rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr);
+                rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr, workspace);
         else
             march_train_kernel<false, false><<<march_grid(n_rays), 256, 0, st>>>(
-                rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr);
+                rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr, workspace);
         B2N_LAUNCH_CHECK();
     }
     march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, capacity, counter);
@@ -287,37 +378,27 @@ extern "C" int b2n_raymarching_train_write(const float *rays_o, const float *ray
                                            const uint8_t *density_bitfield, int cascades, float scale,
                                            float exp_step_factor, const float *noise, int grid_size,
                                            int max_samples, int64_t n_rays, const int64_t *rays_a,
-                                           float *xyzs, float *dirs, float *deltas, float *ts, void *stream) {
+                                           float *xyzs, float *dirs, float *deltas, float *ts,
+                                           const uint32_t *workspace, void *stream) {
     MarchParams p;
     if (fill_params(p, density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples)) return 1;
     if (n_rays <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (exp_step_factor == 0.0f)
         march_train_kernel<true, true><<<march_grid(n_rays), 256, 0, st>>>(
-            rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts);
+            rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts, (uint32_t *)workspace);
     else
         march_train_kernel<false, true><<<march_grid(n_rays), 256, 0, st>>>(
-            rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts);
+            rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts, (uint32_t *)workspace);
     B2N_LAUNCH_CHECK();
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ test
-struct TestSink {
-    float *xyzs, *dirs, *deltas, *ts;
-    int64_t base;  // n * n_samples
-    __device__ __forceinline__ void put(int k, float x, float y, float z, float t, float dt, const Ray &r) const {
-        const int64_t s = base + k;
-        xyzs[3 * s] = x; xyzs[3 * s + 1] = y; xyzs[3 * s + 2] = z;
-        dirs[3 * s] = r.dx; dirs[3 * s + 1] = r.dy; dirs[3 * s + 2] = r.dz;
-        ts[s] = t; deltas[s] = dt;
-    }
-};
-
 template <bool ESF_ZERO>
 __global__ void __launch_bounds__(256) march_test_kernel(const float *__restrict__ rays_o,
                                                          const float *__restrict__ rays_d, float *hits_t,
-                                                         const int64_t *__restrict__ alive, MarchParams p,
+                                                         const int64_t *__restrict__ alive, const __grid_constant__ MarchParams p,
                                                          int n_samples, int64_t n_alive, float *xyzs,
                                                          float *dirs, float *deltas, float *ts,
                                                          int32_t *n_eff) {
@@ -327,10 +408,10 @@ __global__ void __launch_bounds__(256) march_test_kernel(const float *__restrict
         const int64_t r = alive[n];
         const Ray q = load_ray(rays_o, rays_d, r);
         const float t1 = hits_t[2 * r], t2 = hits_t[2 * r + 1];
-        TestSink sink{xyzs, dirs, deltas, ts, n * n_samples};
+        PackedSink sink{xyzs, dirs, deltas, ts, n * n_samples};
         float t_after = t1;
         int s = 0;
-        if (t1 < t2) s = march_ray<ESF_ZERO>(q, t1, t2, n_samples, p, sink, t_after);
+        if (t1 < t2) s = march_ray<ESF_ZERO>(q, t1, t2, n_samples, p, sink, t_after, nullptr);
         // unused slots stay zero (rendering.py:87 relies on dirs == 0 to find them)
         for (int k = s + lane; k < n_samples; k += 32) {
             const int64_t o = n * n_samples + k;

@@ -82,6 +82,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// four 16-column loads in flight, one wait: v[0..63] = columns c..c+63 of this thread's lane
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float *v) {
+    uint32_t r[64];
+    #pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[16 * q + 0]), "=r"(r[16 * q + 1]), "=r"(r[16 * q + 2]), "=r"(r[16 * q + 3]), "=r"(r[16 * q + 4]),
+              "=r"(r[16 * q + 5]), "=r"(r[16 * q + 6]), "=r"(r[16 * q + 7]), "=r"(r[16 * q + 8]), "=r"(r[16 * q + 9]),
+              "=r"(r[16 * q + 10]), "=r"(r[16 * q + 11]), "=r"(r[16 * q + 12]), "=r"(r[16 * q + 13]),
+              "=r"(r[16 * q + 14]), "=r"(r[16 * q + 15])
+            : "r"(taddr + 16 * q)
+            : "memory");
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    #pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- coalesced copies between a canonical tile and row-major global memory ---------------------------
+// NCH = 16-byte chunks per row.  Thread mapping: consecutive threads take consecutive chunks of a row, so every
+// warp-level global access covers whole 128-byte lines, and (thanks to the ACT_LBO padding) the shared-memory
+// side is conflict free.  rows_valid = number of rows of this tile that exist in global memory.
+template <int NCH>
+__device__ __forceinline__ void tile_load(unsigned char *tile, const __half *g_row0, int64_t rows_valid, int tid) {
+    #pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int j = i * 128 + tid, row = j / NCH, c = j % NCH;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (row < rows_valid) v = __ldg(reinterpret_cast<const uint4 *>(g_row0 + (int64_t)row * (NCH * 8)) + c);
+        *reinterpret_cast<uint4 *>(tile + (uint32_t)c * 2064u + (uint32_t)row * 16) = v;
+    }
+}
+template <int NCH>
+__device__ __forceinline__ void tile_store(const unsigned char *tile, __half *g_row0, int64_t rows_valid, int tid) {
+    #pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int j = i * 128 + tid, row = j / NCH, c = j % NCH;
+        const uint4 v = *reinterpret_cast<const uint4 *>(tile + (uint32_t)c * 2064u + (uint32_t)row * 16);
+        if (row < rows_valid) *(reinterpret_cast<uint4 *>(g_row0 + (int64_t)row * (NCH * 8)) + c) = v;
+    }
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -112,9 +155,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 
 // ---- canonical (no-swizzle) tile addressing ------------------------------------------------------
-// activation tile [128 rows x K]: 16-byte chunk c of row r lives at  c*2048 + (r/8)*128 + (r%8)*16
+// activation tile [128 rows x K]: 16-byte chunk c of row r lives at  c*ACT_LBO + (r/8)*128 + (r%8)*16 = c*ACT_LBO + r*16.
+// ACT_LBO carries 16 bytes of padding per chunk plane so that BOTH access patterns are bank-conflict free:
+// "thread = row, fixed chunk" (epilogue) and "8 threads = the 8 chunks of one row" (coalesced global copies).
 constexpr uint32_t ACT_SBO = 128;    // between 8-row groups
-constexpr uint32_t ACT_LBO = 2048;   // between 16-byte K chunks (16 row groups x 128 B)
+constexpr uint32_t ACT_LBO = 2064;   // between 16-byte K chunks (16 row groups x 128 B + 16 B pad)
+constexpr uint32_t TILE16_BYTES = 2 * ACT_LBO, TILE32_BYTES = 4 * ACT_LBO, TILE64_BYTES = 8 * ACT_LBO;
 __device__ __forceinline__ uint32_t act_off(int r, int chunk) {
     return (uint32_t)chunk * ACT_LBO + (uint32_t)(r >> 3) * ACT_SBO + (uint32_t)(r & 7) * 16;
 }

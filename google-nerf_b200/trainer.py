@@ -68,6 +68,7 @@ class NGPTrainer:
         self.rays_o, self.rays_d, self.target = e(n, 3), e(n, 3), e(n, 3)
         self.hits_cnt = e(n, dt=torch.int32); self.hits_t = e(n, 1, 2); self.hits_idx = e(n, 1, dt=torch.int64)
         self.noise = e(n)
+        self.march_ws = e(n, 64, dt=torch.int32)
         self.rays_a = e(n, 3, dt=torch.int64); self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
         self.xyzs, self.dirs, self.deltas, self.ts = e(cap, 3), e(cap, 3), e(cap), e(cap)
         self.enc = e(cap, 32, dt=_f16); self.hid_s = e(cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
@@ -97,8 +98,9 @@ class NGPTrainer:
             self.noise.copy_(self.fixed_noise)
         march = (P(self.rays_o), P(self.rays_d), P(self.hits_t), P(m.density_bitfield), m.cascades, float(m.scale),
                  float(self.esf), P(self.noise), m.grid_size, MAX_SAMPLES, n)
-        call("b2n_raymarching_train_count", *march, cap, P(self.rays_a), P(self.counter))
-        call("b2n_raymarching_train_write", *march, P(self.rays_a), P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts))
+        call("b2n_raymarching_train_count", *march, cap, P(self.rays_a), P(self.counter), P(self.march_ws))
+        call("b2n_raymarching_train_write", *march, P(self.rays_a), P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts),
+             P(self.march_ws))
         # field forward: hash-grid gather, then the fused tcgen05 MLP chain (sigma + colour)
         call("b2n_hashgrid_fw", P(self.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
         call("b2n_field_mlp_fw", P(self.enc), P(self.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),

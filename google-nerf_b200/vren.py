@@ -73,18 +73,19 @@ def packbits(density_grid, density_threshold, density_bitfield, threshold_dev=No
 
 def raymarching_train_count(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise,
                             grid_size, max_samples, capacity=-1):
-    """First half of raymarching_train: -> rays_a (N_rays,3) i64, counter (4) i32 (device), no host sync."""
+    """First half of raymarching_train: -> rays_a (N_rays,3) i64, counter (4) i32 (device), workspace; no host sync."""
     n, dev = rays_o.shape[0], rays_o.device
     rays_a = torch.empty(n, 3, dtype=torch.int64, device=dev)
     counter = torch.empty(4, dtype=torch.int32, device=dev)
+    workspace = torch.empty(n, 64, dtype=torch.int32, device=dev)        # per-chunk emission masks for the write pass
     L.call("b2n_raymarching_train_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(hits_t), L.ptr(density_bitfield),
            int(cascades), float(scale), float(exp_step_factor), L.ptr(noise), int(grid_size), int(max_samples),
-           n, int(capacity), L.ptr(rays_a), L.ptr(counter))
-    return rays_a, counter
+           n, int(capacity), L.ptr(rays_a), L.ptr(counter), L.ptr(workspace))
+    return rays_a, counter, workspace
 
 
 def raymarching_train_write(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise,
-                            grid_size, max_samples, rays_a, n_rows):
+                            grid_size, max_samples, rays_a, n_rows, workspace=None):
     dev = rays_o.device
     xyzs = torch.empty(n_rows, 3, dtype=_f32, device=dev)
     dirs = torch.empty(n_rows, 3, dtype=_f32, device=dev)
@@ -92,7 +93,7 @@ def raymarching_train_write(rays_o, rays_d, hits_t, density_bitfield, cascades, 
     ts = torch.empty(n_rows, dtype=_f32, device=dev)
     L.call("b2n_raymarching_train_write", L.ptr(rays_o), L.ptr(rays_d), L.ptr(hits_t), L.ptr(density_bitfield),
            int(cascades), float(scale), float(exp_step_factor), L.ptr(noise), int(grid_size), int(max_samples),
-           rays_o.shape[0], L.ptr(rays_a), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.ptr(ts))
+           rays_o.shape[0], L.ptr(rays_a), L.ptr(xyzs), L.ptr(dirs), L.ptr(deltas), L.ptr(ts), L.ptr(workspace))
     return xyzs, dirs, deltas, ts
 
 
@@ -102,9 +103,9 @@ def raymarching_train(rays_o, rays_d, hits_t, density_bitfield, cascades, scale,
     rays_o, rays_d, hits_t, noise = (_prep(v) for v in (rays_o, rays_d, hits_t, noise))
     L.require_cuda(density_bitfield)
     args = (rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples)
-    rays_a, counter = raymarching_train_count(*args)
+    rays_a, counter, workspace = raymarching_train_count(*args)
     total = int(counter[0].item())      # the one host sync the reference API forces (custom_functions.py:92)
-    xyzs, dirs, deltas, ts = raymarching_train_write(*args, rays_a, total)
+    xyzs, dirs, deltas, ts = raymarching_train_write(*args, rays_a, total, workspace)
     return rays_a, xyzs, dirs, deltas, ts, counter
 
 

@@ -60,17 +60,19 @@ B2N_API int b2n_packbits(const float *density_grid, int64_t n_bytes, float thres
  * prefix sum of N in ray order, and counter (4) i32 = [total, n_rays, overflow, unclamped_total]; _write
  * re-marches and writes xyzs, dirs (total,3), deltas, ts (total).
  * capacity >= 0 clamps: rays whose samples would pass `capacity` rows are truncated (N reduced) and
- * counter[2] is set; capacity < 0 = unbounded.  hits_t (n_rays,2); noise (n_rays) in [0,1). */
+ * counter[2] is set; capacity < 0 = unbounded.  hits_t (n_rays,2); noise (n_rays) in [0,1).
+ * workspace (optional, may be NULL in both): 64 uint32 per ray; _count records every 32-rung chunk's emission
+ * mask there and _write then replays them without reading the bitfield again. */
 B2N_API int b2n_raymarching_train_count(const float *rays_o, const float *rays_d, const float *hits_t,
                                 const uint8_t *density_bitfield, int cascades, float scale,
                                 float exp_step_factor, const float *noise, int grid_size,
                                 int max_samples, int64_t n_rays, int64_t capacity, int64_t *rays_a,
-                                int32_t *counter, void *stream);
+                                int32_t *counter, uint32_t *workspace, void *stream);
 B2N_API int b2n_raymarching_train_write(const float *rays_o, const float *rays_d, const float *hits_t,
                                 const uint8_t *density_bitfield, int cascades, float scale,
                                 float exp_step_factor, const float *noise, int grid_size,
                                 int max_samples, int64_t n_rays, const int64_t *rays_a, float *xyzs,
-                                float *dirs, float *deltas, float *ts, void *stream);
+                                float *dirs, float *deltas, float *ts, const uint32_t *workspace, void *stream);
 /* vren.raymarching_test (models/rendering.py:79-83).  hits_t (n_rays,2) is advanced IN PLACE;
  * outputs (n_alive,n_samples[,3]) are fully written (unused slots zero); n_eff (n_alive) i32. */
 B2N_API int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,

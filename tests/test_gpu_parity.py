@@ -130,12 +130,14 @@ def test_raymarching_train_capacity_clamp(mods, scene05):
     full = mods["C"].raymarching_train(s["rays_o"], s["rays_d"], hits_t, s["bitfield"], 1, 0.5, 0.0, s["noise"], 128, 1024)
     total = int(full[5][0]); cap = total // 2
     args = (d["rays_o"], d["rays_d"], hits_t.to(DEV), d["bitfield"], 1, 0.5, 0.0, d["noise"], 128, 1024)
-    rays_a, counter = mods["vren"].raymarching_train_count(*args, capacity=cap)
+    rays_a, counter, ws = mods["vren"].raymarching_train_count(*args, capacity=cap)
     c = counter.cpu()
     assert int(c[0]) == cap and int(c[2]) == 1 and int(c[3]) == total
     assert int((rays_a[:, 1] + rays_a[:, 2]).max()) <= cap
-    xyzs, dirs, deltas, ts = mods["vren"].raymarching_train_write(*args, rays_a, cap)
-    assert torch.equal(xyzs.cpu(), full[1][:cap]) and torch.equal(ts.cpu(), full[4][:cap])
+    for workspace in (ws, None):                                   # mask replay and full re-march must agree
+        xyzs, dirs, deltas, ts = mods["vren"].raymarching_train_write(*args, rays_a, cap, workspace)
+        assert torch.equal(xyzs.cpu(), full[1][:cap]) and torch.equal(ts.cpu(), full[4][:cap])
+        assert torch.equal(deltas.cpu(), full[3][:cap]) and torch.equal(dirs.cpu(), full[2][:cap])
 
 
 @pytest.mark.parametrize("scale,esf", [(0.5, 0.0), (4.0, 1 / 256)])
@@ -196,7 +198,8 @@ def test_composite_train_fw_bw(mods, scene05, sigma_max, thr):
     # the sigma gradient is a difference of large terms: compare against its own scale
     scale_s = rb[0].abs().max().item() + 1e-12
     assert (gb[0].cpu() - rb[0]).abs().max().item() <= 2e-5 * scale_s
-    torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-6 * rb[1].abs().max().item())
+    # a = 1 - exp(-x) cancels for small x, so one ulp of expf shows up as ~1e-7 absolute in w = a*T
+    torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-6)
 
 
 def test_composite_uniform_slab_closed_form(mods):
