@@ -157,7 +157,8 @@ def profile_kernels(tr, reps=5):
     L.call = timed
     try:
         for _ in range(reps):
-            tr.step_count += 1; tr._set_hyper(); tr._body()
+            sset = tr.sets[tr.cur]
+            tr.step_count += 1; tr._set_hyper(); tr._march(sset); tr._forward_backward(sset); tr._optimizer()
         torch.cuda.synchronize()
     finally:
         L.call = orig
@@ -215,16 +216,23 @@ def main():
     img_dev, pix_dev, rgb_dev = img_all.to(dev), pix_all.to(dev), rgb_all.to(dev)
 
     it = [0]
+    dev_batch = lambda i: {"img_idxs": img_dev[i], "pix_idxs": pix_dev[i], "rgb": rgb_dev[i]}
+    host_batch = lambda i: {"img_idxs": img_all[i], "pix_idxs": pix_all[i], "rgb": rgb_all[i]}
+    primed = [False]
+
+    def _step(make):
+        # like a prefetching DataLoader (train.py:126-131) the next batch is handed over with the current step, so
+        # its rays are generated and marched while this step's backward runs
+        i = it[0]; it[0] += 1
+        cur = None if primed[0] else make(i)
+        primed[0] = True
+        return tr.step_batch(cur, next_batch=make(i + 1))
 
     def dev_step():                       # inputs already resident in HBM
-        i = it[0]; it[0] += 1
-        tr.set_batch_indices(img_dev[i], pix_dev[i], rgb_dev[i])
-        return tr.step()
+        return _step(dev_batch)
 
-    def host_step():                      # the call a user makes: host batch in, loss out
-        i = it[0]; it[0] += 1
-        loss = tr.step_batch({"img_idxs": img_all[i], "pix_idxs": pix_all[i], "rgb": rgb_all[i]})
-        return float(loss.item())
+    def host_step():                      # the call a user makes: host (pinned) batch in, loss out
+        return float(_step(host_batch).item())
 
     def barrier():
         if world > 1:
@@ -235,12 +243,12 @@ def main():
     for i in range(args.pretrain):
         dev_step()
         if i % 32 == 31 and tr.overflowed():
-            tr.grow(1.5)
+            tr.grow(1.5); primed[0] = False
     for _ in range(max(args.warmup, 3)):
         dev_step()
     barrier()
     if tr.overflowed():
-        tr.grow(1.5)
+        tr.grow(1.5); primed[0] = False
         for _ in range(3):
             dev_step()
         barrier()

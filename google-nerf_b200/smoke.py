@@ -26,11 +26,12 @@ def run(device):
     model.rgb_net.params.data.copy_(ref.rgb_params.detach())
     model.density_bitfield.copy_(ref.density_bitfield)
     tr = NGPTrainer(model, n_rays=n, use_graph=False, samples_per_ray=160, warmup_steps=0, grid_update_interval=10 ** 9)
-    tr.step_count = 1                                      # skip the grid update: the bitfield is the analytic one
+    tr.step_count = 2                                      # no grid update: the bitfield is the analytic one
     tr.fixed_noise = noise.to(device)
     tr.set_batch(rays_o.to(device), rays_d.to(device), target.to(device))
     p_before = tr.p_xyz.clone()
-    tr.step_count += 1; tr._set_hyper(); tr._forward_backward()
+    sset = tr.sets[tr.cur]
+    tr._set_hyper(); tr._march(sset); tr._forward_backward(sset); tr.last_counter = sset.counter
     g_xyz, g_rgb = tr.g_xyz.clone() / tr.loss_scale, tr.g_rgb.clone() / tr.loss_scale
     loss_gpu = float(tr.loss.item())
     n_samples = tr.samples_last_step()

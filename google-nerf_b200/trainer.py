@@ -1,12 +1,19 @@
 """NGPTrainer: one training step of ngp_pl/train.py:144-170 (render -> NeRFLoss -> backward -> FusedAdam,
 density-grid update every 16 steps) run directly on the libb2n kernels, without autograd, on pre-allocated
-buffers and with every count kept on the device, so the whole step can be replayed as one CUDA graph.
+buffers and with every count kept on the device, so the whole step is replayed as one CUDA graph.
+
+Pipelining: ray generation + AABB + marching of batch k+1 depend only on the occupancy bitfield, not on the
+weights, and the marcher is instruction-issue bound while the field backward is latency bound.  When the caller
+hands over the next batch (the reference's DataLoader always has it, train.py:126-131) the graph of step k has two
+branches: [field forward .. Adam on batch k] and [march batch k+1 into the other sample set].  Steps that are
+followed by a density-grid update are not pre-marched, so every batch is marched against exactly the bitfield
+the sequential reference loop would use.
 
 Data-parallel: one process per GPU, each with its own ray batch (like PL DDP at
 train.py:262-263); gradients of the two flat parameters are summed with NCCL all-reduce and averaged, and the
 occupancy grid is max-reduced after every update so that all ranks march the same bitfield.
 """
-import math
+import struct
 
 import torch
 import torch.distributed as dist
@@ -17,6 +24,23 @@ from . import vren
 from .models.rendering import MAX_SAMPLES, NEAR_DISTANCE
 
 _f16, _f32 = torch.float16, torch.float32
+
+
+class _SampleSet:
+    """Inputs of one batch and the packed samples the marcher produces from them."""
+
+    def __init__(self, n, cap, dev):
+        e = lambda *s, dt=_f32: torch.empty(*s, dtype=dt, device=dev)
+        self.rays_o, self.rays_d, self.target = e(n, 3), e(n, 3), e(n, 3)
+        self.img_idxs = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.pix_idxs = torch.zeros(n, dtype=torch.int64, device=dev)
+        self.hits_cnt = e(n, dt=torch.int32); self.hits_t = e(n, 1, 2); self.hits_idx = e(n, 1, dt=torch.int64)
+        self.noise = e(n)
+        self.march_ws = e(n, 64, dt=torch.int32)
+        self.rays_a = e(n, 3, dt=torch.int64)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)      # [0] = #samples (device-side count)
+        self.xyzs, self.dirs, self.deltas, self.ts = e(cap, 3), e(cap, 3), e(cap), e(cap)
+        self.marched = False
 
 
 class NGPTrainer:
@@ -41,8 +65,10 @@ class NGPTrainer:
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.S, self.warmup_steps = grid_update_interval, warmup_steps
         self.step_count = 0
-        self.use_graph, self.graph = use_graph, None
+        self.use_graph = use_graph
         self._from_indices = False
+        self.directions = self.poses = None
+        self.side = torch.cuda.Stream(device=self.dev)
 
         xe, rn = model.xyz_encoder, model.rgb_net
         self.n_mlp = xe.mlp.n_params
@@ -65,12 +91,8 @@ class NGPTrainer:
     def _alloc(self):
         n, cap, dev = self.n_rays, self.capacity, self.dev
         e = lambda *s, dt=_f32: torch.empty(*s, dtype=dt, device=dev)
-        self.rays_o, self.rays_d, self.target = e(n, 3), e(n, 3), e(n, 3)
-        self.hits_cnt = e(n, dt=torch.int32); self.hits_t = e(n, 1, 2); self.hits_idx = e(n, 1, dt=torch.int64)
-        self.noise = e(n)
-        self.march_ws = e(n, 64, dt=torch.int32)
-        self.rays_a = e(n, 3, dt=torch.int64); self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
-        self.xyzs, self.dirs, self.deltas, self.ts = e(cap, 3), e(cap, 3), e(cap), e(cap)
+        self.sets = [_SampleSet(n, cap, dev), _SampleSet(n, cap, dev)]
+        self.cur = 0
         self.enc = e(cap, 32, dt=_f16); self.hid_s = e(cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
         self.hid_r = e(2, cap, 64, dt=_f16)
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
@@ -80,45 +102,53 @@ class NGPTrainer:
         self.zeros_n = torch.zeros(n, device=dev)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
         self.din_enc = e(cap, 32, dt=_f16)
-        self.graph = None
+        self.last_counter = self.sets[0].counter
+        self.graphs = {}
 
     # ------------------------------------------------------------------ the step body (all on the device)
-    def _forward_backward(self):
+    def _march(self, s):
+        """ray generation (train.py:150-157) -> AABB (+ near clamp) -> occupancy marcher, into sample set s."""
         m, P, call = self.model, L.ptr, L.call
         n, cap = self.n_rays, self.capacity
-        nd = self.counter                                             # counter[0] = #samples (device)
         if self._from_indices:
-            self._gen_rays()
-        call("b2n_ray_aabb_intersect", P(self.rays_o), P(self.rays_d), P(m.center), P(m.half_size), n, 1, 1,
-             P(self.hits_cnt), P(self.hits_t), P(self.hits_idx))
-        call("b2n_clamp_near", P(self.hits_t), n, NEAR_DISTANCE)
+            # get_rays (datasets/ray_utils.py:152-175): rotate camera-frame directions, origin = camera centre
+            c2w = self.poses[s.img_idxs]
+            d = self.directions[s.pix_idxs]
+            torch.bmm(d[:, None], c2w[..., :3].transpose(1, 2), out=s.rays_d.view(-1, 1, 3))
+            s.rays_o.copy_(c2w[..., 3])
+        call("b2n_ray_aabb_intersect", P(s.rays_o), P(s.rays_d), P(m.center), P(m.half_size), n, 1, 1,
+             P(s.hits_cnt), P(s.hits_t), P(s.hits_idx))
+        call("b2n_clamp_near", P(s.hits_t), n, NEAR_DISTANCE)
         if self.fixed_noise is None:
-            self.noise.uniform_()                # default CUDA generator: graph-safe (philox offset is replayed)
+            s.noise.uniform_()                   # default CUDA generator: graph-safe (philox offset is replayed)
         else:
-            self.noise.copy_(self.fixed_noise)
-        march = (P(self.rays_o), P(self.rays_d), P(self.hits_t), P(m.density_bitfield), m.cascades, float(m.scale),
-                 float(self.esf), P(self.noise), m.grid_size, MAX_SAMPLES, n)
-        call("b2n_raymarching_train_count", *march, cap, P(self.rays_a), P(self.counter), P(self.march_ws))
-        call("b2n_raymarching_train_write", *march, P(self.rays_a), P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts),
-             P(self.march_ws))
+            s.noise.copy_(self.fixed_noise)
+        march = (P(s.rays_o), P(s.rays_d), P(s.hits_t), P(m.density_bitfield), m.cascades, float(m.scale),
+                 float(self.esf), P(s.noise), m.grid_size, MAX_SAMPLES, n)
+        call("b2n_raymarching_train_count", *march, cap, P(s.rays_a), P(s.counter), P(s.march_ws))
+        call("b2n_raymarching_train_write", *march, P(s.rays_a), P(s.xyzs), P(s.dirs), P(s.deltas), P(s.ts), P(s.march_ws))
+
+    def _forward_backward(self, s):
+        P, call = L.ptr, L.call
+        n, cap, nd = self.n_rays, self.capacity, s.counter
         # field forward: hash-grid gather, then the fused tcgen05 MLP chain (sigma + colour)
-        call("b2n_hashgrid_fw", P(self.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
-        call("b2n_field_mlp_fw", P(self.enc), P(self.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),
+        call("b2n_hashgrid_fw", P(s.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
+        call("b2n_field_mlp_fw", P(self.enc), P(s.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),
              P(self.hid_s), P(self.h), P(self.hid_r))
         # compositing + loss
-        call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.rays_a),
+        call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a),
              self.T_threshold, n, P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb))
         self.loss.zero_()
-        call("b2n_nerf_loss_fwbw", P(self.rgb), P(self.opacity), P(self.target), n, self.bg, self.lambda_opa,
+        call("b2n_nerf_loss_fwbw", P(self.rgb), P(self.opacity), P(s.target), n, self.bg, self.lambda_opa,
              self.loss_scale, P(self.rgb_out), P(self.loss), P(self.dL_drgb), P(self.dL_dopacity))
         call("b2n_composite_train_bw", P(self.dL_dopacity), P(self.zeros_n), P(self.zeros_n), P(self.dL_drgb),
-             P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.rays_a), P(self.opacity), P(self.depth),
+             P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(self.opacity), P(self.depth),
              P(self.depth_sq), P(self.rgb), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs))
         # field backward (gradients carry loss_scale; parameter gradients are unscaled inside Adam)
-        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), P(self.dirs), P(self.w_image), cap,
+        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), P(s.dirs), P(self.w_image), cap,
              P(nd), P(self.rgbs), P(self.hid_s), P(self.h), P(self.hid_r), 1.0, P(self.din_enc), P(self.g_xyz),
              P(self.g_rgb))
-        call("b2n_hashgrid_bw", P(self.xyzs), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
+        call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
              P(self.g_xyz[self.n_mlp:]))
 
     def _allreduce(self):
@@ -140,101 +170,121 @@ class NGPTrainer:
         """fp16 MLP weights -> UMMA canonical shared-memory image for the fused field kernels."""
         L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image))
 
-    # ------------------------------------------------------------------ ray generation (train.py:150-157)
+    def _train(self, p, prefetch):
+        """Train on sample set p; with prefetch, march set 1-p concurrently on the side stream (fork / join)."""
+        main = torch.cuda.current_stream()
+        if prefetch:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self._march(self.sets[1 - p])
+        self._forward_backward(self.sets[p])
+        if self.world == 1:
+            self._optimizer()
+        if prefetch:
+            main.wait_stream(self.side)
+
+    # ------------------------------------------------------------------ graphs
+    def _run(self, key, fn):
+        """Replay the CUDA graph of `fn` (captured on first use), or run it eagerly when graphs are off."""
+        if not self.use_graph:
+            fn()
+            return
+        g = self.graphs.get(key)
+        if g is None:
+            g = self._capture(fn, touches_params=key[0] in ("train", "opt"))
+            self.graphs[key] = g
+        g.replay()
+
+    def _capture(self, fn, touches_params):
+        # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
+        # count as a training step; then capture
+        state_t = (self.p_xyz, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz, self.h_rgb,
+                   self.g_xyz, self.g_rgb)
+        saved = [t.clone() for t in state_t] if touches_params else None
+        warm = torch.cuda.Stream(device=self.dev)
+        warm.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(warm):
+            fn()
+        torch.cuda.current_stream().wait_stream(warm)
+        if saved is not None:
+            for t, sv in zip(state_t, saved):
+                t.copy_(sv)
+            self._pack_weights()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    # ------------------------------------------------------------------ public API
     def set_dataset(self, directions, poses):
         """directions (H*W,3) camera-frame ray directions, poses (N_img,3,4) c2w -- the two buffers the
         reference registers at train.py:99-100.  Batches then arrive as {img_idxs, pix_idxs, rgb}."""
         self.directions = directions.to(self.dev, _f32).contiguous()
         self.poses = poses.to(self.dev, _f32).contiguous()
-        self.img_idxs = torch.zeros(self.n_rays, dtype=torch.int64, device=self.dev)
-        self.pix_idxs = torch.zeros(self.n_rays, dtype=torch.int64, device=self.dev)
-        self.graph = None
+        self.graphs = {}
 
-    def _gen_rays(self):
-        # get_rays (datasets/ray_utils.py:152-175): rotate camera-frame directions, origin = camera centre
-        c2w = self.poses[self.img_idxs]                               # (n,3,4)
-        d = self.directions[self.pix_idxs]                            # (n,3)
-        torch.bmm(d[:, None], c2w[..., :3].transpose(1, 2), out=self.rays_d.view(-1, 1, 3))
-        self.rays_o.copy_(c2w[..., 3])
+    def _load(self, s, batch, non_blocking=True):
+        """Copy one batch (host pinned or device tensors) into sample set s.  batch = (rays_o, rays_d, rgb) or the
+        reference's {img_idxs, pix_idxs, rgb} dict (datasets/base.py:28-33)."""
+        from_idx = isinstance(batch, dict)
+        if from_idx != self._from_indices:
+            self._from_indices, self.graphs = from_idx, {}
+        if from_idx:
+            if self.directions is None:
+                raise RuntimeError("set_dataset(directions, poses) must be called before index batches are used")
+            s.img_idxs.copy_(batch["img_idxs"], non_blocking=non_blocking)
+            s.pix_idxs.copy_(batch["pix_idxs"], non_blocking=non_blocking)
+            s.target.copy_(batch["rgb"], non_blocking=non_blocking)
+        else:
+            s.rays_o.copy_(batch[0], non_blocking=non_blocking)
+            s.rays_d.copy_(batch[1], non_blocking=non_blocking)
+            s.target.copy_(batch[2], non_blocking=non_blocking)
+        s.marched = False
 
-    def _body(self):
-        self._forward_backward()
-        self._allreduce()
-        self._optimizer()
-
-    # ------------------------------------------------------------------ public API
-    def set_batch(self, rays_o, rays_d, target_rgb, non_blocking=True):
-        """Copy one batch (host pinned or device tensors) into the step's input buffers."""
-        if self._from_indices:
-            self._from_indices, self.graph = False, None
-        self.rays_o.copy_(rays_o, non_blocking=non_blocking)
-        self.rays_d.copy_(rays_d, non_blocking=non_blocking)
-        self.target.copy_(target_rgb, non_blocking=non_blocking)
-
-    def set_batch_indices(self, img_idxs, pix_idxs, target_rgb, non_blocking=True):
-        """The reference's training batch (datasets/base.py:28-33): image / pixel indices + ground-truth rgb."""
-        if not self._from_indices:
-            self._from_indices, self.graph = True, None
-        self.img_idxs.copy_(img_idxs, non_blocking=non_blocking)
-        self.pix_idxs.copy_(pix_idxs, non_blocking=non_blocking)
-        self.target.copy_(target_rgb, non_blocking=non_blocking)
-
-    def step_batch(self, batch):
-        self.set_batch_indices(batch["img_idxs"], batch["pix_idxs"], batch["rgb"])
-        return self.step()
+    def set_batch(self, rays_o, rays_d, target_rgb):
+        self._load(self.sets[self.cur], (rays_o, rays_d, target_rgb))
 
     def _set_hyper(self):
-        import struct
         packed = struct.unpack("i", struct.pack("f", float(self.lr)))[0]
         self.hyper.copy_(torch.tensor([packed, self.step_count], dtype=torch.int32), non_blocking=True)
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None):
-        """One optimisation step.  Returns the (device) loss tensor of this step; no host synchronisation."""
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, next_batch=None):
+        """One optimisation step on the given (or previously set / pre-marched) batch.  `next_batch`, if given, is
+        marched concurrently for the following step.  Returns the device loss tensor; no host synchronisation."""
+        p = self.cur
+        s = self.sets[p]
         if rays_o is not None:
-            self.set_batch(rays_o, rays_d, target_rgb)
+            self._load(s, (rays_o, rays_d, target_rgb))
         if self.step_count % self.S == 0:
             self.update_density_grid(warmup=self.step_count < self.warmup_steps)
+            s.marched = False                                # (never pre-marched across an update anyway)
         self.step_count += 1
         self._set_hyper()
-        if not self.use_graph:
-            self._body()
-        else:
-            if self.graph is None:
-                self._capture()
-            if self.world == 1:
-                self.graph.replay()
-            else:                                  # NCCL all-reduce stays outside the captured graphs
-                self.graph[0].replay()
-                self._allreduce()
-                self.graph[1].replay()
+        if not s.marched:
+            self._run(("march", p), lambda: self._march(s))
+        prefetch = next_batch is not None and (self.step_count % self.S != 0)
+        if prefetch:
+            self._load(self.sets[1 - p], next_batch)
+        self._run(("train", p, prefetch), lambda: self._train(p, prefetch))
+        if self.world > 1:                                   # NCCL all-reduce stays outside the captured graphs
+            self._allreduce()
+            self._run(("opt",), self._optimizer)
+        s.marched = False
+        self.last_counter = s.counter
+        if next_batch is not None:
+            if not prefetch:
+                self._load(self.sets[1 - p], next_batch)
+            else:
+                self.sets[1 - p].marched = True
+            self.cur = 1 - p
         return self.loss
 
-    def _capture(self):
-        # warm up on a side stream (allocator, cuBLAS-free path), then capture the whole step
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        state = [t.clone() for t in (self.p_xyz, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb,
-                                      self.h_xyz, self.h_rgb)]
-        with torch.cuda.stream(s):
-            self._body()
-        torch.cuda.current_stream().wait_stream(s)
-        for t, sv in zip((self.p_xyz, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz,
-                          self.h_rgb), state):
-            t.copy_(sv)                                   # the warm-up must not count as a training step
-        self.g_xyz.zero_(); self.g_rgb.zero_()
-        self._pack_weights()
-        if self.world == 1:
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._body()
-            self.graph = g
-        else:
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._forward_backward()
-            with torch.cuda.graph(g2):
-                self._optimizer()
-            self.graph = (g1, g2)
+    def step_batch(self, batch, next_batch=None):
+        """The reference's training_step input: {img_idxs, pix_idxs, rgb}."""
+        s = self.sets[self.cur]
+        if batch is not None:
+            self._load(s, batch)
+        return self.step(next_batch=next_batch)
 
     @torch.no_grad()
     def update_density_grid(self, warmup=False):
@@ -251,16 +301,16 @@ class NGPTrainer:
 
     def overflowed(self):
         """True if the last step hit the sample capacity (host sync; call sparingly)."""
-        return bool(self.counter[2].item())
+        return bool(self.last_counter[2].item())
 
     def samples_last_step(self):
-        return int(self.counter[0].item())
+        return int(self.last_counter[0].item())
 
     def grow(self, factor=1.5):
         self.capacity = int(self.capacity * factor)
         self._alloc()
 
     def sync_model(self):
-        """Make the nn.Module view consistent after direct parameter updates (bump versions, hand over fp16)."""
+        """Make the nn.Module view consistent after direct parameter updates (hand over the fp16 copies)."""
         self.model.xyz_encoder.set_half_params(self.h_xyz)
         self.model.rgb_net.set_half_params(self.h_rgb)
