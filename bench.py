@@ -306,6 +306,40 @@ def main():
         if args.profile:
             for k, v in sorted(table.items(), key=lambda kv: -kv[1]):
                 print(f"  {k:40s} {v * 1e3:9.1f} us", file=sys.stderr)
+        # ---- L2 / HBM read roofline for the gather kernels, marcher and hash-encode rates
+        from google_nerf_b200 import _lib as LL
+        def membench(nbytes, iters):
+            buf = torch.empty(nbytes // 4, dtype=torch.int32, device=dev).zero_(); sink = torch.zeros(1, dtype=torch.int32, device=dev)
+            LL.call("b2n_membench_read", LL.ptr(buf), nbytes, 2, LL.ptr(sink))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); LL.call("b2n_membench_read", LL.ptr(buf), nbytes, iters, LL.ptr(sink)); b.record(); torch.cuda.synchronize()
+            return nbytes * iters / (a.elapsed_time(b) * 1e-3) / 1e9
+        l2_gbs, hbm_read_gbs = membench(32 << 20, 200), membench(2 << 30, 4)
+        t_fw, t_bw = table.get("b2n_hashgrid_fw", 0) * 1e-3, table.get("b2n_hashgrid_bw", 0) * 1e-3
+        hash_encode = dict(fw_gbs=588 * samples / t_fw / 1e9 if t_fw else None, bw_gbs=1100 * samples / t_bw / 1e9 if t_bw else None,
+                           l2_read_gbs_measured=l2_gbs, hbm_read_gbs_measured=hbm_read_gbs,
+                           fw_frac_of_l2=(588 * samples / t_fw / 1e9) / l2_gbs if t_fw else None,
+                           note="algorithmic bytes: 588 B/sample fw, 1100 B/sample bw (SURVEY 8d); table 21.8 MiB fp16, L2-resident")
+        t_m = (table.get("b2n_raymarching_train_count", 0) + table.get("b2n_raymarching_train_write", 0)) * 1e-3
+        marcher = dict(samples_per_s=samples / t_m if t_m else None, rays_per_s=N_RAYS / t_m if t_m else None,
+                       gbs=(120 * N_RAYS + 32 * samples) / t_m / 1e9 if t_m else None)
+        # ---- test-time render of full 800x800 frames (BASELINE.json configs[2]); tile-sharded when world > 1 happens
+        # in the N-GPU run via dist_utils.render_sharded (here: rank 0's local share of the frame)
+        from google_nerf_b200.models.rendering import render
+        from google_nerf_b200.dist_utils import shard_bounds
+        tr.sync_model()
+        lo, hi = shard_bounds(W_IMG * H_IMG, world, rank)
+        frames = []
+        with torch.no_grad():
+            for f in range(3):
+                ro, rd = syn.get_rays(dd[lo:hi], pp[f % N_IMG])
+                torch.cuda.synchronize(); t0 = time.perf_counter()
+                res = render(model, ro, rd, test_time=True, T_threshold=1e-2)
+                torch.cuda.synchronize(); frames.append(time.perf_counter() - t0)
+        render_info = dict(mrays_per_s=(hi - lo) * world / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
+                           rays=W_IMG * H_IMG, samples_per_ray=float(res["total_samples"]) / (hi - lo),
+                           note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 "
+                                "as in test.ipynb; per-rank share of the frame, no gather in this number")
         cb = None
         if not args.skip_cpu:
             cb, _ = cpu_baseline(args.cpu_rays, 2, 1)
@@ -323,7 +357,7 @@ def main():
                     e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
                     gpu_launches=launches_per_step * args.steps + 12 * n_updates,
-                    roofline=roofline, cpu_baseline=cb,
+                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, render=render_info,
                     kernels_us={k: round(v * 1e3, 1) for k, v in table.items()})
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -225,3 +225,30 @@ extern "C" int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const 
     B2N_LAUNCH_CHECK();
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------ membench
+// Read-bandwidth probe used by bench.py to obtain the L2 roofline the hash-grid gather is reported against
+// (MEASURED_PEAKS.json has no L2 figure): every thread streams 16-byte loads over a buffer `iters` times; with a
+// buffer that fits the 126 MB L2 the steady state is served by L2, with a larger one by HBM.
+__global__ void __launch_bounds__(256) membench_read_kernel(const uint4 *__restrict__ buf, int64_t n16, int iters,
+                                                            uint32_t *__restrict__ sink) {
+    uint32_t acc = 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; ++it) {
+        #pragma unroll 4
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            uint4 v;
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(buf + i));
+            acc ^= v.x ^ v.y ^ v.z ^ v.w;
+        }
+    }
+    if (acc == 0x9e3779b9u) sink[0] = acc;   // keeps the loads alive
+}
+
+extern "C" int b2n_membench_read(const void *buf, int64_t bytes, int iters, void *sink, void *stream) {
+    B2N_CHECK_ARG(bytes >= 16 && iters >= 1 && ((uintptr_t)buf & 15) == 0, "bad membench arguments");
+    membench_read_kernel<<<B2N_SMS * 8, 256, 0, (cudaStream_t)stream>>>((const uint4 *)buf, bytes / 16, iters,
+                                                                       (uint32_t *)sink);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}

@@ -70,11 +70,36 @@ class NGP(nn.Module):
     def forward(self, x, d):
         """x (N,3) positions, d (N,3) directions (normalised IN PLACE like the reference, networks.py:113)
         -> sigmas (N) fp32, rgbs (N,3) fp16."""
+        if self.encoding == "HashGrid" and not torch.is_grad_enabled() and x.is_cuda:
+            return self._forward_fused(x, d)
         sigmas, h = self.density(x, return_feat=True)
         d /= torch.norm(d, dim=-1, keepdim=True)
         d = self.dir_encoder((d + 1) / 2)
         rgbs = self.rgb_net(torch.cat([d, h], 1))
         return sigmas, rgbs
+
+    def _forward_fused(self, x, d):
+        """Inference path (no autograd): hash-grid gather + ONE fused tcgen05 kernel for both MLPs, SH and the
+        activations.  Same outputs as the modular path (sigmas fp32, rgbs fp16); the box normalisation and the
+        direction normalisation happen inside the kernels, so `d` is left untouched here."""
+        xe, rn = self.xyz_encoder, self.rgb_net
+        p16, r16 = xe.half_params(), rn.half_params()
+        key = (xe._p16_key, rn._p16_key)
+        if getattr(self, "_image_key", None) != key:
+            self._image = torch.empty(10240, dtype=torch.float16, device=x.device)
+            L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image))
+            self._image_key = key
+            self._layout = L.GridLayout.from_buffer_copy(xe.enc.layout)
+            self._layout.x_offset = -float(self.scale)
+            self._layout.x_scale = 1.0 / (2.0 * float(self.scale))
+        x = x.contiguous().float(); d = d.contiguous().float()
+        n = x.shape[0]
+        enc = torch.empty(n, 32, dtype=torch.float16, device=x.device)
+        sigmas = torch.empty(n, device=x.device); rgbs = torch.empty(n, 3, device=x.device)
+        L.call("b2n_hashgrid_fw", L.ptr(x), L.ptr(p16[xe.mlp.n_params:]), self._layout, n, None, L.ptr(enc), 32)
+        L.call("b2n_field_mlp_fw", L.ptr(enc), L.ptr(d), L.ptr(self._image), n, None, L.ptr(sigmas), L.ptr(rgbs),
+               None, None, None)
+        return sigmas, rgbs.to(torch.float16)
 
     # ------------------------------------------------------------------ occupancy grid
     def init_grid_buffers(self):

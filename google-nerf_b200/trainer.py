@@ -314,3 +314,4 @@ class NGPTrainer:
         """Make the nn.Module view consistent after direct parameter updates (hand over the fp16 copies)."""
         self.model.xyz_encoder.set_half_params(self.h_xyz)
         self.model.rgb_net.set_half_params(self.h_rgb)
+        self.model._image_key = None              # the fused inference path re-packs its weight image

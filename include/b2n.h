@@ -198,6 +198,10 @@ B2N_API int b2n_grid_ema(float *density_grid, const float *tmp, int64_t n_cells,
 B2N_API int b2n_grid_threshold(const float *density_grid, int64_t n_cells, float density_threshold,
                        double *workspace, float *stats_dev, void *stream);
 
+/* Read-bandwidth probe (bench.py): streams `bytes` of buf `iters` times with ld.global.cg; a buffer that fits the
+ * L2 measures L2 bandwidth, a larger one HBM bandwidth.  sink: 4 bytes, never written in practice. */
+B2N_API int b2n_membench_read(const void *buf, int64_t bytes, int iters, void *sink, void *stream);
+
 /* ---------------------------------------------------------------- loss (losses.py:26-40) ------------- */
 /* NeRFLoss + background blend fused: rgb_out = rgb + bg*(1-opacity) (rendering.py:159-164);
  * loss = mean((rgb_out-target)^2) + lambda_opa*mean(-o log o), o = opacity+1e-10 (train.py:160).
