@@ -62,11 +62,14 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, **kwargs):
         return res
     out = {}
     sizes = [shard_bounds(n, world, r) for r in range(world)]
+    longest = max(b - a for a, b in sizes)
     for k in ("rgb", "depth", "opacity"):
         v = res[k].contiguous()
-        parts = [torch.empty((b - a,) + tuple(v.shape[1:]), dtype=v.dtype, device=v.device) for a, b in sizes]
+        if v.shape[0] < longest:                              # all_gather needs equal shapes: pad the short bands
+            v = torch.cat([v, v.new_zeros((longest - v.shape[0],) + tuple(v.shape[1:]))], 0)
+        parts = [torch.empty_like(v) for _ in sizes]
         dist.all_gather(parts, v, group=group)
-        out[k] = torch.cat(parts, 0)
+        out[k] = torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], 0)
     ts = torch.as_tensor(res["total_samples"], device=out["rgb"].device, dtype=torch.int64).reshape(1).clone()
     dist.all_reduce(ts, group=group)
     out["total_samples"] = int(ts.item())

@@ -7,7 +7,7 @@ set -e
 R=${1:-r01}
 CMD="python bench.py --steps 6 --warmup 3 --pretrain 48 --no-graph --skip-cpu"
 $CMD > gpurun_out/${R}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'_kernel' -s 2600 -c 260 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'_kernel' -s 1200 -c 300 --csv \
     --log-file gpurun_out/${R}_launches.csv $CMD > gpurun_out/${R}_ncu_list.log 2>&1
 $CMD > gpurun_out/${R}_plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
