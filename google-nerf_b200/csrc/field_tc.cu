@@ -275,36 +275,45 @@ extern "C" int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2
 
 // ================================================================================================
 // Backward.  Per 128-sample tile, five steps (layer 5 .. layer 1); each step issues, back to back,
-//   wgrad:  dW (+)= g^T . act     (M = 64, K = 128 samples; both operands are the SAME shared-memory tiles the
+//   wgrad:  dW += g^T . act       (M = 64, K = 128 samples; both operands are the SAME shared-memory tiles the
 //                                  forward/dgrad MMAs use, read MN-major; accumulators persist in TMEM across
 //                                  all tiles of the CTA and are flushed once with red.global.add)
 //   dgrad:  g_prev = g . W        (M = 128 samples; W read MN-major from the canonical weight image)
-// then the epilogue threads apply ReLU' / TruncExp' and write the fp16 gradient tile of the next step.
+// then the epilogue threads apply ReLU' / TruncExp' and write the fp16 gradient tile of the next step in place.
 // Activation tiles of the next step are fetched from global memory (coalesced) while the current MMAs run.
-// TMEM columns: [0,64) dgrad work | [64,80) dW5^T | [80,144) dW4 | [144,176) dW3 | [176,192) dW2^T | [192,224) dW1.
+//
+// Latency hiding: the chain of a tile is ~10 dependent MMA groups + global loads, and the 160 TMEM columns of
+// weight-gradient accumulators cap co-resident CTAs, so ONE CTA per SM runs BW_GROUPS = 4 independent 128-thread
+// groups, each with its own tile, shared-memory tiles, mbarrier and 64-column dgrad accumulator, all accumulating
+// into the SAME weight-gradient columns.  MMA issue is serialised by a shared-memory lock bracketed with
+// tcgen05 fences so that accumulation into the shared columns is ordered.
+// TMEM columns: [64 g, 64 g + 64) dgrad of group g | 256.. dW5^T(16) dW4(64) dW3(32) dW2^T(16) dW1(32).
+#define BW_GROUPS 4
 struct FieldBwSmem {
-    __half w[IMG_HALVES];                      // 20480 B
-    unsigned char act[2][TILE64_BYTES];        // 33024 B  activation tiles (ping-pong)
-    unsigned char g[2][TILE64_BYTES];          // 33024 B  gradient tiles   (ping-pong)
-    uint64_t bar_w, bar_mma;
+    __half w[IMG_HALVES];                               //  20480 B
+    unsigned char act[BW_GROUPS][2][TILE64_BYTES];      // 132096 B  activation tiles (ping-pong per group)
+    unsigned char g[BW_GROUPS][TILE64_BYTES];           //  66048 B  gradient tile (in place per group)
+    uint64_t bar_w, bar_mma[BW_GROUPS];
     uint32_t tmem_base;
+    int lock;
 };
 
-#define TM_WORK 0
-#define TM_DW5T 64
-#define TM_DW4 80
-#define TM_DW3 144
-#define TM_DW2T 176
-#define TM_DW1 192
+#define TM_WG 256
+#define TM_DW5T (TM_WG + 0)
+#define TM_DW4 (TM_WG + 16)
+#define TM_DW3 (TM_WG + 80)
+#define TM_DW2T (TM_WG + 112)
+#define TM_DW1 (TM_WG + 128)
+#define TM_WG_COLS 160
 
-// wgrad: D[64 x N] (+)= A_tile^T[64 x 128] * B_tile[128 x N]; A/B tiles are [128 samples x features]
-__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, int N, bool accumulate) {
+// wgrad: D[64 x N] += A_tile^T[64 x 128] * B_tile[128 x N]; A/B tiles are [128 samples x features]
+__device__ __forceinline__ void issue_wgrad(uint32_t tmem_d, uint32_t a_tile, uint32_t b_tile, int N) {
     const uint32_t idesc = make_idesc(64, N, 1, 1);
     #pragma unroll
     for (int k = 0; k < 8; ++k) {                    // 16 samples per instruction = two 8-sample groups
         const uint64_t da = make_desc(a_tile + (uint32_t)k * 2 * ACT_SBO, ACT_SBO, ACT_LBO);
         const uint64_t db = make_desc(b_tile + (uint32_t)k * 2 * ACT_SBO, ACT_SBO, ACT_LBO);
-        mma_f16_ss(tmem_d, da, db, idesc, (accumulate || k > 0) ? 1u : 0u);
+        mma_f16_ss(tmem_d, da, db, idesc, 1u);       // accumulators are zero-initialised at kernel start
     }
 }
 // dgrad: D[128 x N_in] = G_tile[128 x K_out] (K-major) * W[K_out x N_in] (W image has K_out rows: MN-major B)
@@ -318,20 +327,47 @@ __device__ __forceinline__ void issue_dgrad(uint32_t tmem_d, uint32_t g_tile, ui
     }
 }
 
-// g_next = (act > 0) ? v : 0 for this thread's 64 columns, packed to fp16 into its row of g_tile
-__device__ __forceinline__ void relu_bw_to_tile(const float *v, const unsigned char *act_tile, unsigned char *g_tile, int r) {
+__device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(grp + 1) : "memory"); }
+
+#define GROUP_STEP_SYNC()      \
+    do {                       \
+        fence_async_smem();    \
+        fence_before_sync();   \
+        group_sync(grp);       \
+        fence_after_sync();    \
+    } while (0)
+
+__device__ __forceinline__ void issue_lock(int *lock) {
+    while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
+    fence_after_sync();
+}
+__device__ __forceinline__ void issue_unlock(int *lock) {
+    fence_before_sync();
+    __threadfence_block();
+    atomicExch(lock, 0);
+}
+
+// g_next = (act > 0) ? dgrad : 0 for this thread's 64 columns (read from TMEM in two halves to bound registers)
+__device__ __forceinline__ void relu_bw_epilogue(uint32_t tmem_work, const unsigned char *act_tile, unsigned char *g_tile, int r) {
     #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, c));
-        const __half *ah = reinterpret_cast<const __half *>(&a);
-        float o[8];
+    for (int half32 = 0; half32 < 2; ++half32) {
+        float v[32];
+        tmem_ld16(tmem_work + half32 * 32, v);
+        tmem_ld16(tmem_work + half32 * 32 + 16, v + 16);
         #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (__half2float(ah[j]) > 0.f) ? v[8 * c + j] : 0.f;
-        *reinterpret_cast<uint4 *>(g_tile + act_off(r, c)) = pack8(o);
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = half32 * 4 + cc;
+            const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, c));
+            const __half *ah = reinterpret_cast<const __half *>(&a);
+            float o[8];
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (__half2float(ah[j]) > 0.f) ? v[8 * cc + j] : 0.f;
+            *reinterpret_cast<uint4 *>(g_tile + act_off(r, c)) = pack8(o);
+        }
     }
 }
 
-__global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
+__global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
     const float *__restrict__ dL_dsigmas, const float *__restrict__ dL_drgbs, const __half *__restrict__ enc,
     const float *__restrict__ dirs, const __half *__restrict__ image, int64_t n, const int32_t *__restrict__ n_dev,
     const float *__restrict__ rgbs, const __half *__restrict__ hid_s, const __half *__restrict__ h_in,
@@ -339,41 +375,51 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
     float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FieldBwSmem &S = *reinterpret_cast<FieldBwSmem *>(smem_raw);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;
     const int64_t n_alloc = n;
     n = b2n_eff_n(n, n_dev);
     const int64_t n_tiles = (n + 127) / 128;
-    if ((int64_t)blockIdx.x >= n_tiles) return;
+    if ((int64_t)blockIdx.x * BW_GROUPS >= n_tiles) return;          // uniform per CTA
 
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         mbar_init(&S.bar_w, 1);
-        mbar_init(&S.bar_mma, 1);
+        for (int gq = 0; gq < BW_GROUPS; ++gq) mbar_init(&S.bar_mma[gq], 1);
+        S.lock = 0;
         mbar_init_fence();
     }
-    if (warp == 0) tmem_alloc<256>(&S.tmem_base);
+    if (threadIdx.x < 32) tmem_alloc<512>(&S.tmem_base);
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = S.tmem_base;
-    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);
-    if (tid == 0) {
+    const uint32_t tmem_row = tmem + ((uint32_t)(warp * 32) << 16);      // warp % 4 selects the TMEM lane quadrant
+    const uint32_t tmem_work = tmem_row + grp * 64;
+    if (threadIdx.x == 0) {
         mbar_expect_tx(&S.bar_w, IMG_HALVES * 2);
         bulk_g2s(S.w, image, IMG_HALVES * 2, &S.bar_w);
     }
+    if (grp == 0) {                                                      // zero the shared weight-gradient columns
+        for (int c16 = 0; c16 < TM_WG_COLS / 16; ++c16) tmem_st16_zero(tmem_row + TM_WG + c16 * 16);
+        tmem_st_wait();
+    }
     mbar_wait(&S.bar_w, 0);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
 
     const uint32_t w_addr = smem_u32(S.w);
-    const uint32_t act_a[2] = {smem_u32(S.act[0]), smem_u32(S.act[1])};
-    const uint32_t g_a[2] = {smem_u32(S.g[0]), smem_u32(S.g[1])};
-    unsigned char *ACT[2] = {S.act[0], S.act[1]};
-    unsigned char *G[2] = {S.g[0], S.g[1]};
+    const uint32_t act_a[2] = {smem_u32(S.act[grp][0]), smem_u32(S.act[grp][1])};
+    const uint32_t g_a = smem_u32(S.g[grp]);
+    unsigned char *ACT[2] = {S.act[grp][0], S.act[grp][1]};
+    unsigned char *G = S.g[grp];
+    uint64_t *bar = &S.bar_mma[grp];
+    const uint32_t tm_d = tmem + grp * 64;                               // dgrad accumulator (lane 0 base) of this group
     uint32_t phase = 0;
-    bool acc = false;          // wgrad accumulators hold data from an earlier tile
 
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * BW_GROUPS + grp; tile < n_tiles; tile += (int64_t)gridDim.x * BW_GROUPS) {
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
-        // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G0 [128x16]; hid_r2 -> ACT0; hid_r1 -> ACT1
+        // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G [128x16]; hid_r2 -> ACT0; hid_r1 -> ACT1
         {
             float g5[16];
             #pragma unroll
@@ -385,31 +431,31 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
                     g5[c] = __ldg(dL_drgbs + 3 * row + c) * y * (1.0f - y);
                 }
             }
-            *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 0)) = pack8(g5);
-            *reinterpret_cast<uint4 *>(G[0] + act_off(tid, 1)) = pack8(g5 + 8);
+            *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = pack8(g5);
+            *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = pack8(g5 + 8);
             tile_load<8>(ACT[0], hid_r + (n_alloc + row0) * 64, rows_valid, tid);
             tile_load<8>(ACT[1], hid_r + row0 * 64, rows_valid, tid);
         }
-        STEP_SYNC();
+        GROUP_STEP_SYNC();
         // ---- step A: layer 5 (64 -> 16)
         if (tid == 0) {
-            issue_wgrad(tmem + TM_DW5T, act_a[0], g_a[0], 16, acc);          // dW5^T[in][out] += hid_r2^T . g5
-            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W5 * 2, 64, 16);  // g4 = g5 . W5
-            mma_commit(&S.bar_mma);
+            issue_lock(&S.lock);
+            issue_wgrad(tmem + TM_DW5T, act_a[0], g_a, 16);                  // dW5^T[in][out] += hid_r2^T . g5
+            issue_dgrad(tm_d, g_a, w_addr + IMG_W5 * 2, 64, 16);             // g4 = g5 . W5
+            mma_commit(bar);
+            issue_unlock(&S.lock);
         }
-        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        {
-            float v[64];
-            tmem_ld64(tmem_row + TM_WORK, v);
-            relu_bw_to_tile(v, ACT[0], G[1], tid);                           // g4 = . * (hid_r2 > 0)
-        }
-        STEP_SYNC();
+        relu_bw_epilogue(tmem_work, ACT[0], G, tid);                         // g4 = . * (hid_r2 > 0)
+        GROUP_STEP_SYNC();
         // ---- step B: layer 4 (64 -> 64)
         if (tid == 0) {
-            issue_wgrad(tmem + TM_DW4, g_a[1], act_a[1], 64, acc);            // dW4[out][in] += g4^T . hid_r1
-            issue_dgrad(tmem + TM_WORK, g_a[1], w_addr + IMG_W4 * 2, 64, 64);  // g3 = g4 . W4
-            mma_commit(&S.bar_mma);
+            issue_lock(&S.lock);
+            issue_wgrad(tmem + TM_DW4, g_a, act_a[1], 64);                    // dW4[out][in] += g4^T . hid_r1
+            issue_dgrad(tm_d, g_a, w_addr + IMG_W4 * 2, 64, 64);              // g3 = g4 . W4
+            mma_commit(bar);
+            issue_unlock(&S.lock);
         }
         {   // while the MMAs run: colour-net input [SH16 | h16] -> ACT0 (its last readers finished in step A)
             sh_to_tile(dirs, row, live, ACT[0], tid);
@@ -421,81 +467,82 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
             *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 2)) = h0;
             *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 3)) = h1;
         }
-        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        {
-            float v[64];
-            tmem_ld64(tmem_row + TM_WORK, v);
-            relu_bw_to_tile(v, ACT[1], G[0], tid);                           // g3 = . * (hid_r1 > 0)
-        }
-        STEP_SYNC();
+        relu_bw_epilogue(tmem_work, ACT[1], G, tid);                         // g3 = . * (hid_r1 > 0)
+        GROUP_STEP_SYNC();
         // ---- step C: layer 3 (32 -> 64)
         if (tid == 0) {
-            issue_wgrad(tmem + TM_DW3, g_a[0], act_a[0], 32, acc);            // dW3[out][in] += g3^T . [SH|h]
-            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W3 * 2, 32, 64);  // g_in3 = g3 . W3
-            mma_commit(&S.bar_mma);
+            issue_lock(&S.lock);
+            issue_wgrad(tmem + TM_DW3, g_a, act_a[0], 32);                    // dW3[out][in] += g3^T . [SH|h]
+            issue_dgrad(tm_d, g_a, w_addr + IMG_W3 * 2, 32, 64);              // g_in3 = g3 . W3
+            mma_commit(bar);
+            issue_unlock(&S.lock);
         }
         tile_load<8>(ACT[1], hid_s + row0 * 64, rows_valid, tid);             // prefetch hid_s
-        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
         {
             float v[16];
-            tmem_ld16(tmem_row + TM_WORK + 16, v);                           // columns 16..31 = dL/dh from the colour net
+            tmem_ld16(tmem_work + 16, v);                                    // columns 16..31 = dL/dh from the colour net
             // TruncExp backward (custom_functions.py:171-173) joins on channel 0
             const __half2 hh = *reinterpret_cast<const __half2 *>(ACT[0] + act_off(tid, 2));
             const float h0 = __low2float(hh);
             if (live) v[0] += __ldg(dL_dsigmas + row) * expf(fminf(fmaxf(h0, -15.f), 15.f));
-            *reinterpret_cast<uint4 *>(G[1] + act_off(tid, 0)) = pack8(v);
-            *reinterpret_cast<uint4 *>(G[1] + act_off(tid, 1)) = pack8(v + 8);
+            *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = pack8(v);
+            *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = pack8(v + 8);
         }
-        STEP_SYNC();
+        GROUP_STEP_SYNC();
         // ---- step D: layer 2 (64 -> 16)
         if (tid == 0) {
-            issue_wgrad(tmem + TM_DW2T, act_a[1], g_a[1], 16, acc);           // dW2^T[in][out] += hid_s^T . g2
-            issue_dgrad(tmem + TM_WORK, g_a[1], w_addr + IMG_W2 * 2, 64, 16);  // g1 = g2 . W2
-            mma_commit(&S.bar_mma);
+            issue_lock(&S.lock);
+            issue_wgrad(tmem + TM_DW2T, act_a[1], g_a, 16);                   // dW2^T[in][out] += hid_s^T . g2
+            issue_dgrad(tm_d, g_a, w_addr + IMG_W2 * 2, 64, 16);              // g1 = g2 . W2
+            mma_commit(bar);
+            issue_unlock(&S.lock);
         }
         tile_load<4>(ACT[0], enc + row0 * 32, rows_valid, tid);               // prefetch enc -> ACT0 [128x32]
-        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        {
-            float v[64];
-            tmem_ld64(tmem_row + TM_WORK, v);
-            relu_bw_to_tile(v, ACT[1], G[0], tid);                           // g1 = . * (hid_s > 0)
-        }
-        STEP_SYNC();
+        relu_bw_epilogue(tmem_work, ACT[1], G, tid);                         // g1 = . * (hid_s > 0)
+        GROUP_STEP_SYNC();
         // ---- step E: layer 1 (32 -> 64)
         if (tid == 0) {
-            issue_wgrad(tmem + TM_DW1, g_a[0], act_a[0], 32, acc);            // dW1[out][in] += g1^T . enc
-            issue_dgrad(tmem + TM_WORK, g_a[0], w_addr + IMG_W1 * 2, 32, 64);  // g_enc = g1 . W1
-            mma_commit(&S.bar_mma);
+            issue_lock(&S.lock);
+            issue_wgrad(tmem + TM_DW1, g_a, act_a[0], 32);                    // dW1[out][in] += g1^T . enc
+            issue_dgrad(tm_d, g_a, w_addr + IMG_W1 * 2, 32, 64);              // g_enc = g1 . W1
+            mma_commit(bar);
+            issue_unlock(&S.lock);
         }
-        mbar_wait(&S.bar_mma, phase); phase ^= 1;
+        mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        {   // dL/denc: own row -> G1 tile, then one coalesced copy to global
+        {   // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
             float v[32];
-            tmem_ld16(tmem_row + TM_WORK, v);
-            tmem_ld16(tmem_row + TM_WORK + 16, v + 16);
+            tmem_ld16(tmem_work, v);
+            tmem_ld16(tmem_work + 16, v + 16);
             #pragma unroll
-            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(G[1] + act_off(tid, c)) = pack8(v + 8 * c);
+            for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(G + act_off(tid, c)) = pack8(v + 8 * c);
         }
-        acc = true;
         fence_before_sync();
-        __syncthreads();
+        group_sync(grp);
         fence_after_sync();
-        tile_store<4>(G[1], dL_denc + row0 * 32, rows_valid, tid);
+        tile_store<4>(G, dL_denc + row0 * 32, rows_valid, tid);
+        group_sync(grp);                 // the next tile's prologue overwrites G rows other threads just copied out
     }
     // ---- flush the weight gradients: M = 64 accumulators sit in lanes 32*w + (0..15) <-> rows 16*w + lane
-    {
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    if (grp == 0) {
         const int m = warp * 16 + lane;      // valid for lane < 16
         #pragma unroll 1
-        for (int c16 = 0; c16 < 10; ++c16) {  // columns 64 .. 223 in groups of 16
+        for (int c16 = 0; c16 < TM_WG_COLS / 16; ++c16) {
             float v[16];
-            tmem_ld16(tmem_row + 64 + c16 * 16, v);
+            tmem_ld16(tmem_row + TM_WG + c16 * 16, v);
             if (lane < 16) {
                 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const int col = 64 + c16 * 16 + j;
+                    const int col = TM_WG + c16 * 16 + j;
                     const float val = v[j] * grad_scale;
                     if (val == 0.f) continue;
                     if (col < TM_DW4)       atomicAdd(grad_rgb_w + 6144 + (col - TM_DW5T) * 64 + m, val);   // dW5^T[in=m][out]
@@ -509,7 +556,7 @@ __global__ void __launch_bounds__(128, 2) field_mlp_bw_kernel(
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if (threadIdx.x < 32) tmem_dealloc<512>(tmem);
 }
 
 extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
@@ -523,7 +570,9 @@ extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, 
         cudaFuncSetAttribute(field_mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldBwSmem) + 256);
         attr_set = true;
     }
-    field_mlp_bw_kernel<<<b2n_grid((n + 127) / 128, 2), 128, sizeof(FieldBwSmem) + 256, (cudaStream_t)stream>>>(
+    const int64_t n_tiles = (n + 127) / 128;
+    field_mlp_bw_kernel<<<b2n_grid((n_tiles + BW_GROUPS - 1) / BW_GROUPS, 1), 128 * BW_GROUPS, sizeof(FieldBwSmem) + 256,
+                          (cudaStream_t)stream>>>(
         dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)hid_s,
         (const __half *)h, (const __half *)hid_r, grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w);
     B2N_LAUNCH_CHECK();

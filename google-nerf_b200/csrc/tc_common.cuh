@@ -82,6 +82,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// zero 16 consecutive columns of this warp's 32 lanes (tcgen05.st), completion via tmem_st_wait()
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    const uint32_t z = 0;
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(z)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 // four 16-column loads in flight, one wait: v[0..63] = columns c..c+63 of this thread's lane
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float *v) {
     uint32_t r[64];
