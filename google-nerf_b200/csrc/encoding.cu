@@ -70,6 +70,76 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
     return index % size;
 }
 
+// Lane mapping of the forward kernel: TWO lanes per sample, lane parity = x-corner (x0 or x0+1); each lane
+// handles the four (y,z) corners of its x.  Entries of x-neighbours are adjacent (dense levels) or, with the
+// coherent prime hash, differ only in their low bits, so the two lanes of a pair hit the same 128-byte line and a
+// warp-level gather touches half as many L1 wavefronts as a one-lane-per-sample mapping (the kernel is L1
+// wavefront bound on the fine levels: 10 hashed levels x 8 corners x 32 distinct lines per warp instruction).
+// The two half-results are combined with one xor-shuffle.
+struct Corner4 {
+    uint32_t idx[4];
+    float w[4];
+    uint32_t key;     // packed integer lattice position of the cell (for run detection in the backward pass)
+};
+
+__device__ __forceinline__ void level_corners4(float px, float py, float pz, float scale, uint32_t res, uint32_t size,
+                                               uint32_t offset, int cx, Corner4 &c) {
+    const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
+    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
+    const uint32_t x0 = (uint32_t)gx, y0 = (uint32_t)gy, z0 = (uint32_t)gz;
+    c.key = x0 | (y0 << 10) | (z0 << 20);
+    const uint32_t x = x0 + (uint32_t)cx;
+    const float wxc = cx ? wx : 1.0f - wx;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t y = y0 + (k & 1), z = z0 + ((k >> 1) & 1);
+        float w = 1.0f;
+        w *= wxc;                                  // same product order as the 8-corner form: ((1*wx)*wy)*wz
+        w *= (k & 1) ? wy : 1.0f - wy;
+        w *= (k & 2) ? wz : 1.0f - wz;
+        c.idx[k] = offset + grid_index(x, y, z, res, size);
+        c.w[k] = w;
+    }
+}
+
+__global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restrict__ x,
+                                                          const __half2 *__restrict__ table,
+                                                          const __grid_constant__ GridLevels g, int64_t n,
+                                                          const int32_t *__restrict__ n_dev,
+                                                          __half *__restrict__ out, int out_stride) {
+    n = b2n_eff_n(n, n_dev);
+    const int lane = threadIdx.x & 31, cx = lane & 1;
+    const int64_t pairs_per_grid = ((int64_t)gridDim.x * blockDim.x) >> 1;
+    // warp-uniform loop: a warp covers 16 consecutive samples per iteration
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 1; base < n; base += pairs_per_grid) {
+        const int64_t i = base + (lane >> 1);
+        const bool live = i < n;
+        const int64_t ii = live ? i : n - 1;
+        const float px = (__ldg(x + 3 * ii) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * ii + 1) - g.x_offset) * g.x_scale,
+                    pz = (__ldg(x + 3 * ii + 2) - g.x_offset) * g.x_scale;
+        __half2 *row = reinterpret_cast<__half2 *>(out + ii * out_stride);
+        #pragma unroll 4
+        for (int l = 0; l < g.n_levels; ++l) {
+            Corner4 c;
+            level_corners4(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], cx, c);
+            __half2 v[4];
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = __ldg(table + c.idx[k]);
+            float a0 = 0.f, a1 = 0.f;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = __half22float2(v[k]);
+                a0 = fmaf(c.w[k], f.x, a0);
+                a1 = fmaf(c.w[k], f.y, a1);
+            }
+            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+            if (cx == 0 && live) row[l] = __floats2half2_rn(a0, a1);
+        }
+    }
+}
+
 struct Corner8 {
     uint32_t idx[8];
     float w[8];
@@ -90,35 +160,6 @@ __device__ __forceinline__ void level_corners(float px, float py, float pz, floa
         w *= (k & 4) ? wz : 1.0f - wz;
         c.idx[k] = offset + grid_index(x, y, z, res, size);
         c.w[k] = w;
-    }
-}
-
-__global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restrict__ x,
-                                                          const __half2 *__restrict__ table,
-                                                          const __grid_constant__ GridLevels g, int64_t n,
-                                                          const int32_t *__restrict__ n_dev,
-                                                          __half *__restrict__ out, int out_stride) {
-    n = b2n_eff_n(n, n_dev);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const float px = (__ldg(x + 3 * i) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * i + 1) - g.x_offset) * g.x_scale,
-                    pz = (__ldg(x + 3 * i + 2) - g.x_offset) * g.x_scale;
-        __half2 *row = reinterpret_cast<__half2 *>(out + i * out_stride);
-        #pragma unroll 4
-        for (int l = 0; l < g.n_levels; ++l) {
-            Corner8 c;
-            level_corners(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], c);
-            __half2 v[8];
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = __ldg(table + c.idx[k]);
-            float a0 = 0.f, a1 = 0.f;
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const float2 f = __half22float2(v[k]);
-                a0 = fmaf(c.w[k], f.x, a0);
-                a1 = fmaf(c.w[k], f.y, a1);
-            }
-            row[l] = __floats2half2_rn(a0, a1);
-        }
     }
 }
 
@@ -197,7 +238,7 @@ extern "C" int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(out_stride >= 2 * g.n_levels && out_stride % 2 == 0, "out_stride too small / odd");
     if (n <= 0) return 0;
-    hashgrid_fw_kernel<<<b2n_grid(b2n_blocks(n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
+    hashgrid_fw_kernel<<<b2n_grid(b2n_blocks(2 * n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
         x, (const __half2 *)table, g, n, n_dev, (__half *)out, out_stride);
     B2N_LAUNCH_CHECK();
     return 0;

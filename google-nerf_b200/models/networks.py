@@ -78,7 +78,7 @@ class NGP(nn.Module):
         rgbs = self.rgb_net(torch.cat([d, h], 1))
         return sigmas, rgbs
 
-    def _forward_fused(self, x, d):
+    def _forward_fused(self, x, d, rgb_fp32=False):
         """Inference path (no autograd): hash-grid gather + ONE fused tcgen05 kernel for both MLPs, SH and the
         activations.  Same outputs as the modular path (sigmas fp32, rgbs fp16); the box normalisation and the
         direction normalisation happen inside the kernels, so `d` is left untouched here."""
@@ -99,7 +99,7 @@ class NGP(nn.Module):
         L.call("b2n_hashgrid_fw", L.ptr(x), L.ptr(p16[xe.mlp.n_params:]), self._layout, n, None, L.ptr(enc), 32)
         L.call("b2n_field_mlp_fw", L.ptr(enc), L.ptr(d), L.ptr(self._image), n, None, L.ptr(sigmas), L.ptr(rgbs),
                None, None, None)
-        return sigmas, rgbs.to(torch.float16)
+        return sigmas, (rgbs if rgb_fp32 else rgbs.to(torch.float16))   # values are fp16-rounded either way
 
     # ------------------------------------------------------------------ occupancy grid
     def init_grid_buffers(self):

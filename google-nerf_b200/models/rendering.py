@@ -44,6 +44,7 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     hits = hits_t[:, 0]                                   # (N_rays,2) view, advanced in place by the marcher
 
     samples = total_samples = 0
+    fused = getattr(model, "encoding", None) == "HashGrid" and hasattr(model, "_forward_fused")
     alive_indices = torch.arange(N_rays, device=device)
     min_samples = 1 if exp_step_factor == 0 else 4
     while samples < MAX_SAMPLES:
@@ -57,13 +58,20 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
             exp_step_factor, model.grid_size, MAX_SAMPLES, N_samples)
         total_samples += N_eff_samples.sum()
         xyzs = xyzs.view(-1, 3); dirs = dirs.view(-1, 3)
-        valid_mask = ~torch.all(dirs == 0, dim=1)
-        if valid_mask.sum() == 0:
-            break
-        sigmas = torch.zeros(len(xyzs), device=device)
-        rgbs = torch.zeros(len(xyzs), 3, device=device)
-        _sigmas, _rgbs = model(xyzs[valid_mask], dirs[valid_mask])
-        sigmas[valid_mask], rgbs[valid_mask] = _sigmas.float(), _rgbs.float()
+        if fused:
+            # Mask-free variant of rendering.py:87-95: the field is evaluated on every slot in one fused launch;
+            # slots beyond N_eff_samples are never read by composite_test_fw, so the results are identical and the
+            # boolean-mask gathers/scatters (and their host syncs) disappear.  A round without any sample marks
+            # every ray dead in composite_test_fw, which ends the loop exactly like the reference's early break.
+            sigmas, rgbs = model._forward_fused(xyzs, dirs, rgb_fp32=True)
+        else:
+            valid_mask = ~torch.all(dirs == 0, dim=1)
+            if valid_mask.sum() == 0:
+                break
+            sigmas = torch.zeros(len(xyzs), device=device)
+            rgbs = torch.zeros(len(xyzs), 3, device=device)
+            _sigmas, _rgbs = model(xyzs[valid_mask], dirs[valid_mask])
+            sigmas[valid_mask], rgbs[valid_mask] = _sigmas.float(), _rgbs.float()
         vren.composite_test_fw(sigmas.view(-1, N_samples), rgbs.view(-1, N_samples, 3), deltas, ts, hits,
                                alive_indices, T_threshold, N_eff_samples, opacity, depth, rgb)
         alive_indices = alive_indices[alive_indices >= 0]

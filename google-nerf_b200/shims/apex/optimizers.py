@@ -1,0 +1,44 @@
+"""apex.optimizers.FusedAdam as used at ngp_pl/train.py:112 (`FusedAdam(net_params, lr, eps=1e-15)`): Adam with bias
+correction and no weight decay, one fused b2n_adam_step launch per parameter tensor (CUDA fp32 tensors whose size
+is a multiple of 4; anything else falls through to the same formula in torch ops)."""
+import torch
+
+from google_nerf_b200 import _lib as L
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-8, adam_w_mode=True,
+                 weight_decay=0.0, amsgrad=False, set_grad_none=True):
+        if amsgrad or weight_decay != 0.0 or not bias_correction:
+            raise NotImplementedError("only the configuration ngp_pl uses is built (bias-corrected Adam, no decay)")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self.set_grad_none = set_grad_none
+
+    def zero_grad(self, set_to_none=None):
+        super().zero_grad(set_to_none=self.set_grad_none if set_to_none is None else set_to_none)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        for group in self.param_groups:
+            b1, b2 = group["betas"]
+            for p in group["params"]:
+                if p.grad is None or p.numel() == 0:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p, dtype=torch.float32)
+                    st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32)
+                st["step"] += 1
+                g = p.grad
+                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.numel() % 4 == 0:
+                    g = g.to(torch.float32).contiguous().clone()      # the kernel zeroes the gradient buffer it is given
+                    L.call("b2n_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), None,
+                           p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]), 1.0, st["step"], None)
+                else:
+                    m, v = st["exp_avg"], st["exp_avg_sq"]
+                    m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                    c1, c2 = 1 - b1 ** st["step"], 1 - b2 ** st["step"]
+                    p.sub_(group["lr"] * (m / c1) / ((v / c2).sqrt() + group["eps"]))
+        return loss
