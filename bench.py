@@ -340,6 +340,11 @@ def main():
                            rays=W_IMG * H_IMG, samples_per_ray=float(res["total_samples"]) / (hi - lo),
                            note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 "
                                 "as in test.ipynb; per-rank share of the frame, no gather in this number")
+        # ---- cost of one occupancy-grid update (runs every 16 steps, outside the CUDA graph)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(3):
+            tr.update_density_grid(warmup=False)
+        torch.cuda.synchronize(); grid_update_ms = (time.perf_counter() - t0) / 3 * 1e3
         cb = None
         if not args.skip_cpu:
             cb, _ = cpu_baseline(args.cpu_rays, 2, 1)
@@ -357,7 +362,7 @@ def main():
                     e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
                     gpu_launches=launches_per_step * args.steps + 12 * n_updates,
-                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, render=render_info,
+                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, render=render_info, grid_update_ms=grid_update_ms,
                     kernels_us={k: round(v * 1e3, 1) for k, v in table.items()})
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -170,6 +170,7 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
     mbar_wait(&S.bar_w, 0);
 
     const uint32_t w_addr = smem_u32(S.w), a0 = smem_u32(S.a0), a1 = smem_u32(S.a1), a3 = smem_u32(S.a3);
+    const bool density_only = (rgbs == nullptr);
     uint32_t phase = 0;
 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
         const bool live = row < n;
         // ---- stage 0: encoded features (coalesced) and SH(dir) into the operand tiles
         tile_load<4>(S.a0, enc + row0 * 32, rows_valid, tid);
-        sh_to_tile(dirs, row, live, S.a3, tid);
+        if (!density_only) sh_to_tile(dirs, row, live, S.a3, tid);
         STEP_SYNC();
         // ---- layer 1: enc(32) -> 64, ReLU
         if (tid == 0) issue_layer(tmem, a0, w_addr + IMG_W1 * 2, 64, 32, &S.bar_mma);
@@ -208,6 +209,12 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
                     dst[0] = p0; dst[1] = p1;
                 }
             }
+        }
+        if (density_only) {            // NGP.density (networks.py:87-100): only sigma (and h) are wanted
+            fence_before_sync();
+            __syncthreads();
+            fence_after_sync();
+            continue;
         }
         STEP_SYNC();
         // ---- layer 3: [SH16 | h16] -> 64, ReLU
@@ -416,106 +423,151 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
     const uint32_t tm_d = tmem + grp * 64;                               // dgrad accumulator (lane 0 base) of this group
     uint32_t phase = 0;
 
-    for (int64_t tile = (int64_t)blockIdx.x * BW_GROUPS + grp; tile < n_tiles; tile += (int64_t)gridDim.x * BW_GROUPS) {
+    // Software pipeline: every global->shared tile copy is a cp.async issued ONE STEP AHEAD of its consumer (the
+    // buffer roles swap with the tile parity q so that the next tile's first two tiles can be fetched during
+    // step E), and the per-row scalars travel in registers.  Buffers of tile parity q: X = ACT[q], Y = ACT[1-q]:
+    //   step A: X = hid_r2   step B: Y = hid_r1   step C: X = [SH|h]   step D: Y = hid_s   step E: X = enc
+    const int64_t tile_stride = (int64_t)gridDim.x * BW_GROUPS;
+    int64_t tile = (int64_t)blockIdx.x * BW_GROUPS + grp;
+    int q = 0;
+    float c5[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // rgb (3) and dL/drgb (3) of this thread's row
+    if (tile < n_tiles) {
+        const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
+        tile_load_async<8>(ACT[0], hid_r + (n_alloc + row0) * 64, rows_valid, tid);
+        tile_load_async<8>(ACT[1], hid_r + row0 * 64, rows_valid, tid);
+        cp_async_commit();
+        if (row < n) {
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * row + c); c5[3 + c] = __ldg(dL_drgbs + 3 * row + c); }
+        }
+    }
+    for (; tile < n_tiles; tile += tile_stride, q ^= 1) {
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
-        // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G [128x16]; hid_r2 -> ACT0; hid_r1 -> ACT1
+        unsigned char *X = ACT[q], *Y = ACT[q ^ 1];
+        const uint32_t x_a = act_a[q], y_a = act_a[q ^ 1];
+        const int64_t next = tile + tile_stride;
+        const bool has_next = next < n_tiles;
+        const int64_t nrow0 = next * 128, nrow = nrow0 + tid, nrows_valid = n - nrow0;
+        // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G [128x16]
+        float dsx = 0.f, dsy = 0.f, dsz = 1.f, dsig = 0.f;
         {
             float g5[16];
             #pragma unroll
             for (int i = 0; i < 16; ++i) g5[i] = 0.f;
-            if (live) {
-                #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float y = __ldg(rgbs + 3 * row + c);
-                    g5[c] = __ldg(dL_drgbs + 3 * row + c) * y * (1.0f - y);
-                }
-            }
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) g5[c] = live ? c5[3 + c] * c5[c] * (1.0f - c5[c]) : 0.f;
             *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = pack8(g5);
             *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = pack8(g5 + 8);
-            tile_load<8>(ACT[0], hid_r + (n_alloc + row0) * 64, rows_valid, tid);
-            tile_load<8>(ACT[1], hid_r + row0 * 64, rows_valid, tid);
+            if (live) {       // needed in steps B / C: in flight while step A runs
+                dsx = __ldg(dirs + 3 * row); dsy = __ldg(dirs + 3 * row + 1); dsz = __ldg(dirs + 3 * row + 2);
+                dsig = __ldg(dL_dsigmas + row);
+            }
+            cp_async_wait_all();                                              // hid_r2 (X) and hid_r1 (Y) have landed
         }
         GROUP_STEP_SYNC();
         // ---- step A: layer 5 (64 -> 16)
         if (tid == 0) {
             issue_lock(&S.lock);
-            issue_wgrad(tmem + TM_DW5T, act_a[0], g_a, 16);                  // dW5^T[in][out] += hid_r2^T . g5
+            issue_wgrad(tmem + TM_DW5T, x_a, g_a, 16);                        // dW5^T[in][out] += hid_r2^T . g5
             issue_dgrad(tm_d, g_a, w_addr + IMG_W5 * 2, 64, 16);             // g4 = g5 . W5
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        relu_bw_epilogue(tmem_work, ACT[0], G, tid);                         // g4 = . * (hid_r2 > 0)
+        relu_bw_epilogue(tmem_work, X, G, tid);                              // g4 = . * (hid_r2 > 0)
         GROUP_STEP_SYNC();
         // ---- step B: layer 4 (64 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
-            issue_wgrad(tmem + TM_DW4, g_a, act_a[1], 64);                    // dW4[out][in] += g4^T . hid_r1
+            issue_wgrad(tmem + TM_DW4, g_a, y_a, 64);                         // dW4[out][in] += g4^T . hid_r1
             issue_dgrad(tm_d, g_a, w_addr + IMG_W4 * 2, 64, 64);              // g3 = g4 . W4
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
-        {   // while the MMAs run: colour-net input [SH16 | h16] -> ACT0 (its last readers finished in step A)
-            sh_to_tile(dirs, row, live, ACT[0], tid);
-            uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
-            if (live) {
-                h0 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16));
-                h1 = __ldg(reinterpret_cast<const uint4 *>(h_in + row * 16) + 1);
+        {   // X is free (step A done): colour-net input [SH16 | h16] for step C
+            cp_async16(X + act_off(tid, 2), h_in + row * 16, live);
+            cp_async16(X + act_off(tid, 3), h_in + row * 16 + 8, live);
+            cp_async_commit();
+            const float inv = 1.0f / sqrtf(dsx * dsx + dsy * dsy + dsz * dsz);
+            float sh[16];
+            sh4_eval_dev(dsx * inv, dsy * inv, dsz * inv, sh);
+            if (!live) {
+                #pragma unroll
+                for (int i = 0; i < 16; ++i) sh[i] = 0.f;
             }
-            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 2)) = h0;
-            *reinterpret_cast<uint4 *>(ACT[0] + act_off(tid, 3)) = h1;
+            *reinterpret_cast<uint4 *>(X + act_off(tid, 0)) = pack8(sh);
+            *reinterpret_cast<uint4 *>(X + act_off(tid, 1)) = pack8(sh + 8);
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        relu_bw_epilogue(tmem_work, ACT[1], G, tid);                         // g3 = . * (hid_r1 > 0)
+        relu_bw_epilogue(tmem_work, Y, G, tid);                              // g3 = . * (hid_r1 > 0)
+        cp_async_wait_all();
         GROUP_STEP_SYNC();
         // ---- step C: layer 3 (32 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
-            issue_wgrad(tmem + TM_DW3, g_a, act_a[0], 32);                    // dW3[out][in] += g3^T . [SH|h]
+            issue_wgrad(tmem + TM_DW3, g_a, x_a, 32);                         // dW3[out][in] += g3^T . [SH|h]
             issue_dgrad(tm_d, g_a, w_addr + IMG_W3 * 2, 32, 64);              // g_in3 = g3 . W3
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
-        tile_load<8>(ACT[1], hid_s + row0 * 64, rows_valid, tid);             // prefetch hid_s
+        tile_load_async<8>(Y, hid_s + row0 * 64, rows_valid, tid);            // Y is free (step B done): hid_s for step D
+        cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
         {
             float v[16];
             tmem_ld16(tmem_work + 16, v);                                    // columns 16..31 = dL/dh from the colour net
             // TruncExp backward (custom_functions.py:171-173) joins on channel 0
-            const __half2 hh = *reinterpret_cast<const __half2 *>(ACT[0] + act_off(tid, 2));
+            const __half2 hh = *reinterpret_cast<const __half2 *>(X + act_off(tid, 2));
             const float h0 = __low2float(hh);
-            if (live) v[0] += __ldg(dL_dsigmas + row) * expf(fminf(fmaxf(h0, -15.f), 15.f));
+            if (live) v[0] += dsig * expf(fminf(fmaxf(h0, -15.f), 15.f));
             *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = pack8(v);
             *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = pack8(v + 8);
         }
+        cp_async_wait_all();
         GROUP_STEP_SYNC();
         // ---- step D: layer 2 (64 -> 16)
         if (tid == 0) {
             issue_lock(&S.lock);
-            issue_wgrad(tmem + TM_DW2T, act_a[1], g_a, 16);                   // dW2^T[in][out] += hid_s^T . g2
+            issue_wgrad(tmem + TM_DW2T, y_a, g_a, 16);                        // dW2^T[in][out] += hid_s^T . g2
             issue_dgrad(tm_d, g_a, w_addr + IMG_W2 * 2, 64, 16);              // g1 = g2 . W2
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
-        tile_load<4>(ACT[0], enc + row0 * 32, rows_valid, tid);               // prefetch enc -> ACT0 [128x32]
+        tile_load_async<4>(X, enc + row0 * 32, rows_valid, tid);              // X is free (step C done): enc for step E
+        cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        relu_bw_epilogue(tmem_work, ACT[1], G, tid);                         // g1 = . * (hid_s > 0)
+        relu_bw_epilogue(tmem_work, Y, G, tid);                              // g1 = . * (hid_s > 0)
+        cp_async_wait_all();
         GROUP_STEP_SYNC();
         // ---- step E: layer 1 (32 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
-            issue_wgrad(tmem + TM_DW1, g_a, act_a[0], 32);                    // dW1[out][in] += g1^T . enc
+            issue_wgrad(tmem + TM_DW1, g_a, x_a, 32);                         // dW1[out][in] += g1^T . enc
             issue_dgrad(tm_d, g_a, w_addr + IMG_W1 * 2, 32, 64);              // g_enc = g1 . W1
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
+        if (has_next) {       // Y is free (step D done): the next tile's step-A tile and its per-row scalars
+            tile_load_async<8>(Y, hid_r + (n_alloc + nrow0) * 64, nrows_valid, tid);
+            cp_async_commit();
+            #pragma unroll
+            for (int c = 0; c < 6; ++c) c5[c] = 0.f;
+            if (nrow < n) {
+                #pragma unroll
+                for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * nrow + c); c5[3 + c] = __ldg(dL_drgbs + 3 * nrow + c); }
+            }
+        }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
+        if (has_next) {       // X is free (step E done): the next tile's step-B tile
+            tile_load_async<8>(X, hid_r + nrow0 * 64, nrows_valid, tid);
+            cp_async_commit();
+        }
         {   // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
             float v[32];
             tmem_ld16(tmem_work, v);

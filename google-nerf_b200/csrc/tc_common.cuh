@@ -134,6 +134,24 @@ __device__ __forceinline__ void tile_store(const unsigned char *tile, __half *g_
     }
 }
 
+// ---- cp.async (LDGSTS): asynchronous 16-byte global -> shared copies, zero-filled when !valid -----------
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src_gmem, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int NCH>
+__device__ __forceinline__ void tile_load_async(unsigned char *tile, const __half *g_row0, int64_t rows_valid, int tid) {
+    #pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int j = i * 128 + tid, row = j / NCH, c = j % NCH;
+        const bool ok = row < rows_valid;
+        const __half *src = g_row0 + (ok ? ((int64_t)row * (NCH * 8) + c * 8) : 0);
+        cp_async16(tile + (uint32_t)c * 2064u + (uint32_t)row * 16, src, ok);
+    }
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -78,20 +78,37 @@ class NGP(nn.Module):
         rgbs = self.rgb_net(torch.cat([d, h], 1))
         return sigmas, rgbs
 
-    def _forward_fused(self, x, d, rgb_fp32=False):
-        """Inference path (no autograd): hash-grid gather + ONE fused tcgen05 kernel for both MLPs, SH and the
-        activations.  Same outputs as the modular path (sigmas fp32, rgbs fp16); the box normalisation and the
-        direction normalisation happen inside the kernels, so `d` is left untouched here."""
+    def _fused_state(self, device):
         xe, rn = self.xyz_encoder, self.rgb_net
         p16, r16 = xe.half_params(), rn.half_params()
         key = (xe._p16_key, rn._p16_key)
         if getattr(self, "_image_key", None) != key:
-            self._image = torch.empty(10240, dtype=torch.float16, device=x.device)
+            self._image = torch.empty(10240, dtype=torch.float16, device=device)
             L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image))
             self._image_key = key
             self._layout = L.GridLayout.from_buffer_copy(xe.enc.layout)
             self._layout.x_offset = -float(self.scale)
             self._layout.x_scale = 1.0 / (2.0 * float(self.scale))
+        return p16, self._image
+
+    def _density_fused01(self, x01):
+        """sigma at positions already normalised to [0,1]^3 (occupancy-grid update): hash gather + the density half
+        of the fused tcgen05 kernel."""
+        p16, image = self._fused_state(x01.device)
+        n = x01.shape[0]
+        enc = torch.empty(n, 32, dtype=torch.float16, device=x01.device)
+        sigmas = torch.empty(n, device=x01.device)
+        L.call("b2n_hashgrid_fw", L.ptr(x01), L.ptr(p16[self.xyz_encoder.mlp.n_params:]), self.xyz_encoder.enc.layout, n,
+               None, L.ptr(enc), 32)
+        L.call("b2n_field_mlp_fw", L.ptr(enc), None, L.ptr(image), n, None, L.ptr(sigmas), None, None, None, None)
+        return sigmas
+
+    def _forward_fused(self, x, d, rgb_fp32=False):
+        """Inference path (no autograd): hash-grid gather + ONE fused tcgen05 kernel for both MLPs, SH and the
+        activations.  Same outputs as the modular path (sigmas fp32, rgbs fp16); the box normalisation and the
+        direction normalisation happen inside the kernels, so `d` is left untouched here."""
+        xe = self.xyz_encoder
+        p16, _ = self._fused_state(x.device)
         x = x.contiguous().float(); d = d.contiguous().float()
         n = x.shape[0]
         enc = torch.empty(n, 32, dtype=torch.float16, device=x.device)
@@ -174,8 +191,10 @@ class NGP(nn.Module):
             xyz01 = torch.empty(coords.shape[0], 3, device=coords.device)
             L.call("b2n_grid_cell_positions", L.ptr(coords.contiguous()), L.ptr(noise), coords.shape[0], G, float(s),
                    lo, hi, 1, L.ptr(xyz01))
-            h = self.xyz_encoder(xyz01)
-            sigmas = torch.exp(h[:, 0].float())
+            if self.encoding == "HashGrid":
+                sigmas = self._density_fused01(xyz01)
+            else:
+                sigmas = torch.exp(self.xyz_encoder(xyz01)[:, 0].float())
             L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]))
         if not self.density_grid.is_contiguous():
             self.density_grid = self.density_grid.contiguous()

@@ -290,7 +290,7 @@ class NGPTrainer:
     def update_density_grid(self, warmup=False):
         """train.py:145-148: threshold 0.01*MAX_SAMPLES/sqrt(3); all ranks end with the same grid."""
         m = self.model
-        m.xyz_encoder.set_half_params(self.h_xyz)
+        self.sync_model()                                    # the module sees the fp16 copies Adam just wrote
         m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=warmup, erode=False)
         if self.world > 1:
             dist.all_reduce(m.density_grid, op=dist.ReduceOp.MAX, group=self.pg)

@@ -158,7 +158,8 @@ B2N_API int b2n_mlp_bw(const b2n_half *dL_dout, const b2n_half *in, int in_strid
  * image: the two FullyFusedMLP weight sets repacked by b2n_field_pack_weights (10240 halves).
  * enc (n,32) fp16 (b2n_hashgrid_fw output), dirs (n,3) fp32 raw directions -> sigmas (n) fp32,
  * rgbs (n,3) fp32 (fp16-rounded).  Optional saves for the backward pass (NULL to skip):
- * hid_s (n,64), h (n,16), hid_r (2,n,64), all fp16. */
+ * hid_s (n,64), h (n,16), hid_r (2,n,64), all fp16.  rgbs == NULL selects the density-only form
+ * (NGP.density, models/networks.py:87-100): the chain stops after h, dirs is not read. */
 B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights /*3072*/, const b2n_half *rgb_weights /*7168*/,
                                    b2n_half *image /*10240*/, void *stream);
 B2N_API int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2n_half *image, int64_t n,
