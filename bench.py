@@ -273,6 +273,12 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX); dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(ms.item()), float(ms_e2e.item())
 
+    # ---- every rank: gather the model (sharded optimiser) and time the occupancy-grid update (it max-reduces)
+    tr.sync_model()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(3):
+        tr.update_density_grid(warmup=False)
+    torch.cuda.synchronize(); grid_update_ms = (time.perf_counter() - t0) / 3 * 1e3
     if rank == 0:
         # ---- per-kernel table + roofline of the dominant kernel (eager replays of the same step)
         tr.use_graph = False
@@ -327,7 +333,6 @@ def main():
         # in the N-GPU run via dist_utils.render_sharded (here: rank 0's local share of the frame)
         from google_nerf_b200.models.rendering import render
         from google_nerf_b200.dist_utils import shard_bounds
-        tr.sync_model()
         lo, hi = shard_bounds(W_IMG * H_IMG, world, rank)
         frames = []
         with torch.no_grad():
@@ -340,11 +345,6 @@ def main():
                            rays=W_IMG * H_IMG, samples_per_ray=float(res["total_samples"]) / (hi - lo),
                            note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 "
                                 "as in test.ipynb; per-rank share of the frame, no gather in this number")
-        # ---- cost of one occupancy-grid update (runs every 16 steps, outside the CUDA graph)
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(3):
-            tr.update_density_grid(warmup=False)
-        torch.cuda.synchronize(); grid_update_ms = (time.perf_counter() - t0) / 3 * 1e3
         cb = None
         if not args.skip_cpu:
             cb, _ = cpu_baseline(args.cpu_rays, 2, 1)

@@ -46,7 +46,7 @@ class _SampleSet:
 class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
-                 use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256):
+                 use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True):
         if model.encoding != "HashGrid":
             raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
                              "render() + autograd")
@@ -62,7 +62,7 @@ class NGPTrainer:
         torch.cuda.manual_seed(seed)
         self.fixed_noise = None                   # parity tests pin the per-ray jitter here
         self.pg = process_group
-        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.world = dist.get_world_size(process_group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         self.S, self.warmup_steps = grid_update_interval, warmup_steps
         self.step_count = 0
         self.use_graph = use_graph
@@ -72,11 +72,28 @@ class NGPTrainer:
 
         xe, rn = model.xyz_encoder, model.rgb_net
         self.n_mlp = xe.mlp.n_params
-        self.p_xyz, self.p_rgb = xe.params.data, rn.params.data
         z = lambda t: torch.zeros_like(t)
-        self.g_xyz, self.g_rgb = z(self.p_xyz), z(self.p_rgb)
-        self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb = z(self.p_xyz), z(self.p_xyz), z(self.p_rgb), z(self.p_rgb)
-        self.h_xyz = tc.cast_half(self.p_xyz)
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        n_xyz = xe.params.numel()
+        # Sharded optimiser (world > 1): the big flat parameter (MLP + hash table) is padded to world * shard; every
+        # rank reduce-scatters the gradient, runs Adam on ITS shard of the fp32 master / moments only, and the fp16
+        # working copy is all-gathered.  Less traffic than an all-reduce (fp32 RS + fp16 AG) and Adam's HBM sweep
+        # shrinks by the world size.  The model's Parameter is a view of the padded master buffer.
+        self.n_pad = -(-n_xyz // (8 * self.world)) * (8 * self.world)
+        self.shard = self.n_pad // self.world
+        p_pad = torch.zeros(self.n_pad, dtype=_f32, device=self.dev)
+        p_pad[:n_xyz].copy_(xe.params.data)
+        xe.params.data = p_pad[:n_xyz]
+        self.p_pad = p_pad
+        self.p_xyz, self.p_rgb = xe.params.data, rn.params.data
+        self.g_xyz, self.g_rgb = torch.zeros(self.n_pad, dtype=_f32, device=self.dev), z(self.p_rgb)
+        lo = self.rank * self.shard
+        self.p_shard = p_pad[lo:lo + self.shard]
+        self.g_shard = self.g_xyz if self.world == 1 else torch.zeros(self.shard, dtype=_f32, device=self.dev)
+        self.m_xyz, self.v_xyz = z(self.p_shard), z(self.p_shard)
+        self.m_rgb, self.v_rgb = z(self.p_rgb), z(self.p_rgb)
+        self.h_xyz = tc.cast_half(p_pad)
+        self.h_shard = self.h_xyz[lo:lo + self.shard]
         self.h_rgb = tc.cast_half(self.p_rgb)
         self.hyper = torch.zeros(2, dtype=torch.int32, device=self.dev)        # {float lr; int32 step}
         self.w_image = torch.empty(10240, dtype=_f16, device=self.dev)
@@ -151,19 +168,28 @@ class NGPTrainer:
         call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
              P(self.g_xyz[self.n_mlp:]))
 
-    def _allreduce(self):
-        if self.world > 1:
-            dist.all_reduce(self.g_xyz, group=self.pg)
-            dist.all_reduce(self.g_rgb, group=self.pg)
+    def _reduce_grads(self):
+        """world > 1: sum the gradients over ranks -- reduce-scatter for the big sharded parameter, all-reduce for the
+        29 KB colour-net one.  (NCCL; kept outside the captured graphs.)"""
+        dist.reduce_scatter_tensor(self.g_shard, self.g_xyz, op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(self.g_rgb, group=self.pg)
 
     def _optimizer(self):
         P, call = L.ptr, L.call
         inv = 1.0 / (self.loss_scale * self.world)
         b1, b2 = self.betas
-        for p, g, m, v, h in ((self.p_xyz, self.g_xyz, self.m_xyz, self.v_xyz, self.h_xyz),
+        for p, g, m, v, h in ((self.p_shard, self.g_shard, self.m_xyz, self.v_xyz, self.h_shard),
                               (self.p_rgb, self.g_rgb, self.m_rgb, self.v_rgb, self.h_rgb)):
             call("b2n_adam_step", P(p), P(g), P(m), P(v), P(h), p.numel(), self.lr, b1, b2, self.eps, inv, 1,
                  P(self.hyper))
+        if self.world == 1:
+            self._pack_weights()
+        else:
+            self.g_xyz.zero_()                               # Adam only zeroed this rank's reduced shard
+
+    def _gather_params(self):
+        """world > 1: every rank receives the other shards of the fp16 working copy, then re-packs the MLP image."""
+        dist.all_gather_into_tensor(self.h_xyz, self.h_shard, group=self.pg)
         self._pack_weights()
 
     def _pack_weights(self):
@@ -198,8 +224,8 @@ class NGPTrainer:
     def _capture(self, fn, touches_params):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
-        state_t = (self.p_xyz, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz, self.h_rgb,
-                   self.g_xyz, self.g_rgb)
+        state_t = (self.p_pad, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz, self.h_rgb,
+                   self.g_xyz, self.g_rgb, self.g_shard)
         saved = [t.clone() for t in state_t] if touches_params else None
         warm = torch.cuda.Stream(device=self.dev)
         warm.wait_stream(torch.cuda.current_stream())
@@ -266,9 +292,10 @@ class NGPTrainer:
         if prefetch:
             self._load(self.sets[1 - p], next_batch)
         self._run(("train", p, prefetch), lambda: self._train(p, prefetch))
-        if self.world > 1:                                   # NCCL all-reduce stays outside the captured graphs
-            self._allreduce()
+        if self.world > 1:                                   # NCCL collectives stay outside the captured graphs
+            self._reduce_grads()
             self._run(("opt",), self._optimizer)
+            self._gather_params()
         s.marched = False
         self.last_counter = s.counter
         if next_batch is not None:
@@ -311,7 +338,10 @@ class NGPTrainer:
         self._alloc()
 
     def sync_model(self):
-        """Make the nn.Module view consistent after direct parameter updates (hand over the fp16 copies)."""
+        """Make the nn.Module view consistent after direct parameter updates (hand over the fp16 copies; with a
+        sharded optimiser also gather the fp32 master shards so that state_dict() is complete on every rank)."""
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.p_pad, self.p_shard, group=self.pg)
         self.model.xyz_encoder.set_half_params(self.h_xyz)
         self.model.rgb_net.set_half_params(self.h_rgb)
         self.model._image_key = None              # the fused inference path re-packs its weight image

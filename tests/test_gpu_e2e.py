@@ -186,3 +186,42 @@ def test_trainer_pipelined_march_matches_sequential(pair):
         out[pipelined] = ls
     np.testing.assert_allclose(out[True], out[False], rtol=3e-2)
     assert out[True][-1] < 0.6 * out[True][0]
+
+
+def test_trainer_unbounded_config_matches_oracle_step(built_lib):
+    """BASELINE config 5 shape in miniature: scale 4 (3 cascades), exp_step_factor 1/256, black background.  One fused
+    training step (march with exponential stepping through the cascades, field, compositing, backward) against the
+    oracle on the same weights / bitfield / jitter."""
+    from google_nerf_b200 import synthetic as syn
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.trainer import NGPTrainer
+    from oracle import ngp_ref as O
+    scale, n = 4.0, 384
+    s = make_scene(scale, n, seed=13)
+    ref = O.NGPRef(scale, log2_T=14, seed=3)
+    g = torch.Generator().manual_seed(9)
+    with torch.no_grad():
+        ref.xyz_params[ref.n_mlp:] = (torch.rand(ref.layout["n_params"], generator=g) * 2 - 1) * 0.3
+    ref.density_bitfield = s["bitfield"].clone()
+    target = torch.rand(n, 3, generator=g)
+    model = NGP(scale, log2_T=14).to(DEV)
+    assert model.cascades == 4
+    model.xyz_encoder.params.data.copy_(ref.xyz_params.detach()); model.rgb_net.params.data.copy_(ref.rgb_params.detach())
+    model.density_bitfield.copy_(s["bitfield"])
+    tr = NGPTrainer(model, n_rays=n, exp_step_factor=1 / 256, use_graph=False, samples_per_ray=400,
+                    grid_update_interval=10 ** 9)
+    tr.step_count = 1
+    tr.fixed_noise = s["noise"].to(DEV)
+    tr.set_batch(s["rays_o"].to(DEV), s["rays_d"].to(DEV), target.to(DEV))
+    sset = tr.sets[tr.cur]
+    tr._march(sset); tr._forward_backward(sset); tr.last_counter = sset.counter
+    res = O.render(ref, s["rays_o"], s["rays_d"].clone(), noise=s["noise"], exp_step_factor=1 / 256)
+    loss = O.nerf_loss(res, target)
+    (loss * tr.loss_scale).backward()
+    assert tr.samples_last_step() == res["total_samples"] > 1000 and not tr.overflowed()
+    torch.testing.assert_close(tr.opacity.cpu(), res["opacity"].detach(), rtol=5e-3, atol=5e-3)
+    torch.testing.assert_close(tr.rgb_out.cpu(), res["rgb"].detach(), rtol=5e-3, atol=5e-3)
+    assert abs(tr.loss.item() - loss.item()) < 3e-3 * abs(loss.item())
+    for got, want, name in ((tr.g_rgb, ref.rgb_params.grad, "rgb_net"), (tr.g_xyz, ref.xyz_params.grad, "xyz_encoder")):
+        sc = want.abs().max().item()
+        assert (got.cpu() - want).abs().max().item() <= 3e-2 * sc, name
