@@ -289,7 +289,10 @@ def main():
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         tf_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
         costs = kernel_costs(N_RAYS, samples, tr.p_xyz.numel(), tr.p_rgb.numel())
-        top = max(table, key=table.get)
+        # the dominant kernel of the step's critical path (ray generation / AABB / marching of the NEXT batch run on
+        # the side stream underneath it and are reported separately in `marcher`)
+        side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near")
+        top = max((k for k in table if not k.startswith(side)), key=table.get)
         base = top.split("[")[0]
         bound = costs.get(base, ("hbm", None))[0]
         if base == "b2n_adam_step":
@@ -305,7 +308,11 @@ def main():
             ach, peak, unit = alg / dur_s / 1e9, hbm_peak, "GB/s"
         else:
             ach, peak, unit = alg / dur_s / 1e12, tf_peak, "TFLOP/s"
-        roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak, traffic=None,
+        ncu_traffic_per_sample = {"b2n_field_mlp_bw": 615.0, "b2n_field_mlp_fw": 451.0, "b2n_hashgrid_fw": 83.0,
+                                  "b2n_hashgrid_bw": 147.0}          # profiles/r01b_ncu_summary.md (dram read+write / samples)
+        traffic = ncu_traffic_per_sample.get(base)
+        roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
+                        traffic=traffic * samples if traffic else None,
                         peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
                         ms_per_launch=table[top], share_of_step=table[top] / sum(table.values()),
                         algorithmic_per_launch=alg)

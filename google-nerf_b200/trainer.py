@@ -46,7 +46,8 @@ class _SampleSet:
 class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
-                 use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True):
+                 use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
+                 march_ctas_per_sm=None):
         if model.encoding != "HashGrid":
             raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
                              "render() + autograd")
@@ -69,6 +70,8 @@ class NGPTrainer:
         self._from_indices = False
         self.directions = self.poses = None
         self.side = torch.cuda.Stream(device=self.dev)
+        import os
+        self.march_ctas = int(march_ctas_per_sm if march_ctas_per_sm is not None else os.environ.get("B2N_MARCH_CTAS", 8))
 
         xe, rn = model.xyz_encoder, model.rgb_net
         self.n_mlp = xe.mlp.n_params
@@ -127,6 +130,7 @@ class NGPTrainer:
         """ray generation (train.py:150-157) -> AABB (+ near clamp) -> occupancy marcher, into sample set s."""
         m, P, call = self.model, L.ptr, L.call
         n, cap = self.n_rays, self.capacity
+        L.call_nostream("b2n_set_march_ctas_per_sm", self.march_ctas)    # grid size is baked into a captured graph
         if self._from_indices:
             # get_rays (datasets/ray_utils.py:152-175): rotate camera-frame directions, origin = camera centre
             c2w = self.poses[s.img_idxs]

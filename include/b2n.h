@@ -73,6 +73,9 @@ B2N_API int b2n_raymarching_train_write(const float *rays_o, const float *rays_d
                                 float exp_step_factor, const float *noise, int grid_size,
                                 int max_samples, int64_t n_rays, const int64_t *rays_a, float *xyzs,
                                 float *dirs, float *deltas, float *ts, const uint32_t *workspace, void *stream);
+/* Tuning knob (process-wide): resident CTAs per SM of the train marcher, 1..8 (default 8).  The pipelined trainer
+ * lowers it so that the marcher overlaps the backward kernels instead of occupying every warp slot. */
+B2N_API int b2n_set_march_ctas_per_sm(int ctas);
 /* vren.raymarching_test (models/rendering.py:79-83).  hits_t (n_rays,2) is advanced IN PLACE;
  * outputs (n_alive,n_samples[,3]) are fully written (unused slots zero); n_eff (n_alive) i32. */
 B2N_API int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,
