@@ -16,6 +16,8 @@ COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # bit-exact geometry: one IEEE op per source op, no fused multiply-add (DESIGN.md "Numerics")
 PER_FILE = {"geometry.cu": ["-fmad=false"], "march.cu": ["-fmad=false"]}
+if os.environ.get("B2N_BW_TRACE"):            # debug: phase timestamps in the backward field kernel (scratch/bw_trace.py)
+    PER_FILE["field_tc.cu"] = ["-DB2N_BW_TRACE"]
 
 
 def sources():

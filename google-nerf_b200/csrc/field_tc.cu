@@ -173,17 +173,26 @@ __global__ void __launch_bounds__(128, 4) field_mlp_fw_kernel(const __half *__re
     const bool density_only = (rgbs == nullptr);
     uint32_t phase = 0;
 
+    // the encoded tile of the NEXT tile is fetched with cp.async into a0 as soon as layer 1 has consumed the
+    // current one (four layers ahead of its use); the first tile is fetched here
+    tile_load_async<4>(S.a0, enc + (int64_t)blockIdx.x * 128 * 32, n - (int64_t)blockIdx.x * 128, tid);
+    cp_async_commit();
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
-        // ---- stage 0: encoded features (coalesced) and SH(dir) into the operand tiles
-        tile_load<4>(S.a0, enc + row0 * 32, rows_valid, tid);
+        const int64_t next = tile + gridDim.x;
+        // ---- stage 0: SH(dir) into the colour-net operand tile; the encoded features are already in flight
         if (!density_only) sh_to_tile(dirs, row, live, S.a3, tid);
+        cp_async_wait_all();
         STEP_SYNC();
         // ---- layer 1: enc(32) -> 64, ReLU
         if (tid == 0) issue_layer(tmem, a0, w_addr + IMG_W1 * 2, 64, 32, &S.bar_mma);
         mbar_wait(&S.bar_mma, phase); phase ^= 1;
         fence_after_sync();
+        if (next < n_tiles) {                         // a0 is free again: next tile's encoded features
+            tile_load_async<4>(S.a0, enc + next * 128 * 32, n - next * 128, tid);
+            cp_async_commit();
+        }
         {
             float v[64];
             tmem_ld64(tmem_row, v);
@@ -296,6 +305,14 @@ extern "C" int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2
 // tcgen05 fences so that accumulation into the shared columns is ordered.
 // TMEM columns: [64 g, 64 g + 64) dgrad of group g | 256.. dW5^T(16) dW4(64) dW3(32) dW2^T(16) dW1(32).
 #define BW_GROUPS 4
+// Phase trace (debug builds only, -DB2N_BW_TRACE): clock64() of CTA 0 / group 0 / thread 64 at every phase boundary.
+#ifdef B2N_BW_TRACE
+__device__ long long g_bw_trace[64 * 16];
+#define TRACE(slot) do { if (blockIdx.x == 0 && threadIdx.x == 64 && trace_it < 64) g_bw_trace[trace_it * 16 + (slot)] = clock64(); } while (0)
+extern "C" __attribute__((visibility("default"))) int b2n_debug_bw_trace(long long *out) { return (int)cudaMemcpyFromSymbol(out, g_bw_trace, sizeof(g_bw_trace)); }
+#else
+#define TRACE(slot) do { } while (0)
+#endif
 struct FieldBwSmem {
     __half w[IMG_HALVES];                               //  20480 B
     unsigned char act[BW_GROUPS][2][TILE64_BYTES];      // 132096 B  activation tiles (ping-pong per group)
@@ -344,14 +361,25 @@ __device__ __forceinline__ void group_sync(int grp) { asm volatile("bar.sync %0,
         fence_after_sync();    \
     } while (0)
 
+// MMA issue from the four group leaders is NOT serialised: tcgen05.mma executes in the tensor pipe one instruction
+// at a time and D += A*B is a single read-modify-write of TMEM inside that pipe, so accumulations into the shared
+// weight-gradient columns from different issuing threads commute (only their order, i.e. fp32 summation order, is
+// unspecified).  B2N_BW_LOCK=1 at compile time restores a shared-memory lock around every issue sequence.
+#ifndef B2N_BW_LOCK
+#define B2N_BW_LOCK 0
+#endif
 __device__ __forceinline__ void issue_lock(int *lock) {
+#if B2N_BW_LOCK
     while (atomicCAS(lock, 0, 1) != 0) __nanosleep(32);
+#endif
     fence_after_sync();
 }
 __device__ __forceinline__ void issue_unlock(int *lock) {
     fence_before_sync();
+#if B2N_BW_LOCK
     __threadfence_block();
     atomicExch(lock, 0);
+#endif
 }
 
 // g_next = (act > 0) ? dgrad : 0 for this thread's 64 columns (read from TMEM in two halves to bound registers)
@@ -359,8 +387,7 @@ __device__ __forceinline__ void relu_bw_epilogue(uint32_t tmem_work, const unsig
     #pragma unroll
     for (int half32 = 0; half32 < 2; ++half32) {
         float v[32];
-        tmem_ld16(tmem_work + half32 * 32, v);
-        tmem_ld16(tmem_work + half32 * 32 + 16, v + 16);
+        tmem_ld32(tmem_work + half32 * 32, v);
         #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int c = half32 * 4 + cc;
@@ -441,7 +468,10 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * row + c); c5[3 + c] = __ldg(dL_drgbs + 3 * row + c); }
         }
     }
+    int trace_it = -1;
     for (; tile < n_tiles; tile += tile_stride, q ^= 1) {
+        ++trace_it; (void)trace_it;
+        TRACE(0);
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
         const bool live = row < n;
         unsigned char *X = ACT[q], *Y = ACT[q ^ 1];
@@ -465,7 +495,9 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             }
             cp_async_wait_all();                                              // hid_r2 (X) and hid_r1 (Y) have landed
         }
+        TRACE(1);
         GROUP_STEP_SYNC();
+        TRACE(2);
         // ---- step A: layer 5 (64 -> 16)
         if (tid == 0) {
             issue_lock(&S.lock);
@@ -476,8 +508,11 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
+        TRACE(3);
         relu_bw_epilogue(tmem_work, X, G, tid);                              // g4 = . * (hid_r2 > 0)
+        TRACE(4);
         GROUP_STEP_SYNC();
+        TRACE(5);
         // ---- step B: layer 4 (64 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
@@ -500,11 +535,16 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             *reinterpret_cast<uint4 *>(X + act_off(tid, 0)) = pack8(sh);
             *reinterpret_cast<uint4 *>(X + act_off(tid, 1)) = pack8(sh + 8);
         }
+        TRACE(6);
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
+        TRACE(7);
         relu_bw_epilogue(tmem_work, Y, G, tid);                              // g3 = . * (hid_r1 > 0)
+        TRACE(8);
         cp_async_wait_all();
+        TRACE(9);
         GROUP_STEP_SYNC();
+        TRACE(10);
         // ---- step C: layer 3 (32 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
@@ -517,6 +557,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
+        TRACE(12);
         {
             float v[16];
             tmem_ld16(tmem_work + 16, v);                                    // columns 16..31 = dL/dh from the colour net
@@ -529,6 +570,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         }
         cp_async_wait_all();
         GROUP_STEP_SYNC();
+        TRACE(13);
         // ---- step D: layer 2 (64 -> 16)
         if (tid == 0) {
             issue_lock(&S.lock);
@@ -541,9 +583,11 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
+        TRACE(14);
         relu_bw_epilogue(tmem_work, Y, G, tid);                              // g1 = . * (hid_s > 0)
         cp_async_wait_all();
         GROUP_STEP_SYNC();
+        TRACE(15);
         // ---- step E: layer 1 (32 -> 64)
         if (tid == 0) {
             issue_lock(&S.lock);
@@ -570,8 +614,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         }
         {   // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
             float v[32];
-            tmem_ld16(tmem_work, v);
-            tmem_ld16(tmem_work + 16, v + 16);
+            tmem_ld32(tmem_work, v);
             #pragma unroll
             for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4 *>(G + act_off(tid, c)) = pack8(v + 8 * c);
         }
@@ -580,6 +623,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         fence_after_sync();
         tile_store<4>(G, dL_denc + row0 * 32, rows_valid, tid);
         group_sync(grp);                 // the next tile's prologue overwrites G rows other threads just copied out
+        TRACE(11);
     }
     // ---- flush the weight gradients: M = 64 accumulators sit in lanes 32*w + (0..15) <-> rows 16*w + lane
     fence_before_sync();
