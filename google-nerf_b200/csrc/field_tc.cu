@@ -98,12 +98,14 @@ __device__ __forceinline__ void sh_to_tile(const float *__restrict__ dirs, int64
 
 // ReLU + fp16 pack of this thread's 64 accumulator columns into its row of a [128 x 64] tile
 __device__ __forceinline__ void relu_to_tile(const float *v, unsigned char *tile, int r) {
+    const __half2 zero2 = __float2half2_rn(0.f);
     #pragma unroll
     for (int c = 0; c < 8; ++c) {
-        float o[8];
+        uint4 o;
+        __half2 *oh = reinterpret_cast<__half2 *>(&o);
         #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = fmaxf(v[8 * c + j], 0.f);
-        *reinterpret_cast<uint4 *>(tile + act_off(r, c)) = pack8(o);
+        for (int j = 0; j < 4; ++j) oh[j] = __hmax2(__floats2half2_rn(v[8 * c + 2 * j], v[8 * c + 2 * j + 1]), zero2);
+        *reinterpret_cast<uint4 *>(tile + act_off(r, c)) = o;
     }
 }
 
@@ -382,8 +384,12 @@ __device__ __forceinline__ void issue_unlock(int *lock) {
 #endif
 }
 
-// g_next = (act > 0) ? dgrad : 0 for this thread's 64 columns (read from TMEM in two halves to bound registers)
+// g_next = (act > 0) ? dgrad : 0 for this thread's 64 columns (read from TMEM in two halves to bound registers).
+// The mask is applied in the packed fp16 domain: cvt.rn.f16x2 of the gradient pair, HSETP2-style (act > 0) -> {1,0}
+// and one HMUL2 -- three instructions per two values instead of convert / compare / select / pack per value (the
+// epilogue is issue bound when several groups reach it together).
 __device__ __forceinline__ void relu_bw_epilogue(uint32_t tmem_work, const unsigned char *act_tile, unsigned char *g_tile, int r) {
+    const __half2 zero2 = __float2half2_rn(0.f);
     #pragma unroll
     for (int half32 = 0; half32 < 2; ++half32) {
         float v[32];
@@ -392,11 +398,13 @@ __device__ __forceinline__ void relu_bw_epilogue(uint32_t tmem_work, const unsig
         for (int cc = 0; cc < 4; ++cc) {
             const int c = half32 * 4 + cc;
             const uint4 a = *reinterpret_cast<const uint4 *>(act_tile + act_off(r, c));
-            const __half *ah = reinterpret_cast<const __half *>(&a);
-            float o[8];
+            const __half2 *ah = reinterpret_cast<const __half2 *>(&a);
+            uint4 o;
+            __half2 *oh = reinterpret_cast<__half2 *>(&o);
             #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = (__half2float(ah[j]) > 0.f) ? v[8 * cc + j] : 0.f;
-            *reinterpret_cast<uint4 *>(g_tile + act_off(r, c)) = pack8(o);
+            for (int j = 0; j < 4; ++j)
+                oh[j] = __hmul2(__floats2half2_rn(v[8 * cc + 2 * j], v[8 * cc + 2 * j + 1]), __hgt2(ah[j], zero2));
+            *reinterpret_cast<uint4 *>(g_tile + act_off(r, c)) = o;
         }
     }
 }
@@ -449,6 +457,9 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
     uint64_t *bar = &S.bar_mma[grp];
     const uint32_t tm_d = tmem + grp * 64;                               // dgrad accumulator (lane 0 base) of this group
     uint32_t phase = 0;
+    // The four groups start together and would march through their (identical) phases in lock step -- all issuing
+    // MMAs, then all in the issue-bound epilogue.  A one-off skew of a quarter tile per group interleaves them.
+    if (grp) __nanosleep(grp * 2400);
 
     // Software pipeline: every global->shared tile copy is a cp.async issued ONE STEP AHEAD of its consumer (the
     // buffer roles swap with the tile parity q so that the next tile's first two tiles can be fetched during
