@@ -42,18 +42,18 @@ _SIGS = {
     "b2n_set_march_ctas_per_sm": [_I],
     "b2n_raymarching_test": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],
     "b2n_composite_train_fw": [_P, _P, _P, _P, _P, _F, _L, _P, _P, _P, _P, _P],
-    "b2n_composite_train_bw": [_P] * 13 + [_F, _L, _P, _P, _P],
+    "b2n_composite_train_bw": [_P] * 13 + [_F, _L, _P, _P, _P, _P, _P],
     "b2n_composite_test_fw": [_P, _P, _P, _P, _P, _P, _F, _P, _I, _L, _P, _P, _P, _P],
     "b2n_hashgrid_layout": [_I, _I, _I, _I, _D, C.POINTER(GridLayout)],
     "b2n_hashgrid_fw": [_P, _P, C.POINTER(GridLayout), _L, _P, _P, _I, _P],
-    "b2n_hashgrid_bw": [_P, _P, _I, C.POINTER(GridLayout), _L, _P, _F, _P, _P],
+    "b2n_hashgrid_bw": [_P, _P, _I, C.POINTER(GridLayout), _L, _P, _F, _P, _P, _P],
     "b2n_frequency_fw": [_P, _I, _L, _P, _P, _I, _P],
     "b2n_sh4_fw": [_P, _I, _L, _P, _P, _I, _P],
     "b2n_mlp_fw": [_P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _P],
     "b2n_mlp_bw": [_P, _P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _F, _P, _P, _P],
     "b2n_field_pack_weights": [_P, _P, _P, _P],
     "b2n_field_mlp_fw": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P],
-    "b2n_field_mlp_bw": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P],
+    "b2n_field_mlp_bw": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _L, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P],
     "b2n_cast_half": [_P, _P, _L, _P],
     "b2n_grid_cell_positions": [_P, _P, _L, _I, _F, _F, _F, _I, _P, _P],

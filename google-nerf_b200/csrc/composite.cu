@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
     const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
     const float *__restrict__ ts, const int64_t *__restrict__ rays_a, const float *__restrict__ opacity,
     const float *__restrict__ depth, const float *__restrict__ depth_sq, const float *__restrict__ rgb,
-    float T_threshold, int64_t n_rays, float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs) {
+    float T_threshold, int64_t n_rays, float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs,
+    int32_t *__restrict__ alive_idx, int32_t *alive_count) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
@@ -130,6 +131,17 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
                 }
                 dL_dsigmas[s] = ds;
                 dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
+            }
+            if (alive_idx != nullptr) {
+                // compacted list of the samples that carry gradient (everything after an early stop is exactly zero):
+                // the field / hash-grid backward kernels then skip the dead ones
+                const uint32_t incl_m = __ballot_sync(FULL, incl);
+                if (incl_m) {
+                    int base_i = 0;
+                    if (lane == 0) base_i = atomicAdd(alive_count, __popc(incl_m));
+                    base_i = __shfl_sync(FULL, base_i, 0);
+                    if (incl) alive_idx[base_i + __popc(incl_m & ((1u << lane) - 1))] = (int32_t)s;
+                }
             }
             if (first_dead < 32) stopped = true;
             T_run = __shfl_sync(FULL, T_after, 31);
@@ -182,11 +194,14 @@ extern "C" int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_
                                       const float *rgbs, const float *deltas, const float *ts,
                                       const int64_t *rays_a, const float *opacity, const float *depth,
                                       const float *depth_sq, const float *rgb, float T_threshold,
-                                      int64_t n_rays, float *dL_dsigmas, float *dL_drgbs, void *stream) {
+                                      int64_t n_rays, float *dL_dsigmas, float *dL_drgbs, int32_t *alive_idx,
+                                      int32_t *alive_count, void *stream) {
+    B2N_CHECK_ARG((alive_idx == nullptr) == (alive_count == nullptr), "alive_idx and alive_count go together");
+    if (alive_count != nullptr) cudaMemsetAsync(alive_count, 0, sizeof(int32_t), (cudaStream_t)stream);
     if (n_rays <= 0) return 0;
     composite_train_bw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
         dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb, sigmas, rgbs, deltas, ts, rays_a, opacity, depth,
-        depth_sq, rgb, T_threshold, n_rays, dL_dsigmas, dL_drgbs);
+        depth_sq, rgb, T_threshold, n_rays, dL_dsigmas, dL_drgbs, alive_idx, alive_count);
     B2N_LAUNCH_CHECK();
     return 0;
 }

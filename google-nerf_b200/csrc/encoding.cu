@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
                                                           const __half *__restrict__ dy, int dy_stride,
                                                           const __grid_constant__ GridLevels g, int64_t n,
                                                           const int32_t *__restrict__ n_dev, float grad_scale,
-                                                          float2 *__restrict__ grad_table) {
+                                                          float2 *__restrict__ grad_table,
+                                                          const int32_t *__restrict__ sample_idx) {
     // Warp-aggregated scatter.  The 32 lanes of a warp hold 32 CONSECUTIVE packed samples, i.e. neighbours on a ray
     // (0.0017 apart), so on the coarse levels most lanes fall into the same cell and would hit the same 8 table
     // entries: L2 serialises atomics per address.  For levels whose cells are wide enough (resolution <= AGG_RES)
@@ -182,8 +183,9 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
         const int64_t i = base + lane;
         const bool live = i < n;
         const int64_t ii = live ? i : n - 1;
-        const float px = (__ldg(x + 3 * ii) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * ii + 1) - g.x_offset) * g.x_scale,
-                    pz = (__ldg(x + 3 * ii + 2) - g.x_offset) * g.x_scale;
+        const int64_t xi = sample_idx ? (int64_t)__ldg(sample_idx + ii) : ii;     // compacted backward: row ii <-> sample xi
+        const float px = (__ldg(x + 3 * xi) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * xi + 1) - g.x_offset) * g.x_scale,
+                    pz = (__ldg(x + 3 * xi + 2) - g.x_offset) * g.x_scale;
         const __half2 *row = reinterpret_cast<const __half2 *>(dy + ii * dy_stride);
         #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
@@ -246,13 +248,13 @@ extern "C" int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_
 
 extern "C" int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_stride,
                                const b2n_grid_layout *layout, int64_t n, const int32_t *n_dev,
-                               float grad_scale, float *grad_table, void *stream) {
+                               float grad_scale, float *grad_table, const int32_t *sample_idx, void *stream) {
     GridLevels g;
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(dy_stride >= 2 * g.n_levels && dy_stride % 2 == 0, "dy_stride too small / odd");
     if (n <= 0) return 0;
     hashgrid_bw_kernel<<<b2n_grid(b2n_blocks(n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
-        x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table);
+        x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table, sample_idx);
     B2N_LAUNCH_CHECK();
     return 0;
 }

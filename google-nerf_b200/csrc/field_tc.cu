@@ -319,6 +319,7 @@ struct FieldBwSmem {
     __half w[IMG_HALVES];                               //  20480 B
     unsigned char act[BW_GROUPS][2][TILE64_BYTES];      // 132096 B  activation tiles (ping-pong per group)
     unsigned char g[BW_GROUPS][TILE64_BYTES];           //  66048 B  gradient tile (in place per group)
+    int32_t idx[BW_GROUPS][2][128];                     //   4096 B  sample rows of the current / next tile
     uint64_t bar_w, bar_mma[BW_GROUPS];
     uint32_t tmem_base;
     int lock;
@@ -414,11 +415,11 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
     const float *__restrict__ dirs, const __half *__restrict__ image, int64_t n, const int32_t *__restrict__ n_dev,
     const float *__restrict__ rgbs, const __half *__restrict__ hid_s, const __half *__restrict__ h_in,
     const __half *__restrict__ hid_r, float grad_scale, __half *__restrict__ dL_denc,
-    float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w) {
+    float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w, const int32_t *__restrict__ sample_idx,
+    int64_t n_alloc) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     FieldBwSmem &S = *reinterpret_cast<FieldBwSmem *>(smem_raw);
     const int grp = threadIdx.x >> 7, tid = threadIdx.x & 127, warp = tid >> 5, lane = tid & 31;
-    const int64_t n_alloc = n;
     n = b2n_eff_n(n, n_dev);
     const int64_t n_tiles = (n + 127) / 128;
     if ((int64_t)blockIdx.x * BW_GROUPS >= n_tiles) return;          // uniform per CTA
@@ -469,18 +470,24 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
     int64_t tile = (int64_t)blockIdx.x * BW_GROUPS + grp;
     int q = 0;
     float c5[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};          // rgb (3) and dL/drgb (3) of this thread's row
+    // Row r of a tile is sample IDX[r]: the identity, or an entry of the compacted alive list (sample_idx).
+    int32_t *IDX[2] = {S.idx[grp][0], S.idx[grp][1]};
+    int ib = 0;
     if (tile < n_tiles) {
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
-        tile_load_async<8>(ACT[0], hid_r + (n_alloc + row0) * 64, rows_valid, tid);
-        tile_load_async<8>(ACT[1], hid_r + row0 * 64, rows_valid, tid);
+        const int32_t my_s = (row < n) ? (sample_idx ? __ldg(sample_idx + row) : (int32_t)row) : 0;
+        IDX[0][tid] = my_s;
+        group_sync(grp);
+        tile_gather_async<8>(ACT[0], hid_r + n_alloc * 64, IDX[0], rows_valid, tid);
+        tile_gather_async<8>(ACT[1], hid_r, IDX[0], rows_valid, tid);
         cp_async_commit();
         if (row < n) {
             #pragma unroll
-            for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * row + c); c5[3 + c] = __ldg(dL_drgbs + 3 * row + c); }
+            for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * my_s + c); c5[3 + c] = __ldg(dL_drgbs + 3 * my_s + c); }
         }
     }
     int trace_it = -1;
-    for (; tile < n_tiles; tile += tile_stride, q ^= 1) {
+    for (; tile < n_tiles; tile += tile_stride, q ^= 1, ib ^= 1) {
         ++trace_it; (void)trace_it;
         TRACE(0);
         const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
@@ -490,6 +497,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
         const int64_t next = tile + tile_stride;
         const bool has_next = next < n_tiles;
         const int64_t nrow0 = next * 128, nrow = nrow0 + tid, nrows_valid = n - nrow0;
+        const int64_t my_s = IDX[ib][tid];                                     // this thread's sample row
         // ---- step A prologue: g5 = dL_drgb * sigmoid'(rgb) -> G [128x16]
         float dsx = 0.f, dsy = 0.f, dsz = 1.f, dsig = 0.f;
         {
@@ -501,8 +509,8 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = pack8(g5);
             *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = pack8(g5 + 8);
             if (live) {       // needed in steps B / C: in flight while step A runs
-                dsx = __ldg(dirs + 3 * row); dsy = __ldg(dirs + 3 * row + 1); dsz = __ldg(dirs + 3 * row + 2);
-                dsig = __ldg(dL_dsigmas + row);
+                dsx = __ldg(dirs + 3 * my_s); dsy = __ldg(dirs + 3 * my_s + 1); dsz = __ldg(dirs + 3 * my_s + 2);
+                dsig = __ldg(dL_dsigmas + my_s);
             }
             cp_async_wait_all();                                              // hid_r2 (X) and hid_r1 (Y) have landed
         }
@@ -533,8 +541,8 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             issue_unlock(&S.lock);
         }
         {   // X is free (step A done): colour-net input [SH16 | h16] for step C
-            cp_async16(X + act_off(tid, 2), h_in + row * 16, live);
-            cp_async16(X + act_off(tid, 3), h_in + row * 16 + 8, live);
+            cp_async16(X + act_off(tid, 2), h_in + my_s * 16, live);
+            cp_async16(X + act_off(tid, 3), h_in + my_s * 16 + 8, live);
             cp_async_commit();
             const float inv = 1.0f / sqrtf(dsx * dsx + dsy * dsy + dsz * dsz);
             float sh[16];
@@ -564,7 +572,7 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
-        tile_load_async<8>(Y, hid_s + row0 * 64, rows_valid, tid);            // Y is free (step B done): hid_s for step D
+        tile_gather_async<8>(Y, hid_s, IDX[ib], rows_valid, tid);             // Y is free (step B done): hid_s for step D
         cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
@@ -590,7 +598,9 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             mma_commit(bar);
             issue_unlock(&S.lock);
         }
-        tile_load_async<4>(X, enc + row0 * 32, rows_valid, tid);              // X is free (step C done): enc for step E
+        tile_gather_async<4>(X, enc, IDX[ib], rows_valid, tid);               // X is free (step C done): enc for step E
+        if (has_next)                                                         // next tile's sample rows (visible after the sync below)
+            IDX[ib ^ 1][tid] = (nrow < n) ? (sample_idx ? __ldg(sample_idx + nrow) : (int32_t)nrow) : 0;
         cp_async_commit();
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
@@ -608,19 +618,20 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
             issue_unlock(&S.lock);
         }
         if (has_next) {       // Y is free (step D done): the next tile's step-A tile and its per-row scalars
-            tile_load_async<8>(Y, hid_r + (n_alloc + nrow0) * 64, nrows_valid, tid);
+            tile_gather_async<8>(Y, hid_r + n_alloc * 64, IDX[ib ^ 1], nrows_valid, tid);
             cp_async_commit();
             #pragma unroll
             for (int c = 0; c < 6; ++c) c5[c] = 0.f;
             if (nrow < n) {
+                const int64_t ns = IDX[ib ^ 1][tid];
                 #pragma unroll
-                for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * nrow + c); c5[3 + c] = __ldg(dL_drgbs + 3 * nrow + c); }
+                for (int c = 0; c < 3; ++c) { c5[c] = __ldg(rgbs + 3 * ns + c); c5[3 + c] = __ldg(dL_drgbs + 3 * ns + c); }
             }
         }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
         if (has_next) {       // X is free (step E done): the next tile's step-B tile
-            tile_load_async<8>(X, hid_r + nrow0 * 64, nrows_valid, tid);
+            tile_gather_async<8>(X, hid_r, IDX[ib ^ 1], nrows_valid, tid);
             cp_async_commit();
         }
         {   // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
@@ -669,9 +680,11 @@ __global__ void __launch_bounds__(128 * BW_GROUPS, 1) field_mlp_bw_kernel(
 extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
                                 const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs,
                                 const b2n_half *hid_s, const b2n_half *h, const b2n_half *hid_r, float grad_scale,
-                                b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, void *stream) {
+                                b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx,
+                                int64_t n_alloc, void *stream) {
     B2N_CHECK_ARG(hid_s && h && hid_r && rgbs && dL_denc && grad_sigma_w && grad_rgb_w, "saved activations and outputs are required");
     if (n <= 0) return 0;
+    if (sample_idx == nullptr || n_alloc <= 0) n_alloc = n;
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(field_mlp_bw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FieldBwSmem) + 256);
@@ -681,7 +694,8 @@ extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, 
     field_mlp_bw_kernel<<<b2n_grid((n_tiles + BW_GROUPS - 1) / BW_GROUPS, 1), 128 * BW_GROUPS, sizeof(FieldBwSmem) + 256,
                           (cudaStream_t)stream>>>(
         dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)hid_s,
-        (const __half *)h, (const __half *)hid_r, grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w);
+        (const __half *)h, (const __half *)hid_r, grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w, sample_idx,
+        n_alloc);
     B2N_LAUNCH_CHECK();
     return 0;
 }

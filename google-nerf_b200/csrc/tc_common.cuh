@@ -169,6 +169,19 @@ __device__ __forceinline__ void tile_load_async(unsigned char *tile, const __hal
     }
 }
 
+// gather variant: row r of the tile comes from global row row_idx[r] (row_idx: 128 ints in shared memory)
+template <int NCH>
+__device__ __forceinline__ void tile_gather_async(unsigned char *tile, const __half *g_base, const int32_t *row_idx,
+                                                  int64_t rows_valid, int tid) {
+    #pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+        const int j = i * 128 + tid, row = j / NCH, c = j % NCH;
+        const bool ok = row < rows_valid;
+        const __half *src = g_base + (ok ? ((int64_t)row_idx[row] * (NCH * 8) + c * 8) : 0);
+        cp_async16(tile + (uint32_t)c * 2064u + (uint32_t)row * 16, src, ok);
+    }
+}
+
 // ---- mbarrier ---------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

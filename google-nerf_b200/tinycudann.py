@@ -44,7 +44,7 @@ def hashgrid_fw(x, table16, layout, out=None, n_dev=None):
 
 def hashgrid_bw(x, dy16, layout, grad_table, grad_scale, n_dev=None):
     L.call("b2n_hashgrid_bw", L.ptr(x), L.ptr(dy16), dy16.stride(0), layout, x.shape[0], L.ptr(n_dev),
-           float(grad_scale), L.ptr(grad_table))
+           float(grad_scale), L.ptr(grad_table), None)
 
 
 def frequency_fw(x, n_frequencies, out=None, n_dev=None):

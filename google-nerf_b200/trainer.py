@@ -122,6 +122,7 @@ class NGPTrainer:
         self.zeros_n = torch.zeros(n, device=dev)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
         self.din_enc = e(cap, 32, dt=_f16)
+        self.alive_idx = e(cap, dt=torch.int32); self.alive_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
         self.last_counter = self.sets[0].counter
         self.graphs = {}
 
@@ -164,13 +165,16 @@ class NGPTrainer:
              self.loss_scale, P(self.rgb_out), P(self.loss), P(self.dL_drgb), P(self.dL_dopacity))
         call("b2n_composite_train_bw", P(self.dL_dopacity), P(self.zeros_n), P(self.zeros_n), P(self.dL_drgb),
              P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(self.opacity), P(self.depth),
-             P(self.depth_sq), P(self.rgb), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs))
+             P(self.depth_sq), P(self.rgb), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs),
+             P(self.alive_idx), P(self.alive_cnt))
         # field backward (gradients carry loss_scale; parameter gradients are unscaled inside Adam)
+        # only the samples composited before each ray's early stop carry gradient: the two heavy backward kernels
+        # run over that compacted list (alive_cnt is a device-side count)
         call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), P(s.dirs), P(self.w_image), cap,
-             P(nd), P(self.rgbs), P(self.hid_s), P(self.h), P(self.hid_r), 1.0, P(self.din_enc), P(self.g_xyz),
-             P(self.g_rgb))
-        call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(nd), 1.0,
-             P(self.g_xyz[self.n_mlp:]))
+             P(self.alive_cnt), P(self.rgbs), P(self.hid_s), P(self.h), P(self.hid_r), 1.0, P(self.din_enc),
+             P(self.g_xyz), P(self.g_rgb), P(self.alive_idx), cap)
+        call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(self.alive_cnt), 1.0,
+             P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
 
     def _reduce_grads(self):
         """world > 1: sum the gradients over ranks -- reduce-scatter for the big sharded parameter, all-reduce for the

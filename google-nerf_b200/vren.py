@@ -155,7 +155,7 @@ def composite_train_bw(dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb, sigmas, rg
     dL_drgbs = torch.zeros(N, 3, dtype=_f32, device=dev)
     L.call("b2n_composite_train_bw", *[L.ptr(v) for v in g], L.ptr(sigmas), L.ptr(rgbs), L.ptr(deltas), L.ptr(ts),
            L.ptr(rays_a), *[L.ptr(v) for v in outs], float(T_threshold), rays_a.shape[0], L.ptr(dL_dsigmas),
-           L.ptr(dL_drgbs))
+           L.ptr(dL_drgbs), None, None)
     return dL_dsigmas, dL_drgbs
 
 

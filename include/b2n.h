@@ -91,13 +91,15 @@ B2N_API int b2n_composite_train_fw(const float *sigmas, const float *rgbs, const
                            const int64_t *rays_a, float T_threshold, int64_t n_rays, float *opacity,
                            float *depth, float *depth_sq, float *rgb, void *stream);
 /* vren.composite_train_bw (models/custom_functions.py:153-158).  Writes every sample owned by a ray
- * (zeros after an early stop), so dL_dsigmas/dL_drgbs need no pre-zeroing. */
+ * (zeros after an early stop), so dL_dsigmas/dL_drgbs need no pre-zeroing.  Optional (both or neither):
+ * alive_idx (>= total samples) i32 receives the indices of the samples that carry gradient (those composited
+ * before the ray's early stop), in no particular order, and alive_count (1) i32 their number. */
 B2N_API int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_ddepth, const float *dL_ddepth_sq,
                            const float *dL_drgb, const float *sigmas, const float *rgbs,
                            const float *deltas, const float *ts, const int64_t *rays_a,
                            const float *opacity, const float *depth, const float *depth_sq,
                            const float *rgb, float T_threshold, int64_t n_rays, float *dL_dsigmas,
-                           float *dL_drgbs, void *stream);
+                           float *dL_drgbs, int32_t *alive_idx, int32_t *alive_count, void *stream);
 /* vren.composite_test_fw (models/rendering.py:97-100).  In place on alive_indices/opacity/depth/rgb. */
 B2N_API int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
                           const float *hits_t, int64_t *alive_indices, float T_threshold,
@@ -125,9 +127,11 @@ B2N_API int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_s
 B2N_API int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_grid_layout *layout, int64_t n,
                     const int32_t *n_dev, b2n_half *out, int out_stride, void *stream);
 /* HashGrid backward w.r.t. the table: dL_dout (n, dy_stride) fp16, accumulated (+=) into
- * grad_table fp32 (entries,2) as  grad += dL_dout * weight * grad_scale. */
+ * grad_table fp32 (entries,2) as  grad += dL_dout * weight * grad_scale.  sample_idx (may be NULL): row i of dL_dout
+ * belongs to position x[sample_idx[i]] (compacted backward). */
 B2N_API int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_stride, const b2n_grid_layout *layout,
-                    int64_t n, const int32_t *n_dev, float grad_scale, float *grad_table, void *stream);
+                    int64_t n, const int32_t *n_dev, float grad_scale, float *grad_table, const int32_t *sample_idx,
+                    void *stream);
 /* Frequency encoding (models/networks.py:49-53): x (n,3) -> out (n, out_stride) fp16, 3*n_freq*2 columns
  * then ones up to the next multiple of 16. */
 B2N_API int b2n_frequency_fw(const float *x, int n_frequencies, int64_t n, const int32_t *n_dev, b2n_half *out,
@@ -170,11 +174,15 @@ B2N_API int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2n_h
                              b2n_half *hid_r, void *stream);
 /* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale);
  * writes dL_denc (n,32) fp16 for b2n_hashgrid_bw and accumulates (+=) grad_sigma_w (3072) / grad_rgb_w (7168)
- * fp32 in the flat row-major (out,in) layout of the weights, times grad_scale. */
+ * fp32 in the flat row-major (out,in) layout of the weights, times grad_scale.
+ * sample_idx (may be NULL): compacted list of sample rows to process (b2n_composite_train_bw's alive_idx); then n /
+ * n_dev count list entries, row i of dL_denc belongs to sample sample_idx[i], and n_alloc is the row count of the
+ * saved-activation buffers (the stride between the two hid_r planes).  With NULL, n_alloc = n. */
 B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
                              const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs,
                              const b2n_half *hid_s, const b2n_half *h, const b2n_half *hid_r, float grad_scale,
-                             b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, void *stream);
+                             b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx,
+                             int64_t n_alloc, void *stream);
 
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)

@@ -81,10 +81,29 @@ def test_field_tc_backward(built_lib, n):
     gs = torch.zeros(3072, device=DEV); gr = torch.zeros(7168, device=DEV)
     dsig_d, drgb_d = dsig.to(DEV), drgb.to(DEV)
     L.call("b2n_field_mlp_bw", L.ptr(dsig_d), L.ptr(drgb_d), L.ptr(enc_d), L.ptr(dirs_d), L.ptr(image), n, None,
-           L.ptr(rgb_d), L.ptr(hs_d), L.ptr(h_d), L.ptr(hr_d), 1.0, L.ptr(denc), L.ptr(gs), L.ptr(gr))
+           L.ptr(rgb_d), L.ptr(hs_d), L.ptr(h_d), L.ptr(hr_d), 1.0, L.ptr(denc), L.ptr(gs), L.ptr(gr), None, 0)
     torch.cuda.synchronize()
     for got, want, name in ((gr, pr_r.grad, "rgb weights"), (gs, ps_r.grad, "sigma weights"),
                             (denc.float(), enc_r.grad, "dL/denc")):
         sc = want.abs().max().item()
         err = (got.cpu() - want).abs().max().item()
         assert err <= 5e-3 * sc, (name, err, sc)
+    # compacted form: a shuffled subset of the rows with non-zero upstream gradient gives the same parameter
+    # gradients, and row i of dL/denc belongs to sample idx[i]
+    keep = torch.rand(n, generator=g) < 0.6
+    dsig_m, drgb_m = dsig * keep, drgb * keep[:, None]
+    idx = torch.nonzero(keep)[:, 0]
+    idx = idx[torch.randperm(idx.numel(), generator=g)].to(torch.int32).to(DEV)
+    cnt = torch.tensor([idx.numel(), 0, 0, 0], dtype=torch.int32, device=DEV)
+    denc2 = torch.zeros(n, 32, dtype=torch.float16, device=DEV); gs2 = torch.zeros_like(gs); gr2 = torch.zeros_like(gr)
+    gs_f = torch.zeros_like(gs); gr_f = torch.zeros_like(gr); denc_f = torch.empty_like(denc)
+    dsig_md, drgb_md = dsig_m.to(DEV), drgb_m.to(DEV)
+    common = (L.ptr(dsig_md), L.ptr(drgb_md), L.ptr(enc_d), L.ptr(dirs_d), L.ptr(image), n)
+    L.call("b2n_field_mlp_bw", *common, None, L.ptr(rgb_d), L.ptr(hs_d), L.ptr(h_d), L.ptr(hr_d), 1.0, L.ptr(denc_f),
+           L.ptr(gs_f), L.ptr(gr_f), None, 0)
+    L.call("b2n_field_mlp_bw", *common, L.ptr(cnt), L.ptr(rgb_d), L.ptr(hs_d), L.ptr(h_d), L.ptr(hr_d), 1.0, L.ptr(denc2),
+           L.ptr(gs2), L.ptr(gr2), L.ptr(idx), n)
+    torch.cuda.synchronize()
+    assert (gr2 - gr_f).abs().max().item() <= 2e-3 * gr_f.abs().max().item()
+    assert (gs2 - gs_f).abs().max().item() <= 2e-3 * gs_f.abs().max().item()
+    torch.testing.assert_close(denc2[:idx.numel()].float(), denc_f[idx.long()].float(), rtol=1e-2, atol=1e-3 * denc_f.abs().max().item())

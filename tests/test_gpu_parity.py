@@ -198,6 +198,17 @@ def test_composite_train_fw_bw(mods, scene05, sigma_max, thr):
     # the sigma gradient is a difference of large terms: compare against its own scale
     scale_s = rb[0].abs().max().item() + 1e-12
     assert (gb[0].cpu() - rb[0]).abs().max().item() <= 2e-5 * scale_s
+    # the compacted list of gradient-carrying samples (the ones composited before each ray's early stop)
+    from google_nerf_b200 import _lib as L
+    alive = torch.full((N,), -1, dtype=torch.int32, device=DEV); cnt = torch.full((4,), 77, dtype=torch.int32, device=DEV)
+    ds2 = torch.empty(N, device=DEV); dc2 = torch.empty(N, 3, device=DEV)
+    keep = [dv(v).contiguous() for v in (*grads, sig, col, deltas, ts)] + [dv(rays_a)] + [v.contiguous() for v in got]
+    L.call("b2n_composite_train_bw", *[L.ptr(v) for v in keep], thr, n, L.ptr(ds2), L.ptr(dc2), L.ptr(alive), L.ptr(cnt))
+    mask, idx, incl, *_ = mods["R"]._composite_terms(sig, col, deltas, ts, rays_a, thr)
+    want = torch.sort(idx[incl])[0]
+    k = int(cnt[0].item())
+    assert k == want.numel() and torch.equal(torch.sort(alive[:k].cpu().long())[0], want)
+    assert torch.equal(ds2, gb[0]) and torch.equal(dc2, gb[1])
     # a = 1 - exp(-x) cancels for small x, so one ulp of expf shows up as ~1e-7 absolute in w = a*T
     torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-6)
 
@@ -251,6 +262,14 @@ def test_hashgrid_fw_bw(mods, log2_T):
     mods["tcnn"].hashgrid_bw(x.to(DEV), dy.to(DEV), lay, grad, 1.0)
     scale_g = tab.grad.abs().max().item()
     assert (grad.cpu() - tab.grad).abs().max().item() <= 1e-3 * scale_g
+    # compacted form: rows of dy indexed through sample_idx give the same table gradient
+    from google_nerf_b200 import _lib as L
+    perm = torch.randperm(n, generator=g)
+    xs, dys = x.to(DEV), dy[perm].contiguous().to(DEV)            # row i of dys belongs to position x[perm[i]]
+    idx = perm.to(torch.int32).to(DEV)
+    grad2 = torch.zeros_like(grad)
+    L.call("b2n_hashgrid_bw", L.ptr(xs), L.ptr(dys), 32, lay, n, None, 1.0, L.ptr(grad2), L.ptr(idx))
+    assert (grad2 - grad).abs().max().item() <= 1e-4 * scale_g
 
 
 def test_frequency_and_sh(mods):
