@@ -144,9 +144,14 @@ class NGP(nn.Module):
         for c in range(self.cascades):
             coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=dev)
             indices1 = vren.morton3D(coords1).long()
-            indices2 = torch.nonzero(self.density_grid[c] > 0)[:, 0]
-            pick = torch.randint(len(indices2), (M,), device=dev)
-            indices2 = indices2[pick]
+            # M draws (with replacement) from the occupied cells.  The reference materialises them with
+            # torch.nonzero + randint (networks.py:149-152), which forces a host sync for the dynamic shape; the
+            # same distribution is sampled here on the device: rank k ~ U{0..n_occ-1} -> k-th occupied cell by a
+            # binary search in the inclusive prefix count.
+            cs = torch.cumsum(self.density_grid[c] > 0, 0, dtype=torch.int32)
+            k = (torch.rand(M, device=dev) * cs[-1]).to(torch.int32)
+            k = torch.minimum(k, (cs[-1] - 1).clamp(min=0))
+            indices2 = torch.searchsorted(cs, k, right=True)
             coords2 = vren.morton3D_invert(indices2.int())
             cells.append((torch.cat([indices1, indices2]), torch.cat([coords1, coords2])))
         return cells

@@ -119,6 +119,14 @@ def test_update_density_grid_consistency(pair):
     assert abs(m._grid_stats[0].item() - thr) < 1e-5 * max(1.0, thr)
     ref_bits = np.packbits((grid.cpu().numpy().reshape(-1) > m._grid_stats[0].item()), bitorder="little")
     assert np.array_equal(m.density_bitfield.cpu().numpy(), ref_bits)
+    # the device-side occupied-cell sampler only returns occupied cells, roughly uniformly over them
+    (idx_all, coords_all), = m.sample_uniform_and_occupied_cells(20000)
+    occ_idx = idx_all[20000:]
+    assert bool((grid[0, occ_idx] > 0).all())
+    from google_nerf_b200 import vren
+    assert torch.equal(vren.morton3D(coords_all).long(), idx_all)
+    n_occ = int((grid[0] > 0).sum())
+    assert occ_idx.unique().numel() > 0.9 * min(20000, n_occ) * (1 - np.exp(-20000 / n_occ)) if n_occ else True
     before = grid.clone()
     m.update_density_grid(5.912, warmup=False)                           # uniform + occupied sampling path
     assert float((m.density_grid - before).abs().max()) > 0
