@@ -135,9 +135,7 @@ def kernel_costs(n_rays, n_samples, n_params_xyz, n_params_rgb):
         "b2n_field_mlp_bw": ("hbm", 584 * s),
         "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_sh4_fw": ("hbm", 44 * s),
-        "b2n_composite_train_fw": ("hbm", 24 * s + 48 * r),
-        "b2n_composite_train_bw": ("hbm", 40 * s + 96 * r),
-        "b2n_nerf_loss_fwbw": ("hbm", 56 * r),
+        "b2n_composite_loss_fwbw": ("hbm", 40 * s + 76 * r),
         "b2n_adam_step": ("hbm", None),
     }
 

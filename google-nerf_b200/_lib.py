@@ -43,6 +43,7 @@ _SIGS = {
     "b2n_raymarching_test": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],
     "b2n_composite_train_fw": [_P, _P, _P, _P, _P, _F, _L, _P, _P, _P, _P, _P],
     "b2n_composite_train_bw": [_P] * 13 + [_F, _L, _P, _P, _P, _P, _P],
+    "b2n_composite_loss_fwbw": [_P] * 6 + [_F, _L, _F, _F, _F] + [_P] * 9,
     "b2n_composite_test_fw": [_P, _P, _P, _P, _P, _P, _F, _P, _I, _L, _P, _P, _P, _P],
     "b2n_hashgrid_layout": [_I, _I, _I, _I, _D, C.POINTER(GridLayout)],
     "b2n_hashgrid_fw": [_P, _P, C.POINTER(GridLayout), _L, _P, _P, _I, _P],

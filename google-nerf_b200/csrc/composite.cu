@@ -32,6 +32,107 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+struct RayTotals { float O, D, D2, R, G, B; };
+
+// Forward over one ray's packed samples (all 32 lanes of the warp take part; the totals are warp-uniform).
+__device__ __forceinline__ RayTotals ray_forward(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                                                 const float *__restrict__ deltas, const float *__restrict__ ts,
+                                                 int64_t start, int N, float T_threshold, int lane) {
+    float T_run = 1.0f, aO = 0.f, aD = 0.f, aD2 = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
+    for (int base = 0; base < N; base += 32) {
+        const int k = base + lane;
+        const bool active = k < N;
+        const int64_t s = start + k;
+        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (active) {
+            a = 1.0f - expf(-__ldg(sigmas + s) * __ldg(deltas + s));
+            t = __ldg(ts + s);
+            cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
+        }
+        const float P = warp_scan_mul(1.0f - a, lane);   // prod_{i<=lane} (1-a_i)
+        float Pprev = __shfl_up_sync(FULL, P, 1);
+        if (lane == 0) Pprev = 1.0f;
+        const float T_after = T_run * P, T_before = T_run * Pprev;
+        const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
+        const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
+        if (active && lane <= first_dead) {
+            const float w = a * T_before;
+            aO += w; aD += w * t; aD2 += w * t * t;
+            aR += w * cr; aG += w * cg; aB += w * cb;
+        }
+        if (first_dead < 32) break;
+        T_run = __shfl_sync(FULL, T_after, 31);
+    }
+    RayTotals r;
+    r.O = warp_sum(aO); r.D = warp_sum(aD); r.D2 = warp_sum(aD2);
+    r.R = warp_sum(aR); r.G = warp_sum(aG); r.B = warp_sum(aB);
+    return r;
+}
+
+// Backward over one ray: g* are dL/d(ray outputs), tot the forward totals.
+__device__ __forceinline__ void ray_backward(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                                             const float *__restrict__ deltas, const float *__restrict__ ts,
+                                             int64_t start, int N, float T_threshold, int lane, float gO, float gD,
+                                             float gD2, float gR, float gG, float gB, const RayTotals &tot,
+                                             float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs,
+                                             int32_t *__restrict__ alive_idx, int32_t *alive_count) {
+    // sum_c g_c*(C_c - c_c) + gD*(D-d) + gD2*(D2-d2) = Q_total - q_prefix  (the reference's six terms,
+    // regrouped so that one sum-scan per chunk suffices)
+    const float Q_total = gR * tot.R + gG * tot.G + gB * tot.B + gD * tot.D + gD2 * tot.D2;
+    const float opa_term = gO * (1.0f - tot.O);
+    float T_run = 1.0f, q_run = 0.0f;
+    bool stopped = false;
+    for (int base = 0; base < N; base += 32) {
+        const int k = base + lane;
+        const bool active = k < N;
+        const int64_t s = start + k;
+        if (stopped) {  // samples after an early stop get zero gradient
+            if (active) { dL_dsigmas[s] = 0.f; dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; }
+            continue;
+        }
+        float a = 0.f, t = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+        if (active) {
+            dl = __ldg(deltas + s);
+            a = 1.0f - expf(-__ldg(sigmas + s) * dl);
+            t = __ldg(ts + s);
+            cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
+        }
+        const float P = warp_scan_mul(1.0f - a, lane);
+        float Pprev = __shfl_up_sync(FULL, P, 1);
+        if (lane == 0) Pprev = 1.0f;
+        const float T_after = T_run * P, T_before = T_run * Pprev;
+        const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
+        const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
+        const bool incl = active && lane <= first_dead;
+        const float w = incl ? a * T_before : 0.0f;
+        const float gc = gR * cr + gG * cg + gB * cb + gD * t + gD2 * t * t;
+        const float q_incl = q_run + warp_scan_add(w * gc, lane);
+        if (active) {
+            float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+            if (incl) {
+                dr = gR * w; dg = gG * w; db = gB * w;
+                ds = dl * (gc * T_after - (Q_total - q_incl) + opa_term);
+            }
+            dL_dsigmas[s] = ds;
+            dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
+        }
+        if (alive_idx != nullptr) {
+            // compacted list of the samples that carry gradient (everything after an early stop is exactly zero):
+            // the field / hash-grid backward kernels then skip the dead ones
+            const uint32_t incl_m = __ballot_sync(FULL, incl);
+            if (incl_m) {
+                int base_i = 0;
+                if (lane == 0) base_i = atomicAdd(alive_count, __popc(incl_m));
+                base_i = __shfl_sync(FULL, base_i, 0);
+                if (incl) alive_idx[base_i + __popc(incl_m & ((1u << lane) - 1))] = (int32_t)s;
+            }
+        }
+        if (first_dead < 32) stopped = true;
+        T_run = __shfl_sync(FULL, T_after, 31);
+        q_run = __shfl_sync(FULL, q_incl, 31);
+    }
+}
+
 __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
     const float *__restrict__ ts, const int64_t *__restrict__ rays_a, float T_threshold, int64_t n_rays,
@@ -42,36 +143,10 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
         const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
         const int N = (int)rays_a[3 * n + 2];
-        float T_run = 1.0f, aO = 0.f, aD = 0.f, aD2 = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
-        for (int base = 0; base < N; base += 32) {
-            const int k = base + lane;
-            const bool active = k < N;
-            const int64_t s = start + k;
-            float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-            if (active) {
-                a = 1.0f - expf(-__ldg(sigmas + s) * __ldg(deltas + s));
-                t = __ldg(ts + s);
-                cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
-            }
-            const float P = warp_scan_mul(1.0f - a, lane);   // prod_{i<=lane} (1-a_i)
-            float Pprev = __shfl_up_sync(FULL, P, 1);
-            if (lane == 0) Pprev = 1.0f;
-            const float T_after = T_run * P, T_before = T_run * Pprev;
-            const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
-            const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
-            if (active && lane <= first_dead) {
-                const float w = a * T_before;
-                aO += w; aD += w * t; aD2 += w * t * t;
-                aR += w * cr; aG += w * cg; aB += w * cb;
-            }
-            if (first_dead < 32) break;
-            T_run = __shfl_sync(FULL, T_after, 31);
-        }
-        aO = warp_sum(aO); aD = warp_sum(aD); aD2 = warp_sum(aD2);
-        aR = warp_sum(aR); aG = warp_sum(aG); aB = warp_sum(aB);
+        const RayTotals t = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane);
         if (lane == 0) {
-            opacity[ray] = aO; depth[ray] = aD; depth_sq[ray] = aD2;
-            rgb[3 * ray] = aR; rgb[3 * ray + 1] = aG; rgb[3 * ray + 2] = aB;
+            opacity[ray] = t.O; depth[ray] = t.D; depth_sq[ray] = t.D2;
+            rgb[3 * ray] = t.R; rgb[3 * ray + 1] = t.G; rgb[3 * ray + 2] = t.B;
         }
     }
 }
@@ -89,64 +164,61 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
         const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
         const int N = (int)rays_a[3 * n + 2];
-        const float gR = __ldg(dL_drgb + 3 * ray), gG = __ldg(dL_drgb + 3 * ray + 1), gB = __ldg(dL_drgb + 3 * ray + 2);
-        const float gO = __ldg(dL_dopacity + ray), gD = __ldg(dL_ddepth + ray), gD2 = __ldg(dL_ddepth_sq + ray);
-        // sum_c g_c*(C_c - c_c) + gD*(D-d) + gD2*(D2-d2) = Q_total - q_prefix  (the reference's six terms,
-        // regrouped so that one sum-scan per chunk suffices)
-        const float Q_total = gR * __ldg(rgb + 3 * ray) + gG * __ldg(rgb + 3 * ray + 1) + gB * __ldg(rgb + 3 * ray + 2) +
-                              gD * __ldg(depth + ray) + gD2 * __ldg(depth_sq + ray);
-        const float opa_term = gO * (1.0f - __ldg(opacity + ray));
-        float T_run = 1.0f, q_run = 0.0f;
-        bool stopped = false;
-        for (int base = 0; base < N; base += 32) {
-            const int k = base + lane;
-            const bool active = k < N;
-            const int64_t s = start + k;
-            if (stopped) {  // samples after an early stop get zero gradient
-                if (active) { dL_dsigmas[s] = 0.f; dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; }
-                continue;
-            }
-            float a = 0.f, t = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-            if (active) {
-                dl = __ldg(deltas + s);
-                a = 1.0f - expf(-__ldg(sigmas + s) * dl);
-                t = __ldg(ts + s);
-                cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
-            }
-            const float P = warp_scan_mul(1.0f - a, lane);
-            float Pprev = __shfl_up_sync(FULL, P, 1);
-            if (lane == 0) Pprev = 1.0f;
-            const float T_after = T_run * P, T_before = T_run * Pprev;
-            const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
-            const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
-            const bool incl = active && lane <= first_dead;
-            const float w = incl ? a * T_before : 0.0f;
-            const float gc = gR * cr + gG * cg + gB * cb + gD * t + gD2 * t * t;
-            const float q_incl = q_run + warp_scan_add(w * gc, lane);
-            if (active) {
-                float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
-                if (incl) {
-                    dr = gR * w; dg = gG * w; db = gB * w;
-                    ds = dl * (gc * T_after - (Q_total - q_incl) + opa_term);
-                }
-                dL_dsigmas[s] = ds;
-                dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
-            }
-            if (alive_idx != nullptr) {
-                // compacted list of the samples that carry gradient (everything after an early stop is exactly zero):
-                // the field / hash-grid backward kernels then skip the dead ones
-                const uint32_t incl_m = __ballot_sync(FULL, incl);
-                if (incl_m) {
-                    int base_i = 0;
-                    if (lane == 0) base_i = atomicAdd(alive_count, __popc(incl_m));
-                    base_i = __shfl_sync(FULL, base_i, 0);
-                    if (incl) alive_idx[base_i + __popc(incl_m & ((1u << lane) - 1))] = (int32_t)s;
-                }
-            }
-            if (first_dead < 32) stopped = true;
-            T_run = __shfl_sync(FULL, T_after, 31);
-            q_run = __shfl_sync(FULL, q_incl, 31);
+        RayTotals tot;
+        tot.O = __ldg(opacity + ray); tot.D = __ldg(depth + ray); tot.D2 = __ldg(depth_sq + ray);
+        tot.R = __ldg(rgb + 3 * ray); tot.G = __ldg(rgb + 3 * ray + 1); tot.B = __ldg(rgb + 3 * ray + 2);
+        ray_backward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, __ldg(dL_dopacity + ray),
+                     __ldg(dL_ddepth + ray), __ldg(dL_ddepth_sq + ray), __ldg(dL_drgb + 3 * ray),
+                     __ldg(dL_drgb + 3 * ray + 1), __ldg(dL_drgb + 3 * ray + 2), tot, dL_dsigmas, dL_drgbs,
+                     alive_idx, alive_count);
+    }
+}
+
+// Training fast path: compositing forward, NeRFLoss (losses.py:20-40: MSE + opacity entropy, random-background blend
+// of rendering.py:163-164) and compositing backward of one ray in one warp.  The loss gradient of a ray depends on
+// that ray's totals only, so nothing crosses rays except the scalar loss (one atomicAdd per block).  Saves two
+// launches and the round trip of the per-ray tensors; the second pass over the ray's samples hits L1/L2.
+__global__ void __launch_bounds__(256) composite_loss_fwbw_kernel(
+    const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
+    const float *__restrict__ ts, const int64_t *__restrict__ rays_a, const float *__restrict__ target,
+    float T_threshold, int64_t n_rays, float bg, float lambda_opa, float loss_scale, float *__restrict__ opacity,
+    float *__restrict__ depth, float *__restrict__ rgb_out, float *loss, float *__restrict__ dL_dsigmas,
+    float *__restrict__ dL_drgbs, int32_t *__restrict__ alive_idx, int32_t *alive_count) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const float inv3n = 1.0f / (3.0f * (float)n_rays), invn = 1.0f / (float)n_rays;
+    float part = 0.f;
+    for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
+        const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
+        const int N = (int)rays_a[3 * n + 2];
+        const RayTotals tot = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane);
+        const float c[3] = {tot.R, tot.G, tot.B};
+        float g[3], dsum = 0.f, lray = 0.f;
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = c[k] + bg * (1.0f - tot.O);
+            const float e = v - __ldg(target + 3 * ray + k);
+            if (lane == 0 && rgb_out) rgb_out[3 * ray + k] = v;
+            lray += e * e * inv3n;
+            g[k] = 2.0f * e * inv3n * loss_scale;
+            dsum += g[k];
         }
+        const float o = tot.O + 1e-10f;
+        const float lo = logf(o);
+        lray += lambda_opa * (-o * lo) * invn;
+        const float gO = -bg * dsum + lambda_opa * (-(lo + 1.0f)) * invn * loss_scale;
+        part += lray;                                        // warp-uniform; lane 0's copy is the one that is used
+        if (lane == 0) { opacity[ray] = tot.O; depth[ray] = tot.D; }
+        ray_backward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, gO, 0.f, 0.f, g[0], g[1], g[2], tot,
+                     dL_dsigmas, dL_drgbs, alive_idx, alive_count);
+    }
+    __shared__ float sp[8];
+    if (lane == 0) sp[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int k = 0; k < 8; ++k) s += sp[k];
+        atomicAdd(loss, s);
     }
 }
 
@@ -202,6 +274,24 @@ extern "C" int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_
     composite_train_bw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
         dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb, sigmas, rgbs, deltas, ts, rays_a, opacity, depth,
         depth_sq, rgb, T_threshold, n_rays, dL_dsigmas, dL_drgbs, alive_idx, alive_count);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                                       const int64_t *rays_a, const float *target, float T_threshold,
+                                       int64_t n_rays, float bg, float lambda_opa, float loss_scale,
+                                       float *opacity, float *depth, float *rgb_out, float *loss_dev,
+                                       float *dL_dsigmas, float *dL_drgbs, int32_t *alive_idx,
+                                       int32_t *alive_count, void *stream) {
+    B2N_CHECK_ARG((alive_idx == nullptr) == (alive_count == nullptr), "alive_idx and alive_count go together");
+    B2N_CHECK_ARG(loss_dev != nullptr, "loss_dev is required");
+    if (alive_count != nullptr) cudaMemsetAsync(alive_count, 0, sizeof(int32_t), (cudaStream_t)stream);
+    cudaMemsetAsync(loss_dev, 0, sizeof(float), (cudaStream_t)stream);
+    if (n_rays <= 0) return 0;
+    composite_loss_fwbw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, rays_a, target, T_threshold, n_rays, bg, lambda_opa, loss_scale, opacity, depth,
+        rgb_out, loss_dev, dL_dsigmas, dL_drgbs, alive_idx, alive_count);
     B2N_LAUNCH_CHECK();
     return 0;
 }

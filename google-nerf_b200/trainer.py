@@ -116,10 +116,8 @@ class NGPTrainer:
         self.enc = e(cap, 32, dt=_f16); self.hid_s = e(cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
         self.hid_r = e(2, cap, 64, dt=_f16)
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
-        self.opacity, self.depth, self.depth_sq, self.rgb = e(n), e(n), e(n), e(n, 3)
+        self.opacity, self.depth = e(n), e(n)
         self.rgb_out, self.loss = e(n, 3), torch.zeros(1, device=dev)
-        self.dL_drgb, self.dL_dopacity = e(n, 3), e(n)
-        self.zeros_n = torch.zeros(n, device=dev)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
         self.din_enc = e(cap, 32, dt=_f16)
         self.alive_idx = e(cap, dt=torch.int32); self.alive_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
@@ -158,15 +156,10 @@ class NGPTrainer:
         call("b2n_field_mlp_fw", P(self.enc), P(s.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),
              P(self.hid_s), P(self.h), P(self.hid_r))
         # compositing + loss
-        call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a),
-             self.T_threshold, n, P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb))
-        self.loss.zero_()
-        call("b2n_nerf_loss_fwbw", P(self.rgb), P(self.opacity), P(s.target), n, self.bg, self.lambda_opa,
-             self.loss_scale, P(self.rgb_out), P(self.loss), P(self.dL_drgb), P(self.dL_dopacity))
-        call("b2n_composite_train_bw", P(self.dL_dopacity), P(self.zeros_n), P(self.zeros_n), P(self.dL_drgb),
-             P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(self.opacity), P(self.depth),
-             P(self.depth_sq), P(self.rgb), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs),
-             P(self.alive_idx), P(self.alive_cnt))
+        call("b2n_composite_loss_fwbw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(s.target),
+             self.T_threshold, n, self.bg, self.lambda_opa, self.loss_scale, P(self.opacity), P(self.depth),
+             P(self.rgb_out), P(self.loss), P(self.dL_dsigmas), P(self.dL_drgbs), P(self.alive_idx),
+             P(self.alive_cnt))
         # field backward (gradients carry loss_scale; parameter gradients are unscaled inside Adam)
         # only the samples composited before each ray's early stop carry gradient: the two heavy backward kernels
         # run over that compacted list (alive_cnt is a device-side count)
@@ -225,15 +218,17 @@ class NGPTrainer:
             return
         g = self.graphs.get(key)
         if g is None:
-            g = self._capture(fn, touches_params=key[0] in ("train", "opt"))
+            g = self._capture(fn, touches_params=key[0] in ("train", "opt"), touches_grid=key[0] == "grid")
             self.graphs[key] = g
         g.replay()
 
-    def _capture(self, fn, touches_params):
+    def _capture(self, fn, touches_params, touches_grid=False):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
         state_t = (self.p_pad, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz, self.h_rgb,
                    self.g_xyz, self.g_rgb, self.g_shard)
+        if touches_grid:
+            state_t, touches_params = (self.model.density_grid, self.model.density_bitfield), True
         saved = [t.clone() for t in state_t] if touches_params else None
         warm = torch.cuda.Stream(device=self.dev)
         warm.wait_stream(torch.cuda.current_stream())
@@ -243,7 +238,8 @@ class NGPTrainer:
         if saved is not None:
             for t, sv in zip(state_t, saved):
                 t.copy_(sv)
-            self._pack_weights()
+            if not touches_grid:
+                self._pack_weights()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             fn()
@@ -323,16 +319,26 @@ class NGPTrainer:
 
     @torch.no_grad()
     def update_density_grid(self, warmup=False):
-        """train.py:145-148: threshold 0.01*MAX_SAMPLES/sqrt(3); all ranks end with the same grid."""
-        m = self.model
-        self.sync_model()                                    # the module sees the fp16 copies Adam just wrote
-        m.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=warmup, erode=False)
+        """train.py:145-148: threshold 0.01*MAX_SAMPLES/sqrt(3); all ranks end with the same grid.  The update has no
+        host synchronisation, so it is replayed as a CUDA graph as well (it is ~25 small launches)."""
+        self.sync_model_half()
+        self._run(("grid", bool(warmup)), lambda: self._update_density_grid_body(warmup))
         if self.world > 1:
+            m = self.model
             dist.all_reduce(m.density_grid, op=dist.ReduceOp.MAX, group=self.pg)
             ws = torch.empty(3, dtype=torch.float64, device=self.dev); stats = torch.empty(3, device=self.dev)
             L.call("b2n_grid_threshold", L.ptr(m.density_grid), m.density_grid.numel(),
                    float(0.01 * MAX_SAMPLES / 3 ** 0.5), L.ptr(ws), L.ptr(stats))
             vren.packbits(m.density_grid, 0.0, m.density_bitfield, threshold_dev=stats)
+
+    def _update_density_grid_body(self, warmup):
+        self.model.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=warmup, erode=False)
+
+    def sync_model_half(self):
+        """Hand the fp16 working copies (always current) to the nn.Module view; no communication."""
+        self.model.xyz_encoder.set_half_params(self.h_xyz)
+        self.model.rgb_net.set_half_params(self.h_rgb)
+        self.model._image_key = None              # the fused inference path re-packs its weight image
 
     def overflowed(self):
         """True if the last step hit the sample capacity (host sync; call sparingly)."""
@@ -350,6 +356,4 @@ class NGPTrainer:
         sharded optimiser also gather the fp32 master shards so that state_dict() is complete on every rank)."""
         if self.world > 1:
             dist.all_gather_into_tensor(self.p_pad, self.p_shard, group=self.pg)
-        self.model.xyz_encoder.set_half_params(self.h_xyz)
-        self.model.rgb_net.set_half_params(self.h_rgb)
-        self.model._image_key = None              # the fused inference path re-packs its weight image
+        self.sync_model_half()

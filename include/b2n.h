@@ -100,6 +100,15 @@ B2N_API int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_dde
                            const float *opacity, const float *depth, const float *depth_sq,
                            const float *rgb, float T_threshold, int64_t n_rays, float *dL_dsigmas,
                            float *dL_drgbs, int32_t *alive_idx, int32_t *alive_count, void *stream);
+/* Training fast path: composite_train_fw + NeRFLoss (losses.py:20-40, incl. the random-background blend of
+ * models/rendering.py:163-164) + composite_train_bw of each ray in one launch; the results equal the three separate
+ * calls.  target (n_rays,3); writes opacity/depth (n_rays), rgb_out (n_rays,3, background-blended; may be NULL),
+ * loss_dev (1) fp32 (unscaled loss), dL_dsigmas/dL_drgbs (scaled by loss_scale) and the optional alive list. */
+B2N_API int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                            const int64_t *rays_a, const float *target, float T_threshold, int64_t n_rays,
+                            float bg, float lambda_opa, float loss_scale, float *opacity, float *depth,
+                            float *rgb_out, float *loss_dev, float *dL_dsigmas, float *dL_drgbs,
+                            int32_t *alive_idx, int32_t *alive_count, void *stream);
 /* vren.composite_test_fw (models/rendering.py:97-100).  In place on alive_indices/opacity/depth/rgb. */
 B2N_API int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
                           const float *hits_t, int64_t *alive_indices, float T_threshold,

@@ -213,6 +213,46 @@ def test_composite_train_fw_bw(mods, scene05, sigma_max, thr):
     torch.testing.assert_close(gb[1].cpu(), rb[1], rtol=1e-5, atol=1e-6)
 
 
+def test_composite_loss_fused_equals_separate(mods, scene05):
+    """b2n_composite_loss_fwbw (the trainer's one-launch path) against composite_train_fw -> nerf_loss -> composite_train_bw."""
+    from google_nerf_b200 import _lib as L
+    rays_a, xyzs, dirs, deltas, ts, _ = _packed(mods, scene05)
+    N, n = xyzs.shape[0], rays_a.shape[0]
+    g = torch.Generator().manual_seed(12)
+    dv = lambda t: t.to(DEV).contiguous()
+    sig, col = dv(torch.rand(N, generator=g) * 40.0), dv(torch.rand(N, 3, generator=g))
+    target = dv(torch.rand(n, 3, generator=g))
+    deltas, ts, rays_a = dv(deltas), dv(ts), dv(rays_a)
+    thr, bg, lam, ls = 1e-4, 0.37, 1e-3, 128.0
+    P = L.ptr
+    e = lambda *sh: torch.empty(*sh, device=DEV)
+    op, dp, dp2, rgb = mods["vren"].composite_train_fw(sig, col, deltas, ts, rays_a, thr)
+    rgb_out, loss, d_rgb, d_op = e(n, 3), torch.zeros(1, device=DEV), e(n, 3), e(n)
+    L.call("b2n_nerf_loss_fwbw", P(rgb), P(op), P(target), n, bg, lam, ls, P(rgb_out), P(loss), P(d_rgb), P(d_op))
+    zeros = torch.zeros(n, device=DEV)
+    ds, dc = mods["vren"].composite_train_bw(d_op, zeros, zeros, d_rgb, sig, col, deltas, ts, rays_a, op, dp, dp2, rgb, thr)
+    op2, dp2_, rgb_out2, loss2, ds2, dc2 = e(n), e(n), e(n, 3), torch.full((1,), 5.0, device=DEV), e(N), e(N, 3)
+    alive = torch.empty(N, dtype=torch.int32, device=DEV); cnt = torch.full((4,), 9, dtype=torch.int32, device=DEV)
+    L.call("b2n_composite_loss_fwbw", P(sig), P(col), P(deltas), P(ts), P(rays_a), P(target), thr, n, bg, lam, ls,
+           P(op2), P(dp2_), P(rgb_out2), P(loss2), P(ds2), P(dc2), P(alive), P(cnt))
+    torch.testing.assert_close(op2, op, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(dp2_, dp, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(rgb_out2, rgb_out, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(loss2, loss, rtol=1e-5, atol=0)
+    scale_s = ds.abs().max().item() + 1e-12
+    assert (ds2 - ds).abs().max().item() <= 1e-5 * scale_s
+    torch.testing.assert_close(dc2, dc, rtol=1e-5, atol=1e-7 * ls)
+    # the alive list is the set of samples composited before each ray's early stop
+    mask, idx, incl, *_ = mods["R"]._composite_terms(sig.cpu(), col.cpu(), deltas.cpu(), ts.cpu(), rays_a.cpu(), thr)
+    want = torch.sort(idx[incl])[0]
+    k = int(cnt[0].item())
+    assert k == want.numel() and torch.equal(torch.sort(alive[:k].cpu().long())[0], want)
+    # and the loss against the torch oracle (losses.py:32-40)
+    from oracle import ngp_ref
+    lref = ngp_ref.nerf_loss({"rgb": rgb_out.cpu().double(), "opacity": op.cpu().double()}, target.cpu().double(), lam)
+    assert abs(float(lref) - float(loss2.item())) <= 1e-5 * abs(float(lref))
+
+
 def test_composite_uniform_slab_closed_form(mods):
     # one ray, constant sigma over n equal steps: opacity = 1 - exp(-sigma * L)
     n, sigma, dt = 200, 3.0, 0.01
