@@ -8,8 +8,9 @@
 // path-independent "ladder" t_0, t_1, ...; a rung is probed iff no earlier probed-empty rung set a skip
 // target beyond it.  One warp owns one ray: the 32 lanes hold 32 consecutive rungs, probe the bitfield in
 // parallel (one L2-latency per 32 rungs instead of one per rung), then resolve which rungs the serial
-// loop would have visited with ballots and a short uniform walk over the empty rungs; emitted samples are
-// compacted with a popcount rank.  Results are bit-identical to the serial loop (oracle cross-check).
+// loop would have visited: every rung knows its successor in the serial walk (a binary search over the
+// chunk's rungs for the skip landing), and the visited set is the orbit of the entry rung, found with five
+// rounds of pointer doubling (shuffle + warp OR-reduce); emitted samples are compacted with a popcount rank.  Results are bit-identical to the serial loop (oracle cross-check).
 //
 // The ladder itself is a serial fp32 recurrence, but where the step is constant (exp_step_factor == 0, or the
 // clamped ends of the exponential schedule) and the 32 rungs stay inside one binade, repeated rounding adds
@@ -153,24 +154,31 @@ __device__ __forceinline__ int march_ray(const Ray &r, float t_start, float t2, 
                 const float tm = __shfl_sync(FULL, tj, mid);
                 if (tm < target) lo = mid + 1; else hi = mid;
             }
-            const int next = max(lane + 1, lo);
-            // which rungs does the serial loop visit?  (uniform walk; one iteration per visited empty rung)
+            // rung the serial loop probes after rung j: j+1 after an emitted (occupied) one, the skip landing after an
+            // empty one; 32 = leaves the chunk (or the ray: rungs at or beyond t2 are terminal)
+            int hop = !valid ? 32 : (occ ? lane + 1 : max(lane + 1, lo));
+            // which rungs does the serial loop visit?  The orbit of the entry rung under `hop`, found by pointer
+            // doubling: after round k the set holds every rung within 2^(k+1)-1 hops (5 rounds cover 31 hops).
             const uint32_t reach_m = __ballot_sync(FULL, tj >= pending);
-            int cur = reach_m ? (__ffs(reach_m) - 1) : 32;
-            bool carried = (cur == 32);
-            while (cur < 32) {
-                if (!((valid_m >> cur) & 1)) { done = true; break; }
-                const uint32_t stop_m = (~occ_m) & (FULL << cur);   // first non-occupied (or invalid) rung >= cur
-                const int run_end = stop_m ? (__ffs(stop_m) - 1) : 32;
-                if (run_end > cur) emit_m |= (run_end == 32 ? FULL : ((1u << run_end) - 1)) & (FULL << cur);
-                cur = run_end;
-                if (cur == 32) break;
-                if (!((valid_m >> cur) & 1)) { done = true; break; }
-                const int nx = __shfl_sync(FULL, next, cur);
-                if (nx >= 32) { pending = __shfl_sync(FULL, target, cur); carried = true; cur = 32; }
-                else cur = nx;
+            uint32_t visit_m = reach_m ? (1u << (__ffs(reach_m) - 1)) : 0u;
+            if (visit_m) {
+                #pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const uint32_t contrib = (((visit_m >> lane) & 1) && hop < 32) ? (1u << hop) : 0u;
+                    visit_m |= __reduce_or_sync(FULL, contrib);
+                    const int hop2 = __shfl_sync(FULL, hop, hop & 31);
+                    hop = hop < 32 ? hop2 : 32;
+                }
+                emit_m = visit_m & occ_m;
+                done = (visit_m & ~valid_m) != 0;
+                const int last = 31 - __clz(visit_m);                    // the rung the walk leaves the chunk from
+                const float last_target = __shfl_sync(FULL, target, last);
+                const bool last_occ = (occ_m >> last) & 1;
+                // an occupied last rung is rung 31 (the next chunk starts at its successor); an empty one carries its
+                // skip target into the next chunk
+                pending = last_occ ? NEG_INF : last_target;
             }
-            if (!carried) pending = NEG_INF;
+            // visit_m == 0: no rung of this chunk reaches the pending skip target; it stays pending
         }
         // ---- compaction: rank among emitted rungs, honour the per-ray limit
         const int rank = __popc(emit_m & ((1u << lane) - 1));
