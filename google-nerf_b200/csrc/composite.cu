@@ -34,34 +34,92 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 struct RayTotals { float O, D, D2, R, G, B; };
 
+// A ray is consumed CU chunks of 32 samples at a time: the loads of the CU chunks are issued together and their
+// product / sum scans are independent instruction streams, so a long ray (the kernel's critical path: half of the
+// rays of a batch are empty, the rest carry 100-1000 samples) costs one memory latency and one scan latency per
+// 32*CU samples.  The arithmetic per chunk -- and so every result bit -- is that of the one-chunk-at-a-time form.
+#define CU 4
+
+__device__ __forceinline__ void warp_scan_mul_cu(float (&v)[CU], int lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const float w = __shfl_up_sync(FULL, v[u], o);
+            if (lane >= o) v[u] *= w;
+        }
+    }
+}
+__device__ __forceinline__ void warp_scan_add_cu(float (&v)[CU], int lane) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const float w = __shfl_up_sync(FULL, v[u], o);
+            if (lane >= o) v[u] += w;
+        }
+    }
+}
+
+// Transmittance entering each of the CU chunks and after the last one.  The serial form carries
+// T_run <- (T_run * P)[lane 31] from chunk to chunk; the same products are formed here from the chunk tails, so the
+// values are bit-identical while the CU chunks no longer wait for one another.
+__device__ __forceinline__ float chunk_entries(const float (&P)[CU], float T_run, float (&Tr)[CU]) {
+    float E[CU];
+    #pragma unroll
+    for (int u = 0; u < CU; ++u) E[u] = __shfl_sync(FULL, P[u], 31);
+    #pragma unroll
+    for (int u = 0; u < CU; ++u) { Tr[u] = T_run; T_run = T_run * E[u]; }
+    return T_run;
+}
+
 // Forward over one ray's packed samples (all 32 lanes of the warp take part; the totals are warp-uniform).
+// n_incl receives the number of samples composited (everything up to and including the one that triggers the early
+// stop): they form a prefix of the ray.
 __device__ __forceinline__ RayTotals ray_forward(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
                                                  const float *__restrict__ deltas, const float *__restrict__ ts,
-                                                 int64_t start, int N, float T_threshold, int lane) {
+                                                 int64_t start, int N, float T_threshold, int lane, int &n_incl) {
     float T_run = 1.0f, aO = 0.f, aD = 0.f, aD2 = 0.f, aR = 0.f, aG = 0.f, aB = 0.f;
-    for (int base = 0; base < N; base += 32) {
-        const int k = base + lane;
-        const bool active = k < N;
-        const int64_t s = start + k;
-        float a = 0.f, t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        if (active) {
-            a = 1.0f - expf(-__ldg(sigmas + s) * __ldg(deltas + s));
-            t = __ldg(ts + s);
-            cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
+    bool stopped = false;
+    n_incl = N;
+    for (int base = 0; base < N && !stopped; base += 32 * CU) {
+        float a[CU], t[CU], cr[CU], cg[CU], cb[CU], P[CU], Tr[CU];
+        bool active[CU];
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int k = base + 32 * u + lane;
+            active[u] = k < N;
+            const int64_t s = start + k;
+            a[u] = 0.f; t[u] = 0.f; cr[u] = 0.f; cg[u] = 0.f; cb[u] = 0.f;
+            if (active[u]) {
+                a[u] = 1.0f - expf(-__ldg(sigmas + s) * __ldg(deltas + s));
+                t[u] = __ldg(ts + s);
+                cr[u] = __ldg(rgbs + 3 * s); cg[u] = __ldg(rgbs + 3 * s + 1); cb[u] = __ldg(rgbs + 3 * s + 2);
+            }
+            P[u] = 1.0f - a[u];
         }
-        const float P = warp_scan_mul(1.0f - a, lane);   // prod_{i<=lane} (1-a_i)
-        float Pprev = __shfl_up_sync(FULL, P, 1);
-        if (lane == 0) Pprev = 1.0f;
-        const float T_after = T_run * P, T_before = T_run * Pprev;
-        const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
-        const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
-        if (active && lane <= first_dead) {
-            const float w = a * T_before;
-            aO += w; aD += w * t; aD2 += w * t * t;
-            aR += w * cr; aG += w * cg; aB += w * cb;
+        warp_scan_mul_cu(P, lane);                           // P[u] = prod_{i<=lane} (1-a_i) within chunk u
+        T_run = chunk_entries(P, T_run, Tr);
+        float T_before[CU];
+        uint32_t dead_m[CU];
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            float Pprev = __shfl_up_sync(FULL, P[u], 1);
+            if (lane == 0) Pprev = 1.0f;
+            T_before[u] = Tr[u] * Pprev;
+            dead_m[u] = __ballot_sync(FULL, active[u] && !(Tr[u] * P[u] > T_threshold));
         }
-        if (first_dead < 32) break;
-        T_run = __shfl_sync(FULL, T_after, 31);
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            if (stopped) break;
+            const int first_dead = dead_m[u] ? (__ffs(dead_m[u]) - 1) : 32;
+            if (active[u] && lane <= first_dead) {
+                const float w = a[u] * T_before[u];
+                aO += w; aD += w * t[u]; aD2 += w * t[u] * t[u];
+                aR += w * cr[u]; aG += w * cg[u]; aB += w * cb[u];
+            }
+            if (first_dead < 32) { stopped = true; n_incl = base + 32 * u + first_dead + 1; }
+        }
     }
     RayTotals r;
     r.O = warp_sum(aO); r.D = warp_sum(aD); r.D2 = warp_sum(aD2);
@@ -69,68 +127,101 @@ __device__ __forceinline__ RayTotals ray_forward(const float *__restrict__ sigma
     return r;
 }
 
-// Backward over one ray: g* are dL/d(ray outputs), tot the forward totals.
-__device__ __forceinline__ void ray_backward(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
-                                             const float *__restrict__ deltas, const float *__restrict__ ts,
-                                             int64_t start, int N, float T_threshold, int lane, float gO, float gD,
-                                             float gD2, float gR, float gG, float gB, const RayTotals &tot,
-                                             float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs,
-                                             int32_t *__restrict__ alive_idx, int32_t *alive_count) {
+// Backward over one ray: g* are dL/d(ray outputs), tot the forward totals.  Returns the number of samples that
+// carry gradient (the composited prefix of the ray); the rest get exact zeros.
+__device__ __forceinline__ int ray_backward(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                                            const float *__restrict__ deltas, const float *__restrict__ ts,
+                                            int64_t start, int N, float T_threshold, int lane, float gO, float gD,
+                                            float gD2, float gR, float gG, float gB, const RayTotals &tot,
+                                            float *__restrict__ dL_dsigmas, float *__restrict__ dL_drgbs) {
     // sum_c g_c*(C_c - c_c) + gD*(D-d) + gD2*(D2-d2) = Q_total - q_prefix  (the reference's six terms,
     // regrouped so that one sum-scan per chunk suffices)
     const float Q_total = gR * tot.R + gG * tot.G + gB * tot.B + gD * tot.D + gD2 * tot.D2;
     const float opa_term = gO * (1.0f - tot.O);
     float T_run = 1.0f, q_run = 0.0f;
     bool stopped = false;
-    for (int base = 0; base < N; base += 32) {
-        const int k = base + lane;
-        const bool active = k < N;
-        const int64_t s = start + k;
+    int n_incl = N;
+    for (int base = 0; base < N; base += 32 * CU) {
         if (stopped) {  // samples after an early stop get zero gradient
-            if (active) { dL_dsigmas[s] = 0.f; dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; }
+            #pragma unroll
+            for (int u = 0; u < CU; ++u) {
+                const int k = base + 32 * u + lane;
+                const int64_t s = start + k;
+                if (k < N) { dL_dsigmas[s] = 0.f; dL_drgbs[3 * s] = 0.f; dL_drgbs[3 * s + 1] = 0.f; dL_drgbs[3 * s + 2] = 0.f; }
+            }
             continue;
         }
-        float a = 0.f, t = 0.f, dl = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
-        if (active) {
-            dl = __ldg(deltas + s);
-            a = 1.0f - expf(-__ldg(sigmas + s) * dl);
-            t = __ldg(ts + s);
-            cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
-        }
-        const float P = warp_scan_mul(1.0f - a, lane);
-        float Pprev = __shfl_up_sync(FULL, P, 1);
-        if (lane == 0) Pprev = 1.0f;
-        const float T_after = T_run * P, T_before = T_run * Pprev;
-        const uint32_t dead_m = __ballot_sync(FULL, active && !(T_after > T_threshold));
-        const int first_dead = dead_m ? (__ffs(dead_m) - 1) : 32;
-        const bool incl = active && lane <= first_dead;
-        const float w = incl ? a * T_before : 0.0f;
-        const float gc = gR * cr + gG * cg + gB * cb + gD * t + gD2 * t * t;
-        const float q_incl = q_run + warp_scan_add(w * gc, lane);
-        if (active) {
-            float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
-            if (incl) {
-                dr = gR * w; dg = gG * w; db = gB * w;
-                ds = dl * (gc * T_after - (Q_total - q_incl) + opa_term);
+        float a[CU], dl[CU], gc[CU], P[CU], Tr[CU], wq[CU], w[CU], T_after[CU], T_before[CU];
+        bool active[CU], incl[CU];
+        uint32_t dead_m[CU];
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int k = base + 32 * u + lane;
+            active[u] = k < N;
+            const int64_t s = start + k;
+            float t = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            a[u] = 0.f; dl[u] = 0.f;
+            if (active[u]) {
+                dl[u] = __ldg(deltas + s);
+                a[u] = 1.0f - expf(-__ldg(sigmas + s) * dl[u]);
+                t = __ldg(ts + s);
+                cr = __ldg(rgbs + 3 * s); cg = __ldg(rgbs + 3 * s + 1); cb = __ldg(rgbs + 3 * s + 2);
             }
-            dL_dsigmas[s] = ds;
-            dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
+            gc[u] = gR * cr + gG * cg + gB * cb + gD * t + gD2 * t * t;
+            P[u] = 1.0f - a[u];
         }
-        if (alive_idx != nullptr) {
-            // compacted list of the samples that carry gradient (everything after an early stop is exactly zero):
-            // the field / hash-grid backward kernels then skip the dead ones
-            const uint32_t incl_m = __ballot_sync(FULL, incl);
-            if (incl_m) {
-                int base_i = 0;
-                if (lane == 0) base_i = atomicAdd(alive_count, __popc(incl_m));
-                base_i = __shfl_sync(FULL, base_i, 0);
-                if (incl) alive_idx[base_i + __popc(incl_m & ((1u << lane) - 1))] = (int32_t)s;
+        warp_scan_mul_cu(P, lane);
+        T_run = chunk_entries(P, T_run, Tr);
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            float Pprev = __shfl_up_sync(FULL, P[u], 1);
+            if (lane == 0) Pprev = 1.0f;
+            T_after[u] = Tr[u] * P[u];
+            T_before[u] = Tr[u] * Pprev;
+            dead_m[u] = __ballot_sync(FULL, active[u] && !(T_after[u] > T_threshold));
+        }
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int first_dead = dead_m[u] ? (__ffs(dead_m[u]) - 1) : 32;
+            incl[u] = !stopped && active[u] && lane <= first_dead;
+            w[u] = incl[u] ? a[u] * T_before[u] : 0.0f;
+            wq[u] = w[u] * gc[u];
+            if (!stopped && first_dead < 32) { stopped = true; n_incl = base + 32 * u + first_dead + 1; }
+        }
+        warp_scan_add_cu(wq, lane);
+        float tails[CU];
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) tails[u] = __shfl_sync(FULL, wq[u], 31);
+        #pragma unroll
+        for (int u = 0; u < CU; ++u) {
+            const int64_t s = start + base + 32 * u + lane;
+            const float q_incl = q_run + wq[u];
+            if (active[u]) {
+                float ds = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+                if (incl[u]) {
+                    dr = gR * w[u]; dg = gG * w[u]; db = gB * w[u];
+                    ds = dl[u] * (gc[u] * T_after[u] - (Q_total - q_incl) + opa_term);
+                }
+                dL_dsigmas[s] = ds;
+                dL_drgbs[3 * s] = dr; dL_drgbs[3 * s + 1] = dg; dL_drgbs[3 * s + 2] = db;
             }
+            q_run = q_run + tails[u];                        // = q_incl of lane 31
         }
-        if (first_dead < 32) stopped = true;
-        T_run = __shfl_sync(FULL, T_after, 31);
-        q_run = __shfl_sync(FULL, q_incl, 31);
     }
+    return n_incl;
+}
+
+// Appends the composited prefix [start, start + n_incl) of a ray to the compacted list of gradient-carrying samples
+// (one atomicAdd per ray; the field / hash-grid backward kernels then skip the dead samples).
+__device__ __forceinline__ int alive_reserve(int32_t *alive_count, int n_incl, int lane) {
+    int base_i = 0;
+    if (lane == 0 && n_incl > 0) base_i = atomicAdd(alive_count, n_incl);
+    return base_i;                                           // lane 0's value is the one that counts
+}
+__device__ __forceinline__ void alive_emit(int32_t *__restrict__ alive_idx, int base_lane0, int64_t start, int n_incl,
+                                           int lane) {
+    const int base_i = __shfl_sync(FULL, base_lane0, 0);
+    for (int k = lane; k < n_incl; k += 32) alive_idx[base_i + k] = (int32_t)(start + k);
 }
 
 __global__ void __launch_bounds__(256) composite_train_fw_kernel(
@@ -143,7 +234,8 @@ __global__ void __launch_bounds__(256) composite_train_fw_kernel(
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
         const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
         const int N = (int)rays_a[3 * n + 2];
-        const RayTotals t = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane);
+        int n_incl;
+        const RayTotals t = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, n_incl);
         if (lane == 0) {
             opacity[ray] = t.O; depth[ray] = t.D; depth_sq[ray] = t.D2;
             rgb[3 * ray] = t.R; rgb[3 * ray + 1] = t.G; rgb[3 * ray + 2] = t.B;
@@ -167,10 +259,11 @@ __global__ void __launch_bounds__(256) composite_train_bw_kernel(
         RayTotals tot;
         tot.O = __ldg(opacity + ray); tot.D = __ldg(depth + ray); tot.D2 = __ldg(depth_sq + ray);
         tot.R = __ldg(rgb + 3 * ray); tot.G = __ldg(rgb + 3 * ray + 1); tot.B = __ldg(rgb + 3 * ray + 2);
-        ray_backward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, __ldg(dL_dopacity + ray),
-                     __ldg(dL_ddepth + ray), __ldg(dL_ddepth_sq + ray), __ldg(dL_drgb + 3 * ray),
-                     __ldg(dL_drgb + 3 * ray + 1), __ldg(dL_drgb + 3 * ray + 2), tot, dL_dsigmas, dL_drgbs,
-                     alive_idx, alive_count);
+        const int n_incl = ray_backward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, __ldg(dL_dopacity + ray),
+                                        __ldg(dL_ddepth + ray), __ldg(dL_ddepth_sq + ray), __ldg(dL_drgb + 3 * ray),
+                                        __ldg(dL_drgb + 3 * ray + 1), __ldg(dL_drgb + 3 * ray + 2), tot, dL_dsigmas,
+                                        dL_drgbs);
+        if (alive_idx != nullptr) alive_emit(alive_idx, alive_reserve(alive_count, n_incl, lane), start, n_incl, lane);
     }
 }
 
@@ -191,7 +284,10 @@ __global__ void __launch_bounds__(256) composite_loss_fwbw_kernel(
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
         const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
         const int N = (int)rays_a[3 * n + 2];
-        const RayTotals tot = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane);
+        int n_incl;
+        const RayTotals tot = ray_forward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, n_incl);
+        // reserve the ray's slots in the alive list now; the returned offset is only needed after the backward pass
+        const int alive_base = alive_idx != nullptr ? alive_reserve(alive_count, n_incl, lane) : 0;
         const float c[3] = {tot.R, tot.G, tot.B};
         float g[3], dsum = 0.f, lray = 0.f;
         #pragma unroll
@@ -210,7 +306,8 @@ __global__ void __launch_bounds__(256) composite_loss_fwbw_kernel(
         part += lray;                                        // warp-uniform; lane 0's copy is the one that is used
         if (lane == 0) { opacity[ray] = tot.O; depth[ray] = tot.D; }
         ray_backward(sigmas, rgbs, deltas, ts, start, N, T_threshold, lane, gO, 0.f, 0.f, g[0], g[1], g[2], tot,
-                     dL_dsigmas, dL_drgbs, alive_idx, alive_count);
+                     dL_dsigmas, dL_drgbs);
+        if (alive_idx != nullptr) alive_emit(alive_idx, alive_base, start, n_incl, lane);
     }
     __shared__ float sp[8];
     if (lane == 0) sp[threadIdx.x >> 5] = part;

@@ -143,7 +143,7 @@ class NGP(nn.Module):
         dev = self.density_grid.device
         for c in range(self.cascades):
             coords1 = torch.randint(self.grid_size, (M, 3), dtype=torch.int32, device=dev)
-            indices1 = vren.morton3D(coords1).long()
+            indices1 = vren.morton3D(coords1)
             # M draws (with replacement) from the occupied cells.  The reference materialises them with
             # torch.nonzero + randint (networks.py:149-152), which forces a host sync for the dynamic shape; the
             # same distribution is sampled here on the device: rank k ~ U{0..n_occ-1} -> k-th occupied cell by a
@@ -152,8 +152,11 @@ class NGP(nn.Module):
             k = (torch.rand(M, device=dev) * cs[-1]).to(torch.int32)
             k = torch.minimum(k, (cs[-1] - 1).clamp(min=0))
             indices2 = torch.searchsorted(cs, k, right=True)
-            coords2 = vren.morton3D_invert(indices2.int())
-            cells.append((torch.cat([indices1, indices2]), torch.cat([coords1, coords2])))
+            # the order of the cells is immaterial (each one scatters into its own slot), so evaluate them in Morton
+            # order: neighbouring cells share hash-grid corners, which turns most of the coarse-level gathers of the
+            # 1M-cell density query into L1 hits
+            indices = torch.sort(torch.cat([indices1.int(), indices2.int()]))[0]
+            cells.append((indices.long(), vren.morton3D_invert(indices)))
         return cells
 
     @torch.no_grad()
