@@ -289,7 +289,7 @@ def main():
         costs = kernel_costs(N_RAYS, samples, tr.p_xyz.numel(), tr.p_rgb.numel())
         # the dominant kernel of the step's critical path (ray generation / AABB / marching of the NEXT batch run on
         # the side stream underneath it and are reported separately in `marcher`)
-        side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near")
+        side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near", "b2n_rays_from_indices")
         top = max((k for k in table if not k.startswith(side)), key=table.get)
         base = top.split("[")[0]
         bound = costs.get(base, ("hbm", None))[0]

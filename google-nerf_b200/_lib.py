@@ -34,6 +34,7 @@ _SIGS = {
     "b2n_ray_aabb_intersect": [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "b2n_ray_sphere_intersect": [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "b2n_clamp_near": [_P, _L, _F, _P],
+    "b2n_rays_from_indices": [_P, _P, _P, _P, _L, _P, _P, _P],
     "b2n_morton3D": [_P, _L, _P, _P],
     "b2n_morton3D_invert": [_P, _L, _P, _P],
     "b2n_packbits": [_P, _L, _F, _P, _P, _P],

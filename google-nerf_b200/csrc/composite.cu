@@ -383,8 +383,12 @@ extern "C" int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, c
                                        int32_t *alive_count, void *stream) {
     B2N_CHECK_ARG((alive_idx == nullptr) == (alive_count == nullptr), "alive_idx and alive_count go together");
     B2N_CHECK_ARG(loss_dev != nullptr, "loss_dev is required");
-    if (alive_count != nullptr) cudaMemsetAsync(alive_count, 0, sizeof(int32_t), (cudaStream_t)stream);
-    cudaMemsetAsync(loss_dev, 0, sizeof(float), (cudaStream_t)stream);
+    if (alive_count != nullptr && (void *)loss_dev == (void *)(alive_count + 1)) {
+        cudaMemsetAsync(alive_count, 0, 8, (cudaStream_t)stream);     // adjacent words: one clear for both
+    } else {
+        if (alive_count != nullptr) cudaMemsetAsync(alive_count, 0, sizeof(int32_t), (cudaStream_t)stream);
+        cudaMemsetAsync(loss_dev, 0, sizeof(float), (cudaStream_t)stream);
+    }
     if (n_rays <= 0) return 0;
     composite_loss_fwbw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, target, T_threshold, n_rays, bg, lambda_opa, loss_scale, opacity, depth,

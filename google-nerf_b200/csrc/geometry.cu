@@ -151,6 +151,37 @@ extern "C" int b2n_clamp_near(float *hits_t, int64_t n_rays, float near_distance
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ ray generation
+// get_rays (ngp_pl/datasets/ray_utils.py:152-175) for a batch drawn as (img_idxs, pix_idxs) (datasets/base.py:24-40):
+// rays_d = directions[pix] @ c2w[img][:, :3]^T, rays_o = c2w[img][:, 3].  One thread per ray; no FMA contraction in
+// this file, the three products are summed left to right.
+__global__ void __launch_bounds__(256) rays_from_indices_kernel(const float *__restrict__ directions,
+                                                                const float *__restrict__ poses,
+                                                                const int64_t *__restrict__ img_idxs,
+                                                                const int64_t *__restrict__ pix_idxs, int64_t n,
+                                                                float *__restrict__ rays_o, float *__restrict__ rays_d) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *d = directions + 3 * pix_idxs[i];
+    const float *c = poses + 12 * img_idxs[i];
+    const float d0 = __ldg(d), d1 = __ldg(d + 1), d2 = __ldg(d + 2);
+    #pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        rays_d[3 * i + a] = d0 * __ldg(c + 4 * a) + d1 * __ldg(c + 4 * a + 1) + d2 * __ldg(c + 4 * a + 2);
+        rays_o[3 * i + a] = __ldg(c + 4 * a + 3);
+    }
+}
+
+extern "C" int b2n_rays_from_indices(const float *directions, const float *poses, const int64_t *img_idxs,
+                                     const int64_t *pix_idxs, int64_t n_rays, float *rays_o, float *rays_d,
+                                     void *stream) {
+    if (n_rays <= 0) return 0;
+    rays_from_indices_kernel<<<b2n_blocks(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(
+        directions, poses, img_idxs, pix_idxs, n_rays, rays_o, rays_d);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 __global__ void morton3D_kernel(const int32_t *__restrict__ coords, int64_t n, int32_t *__restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

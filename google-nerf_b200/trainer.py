@@ -70,6 +70,7 @@ class NGPTrainer:
         self._from_indices = False
         self.directions = self.poses = None
         self.side = torch.cuda.Stream(device=self.dev)
+        self._fork = torch.cuda.Event()
         import os
         self.march_ctas = int(march_ctas_per_sm if march_ctas_per_sm is not None else os.environ.get("B2N_MARCH_CTAS", 8))
 
@@ -117,10 +118,13 @@ class NGPTrainer:
         self.hid_r = e(2, cap, 64, dt=_f16)
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
         self.opacity, self.depth = e(n), e(n)
-        self.rgb_out, self.loss = e(n, 3), torch.zeros(1, device=dev)
+        self.rgb_out = e(n, 3)
+        # [alive count, loss] side by side, so that the compositing launch clears both with one memset
+        self._scalars = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.alive_cnt, self.loss = self._scalars[0:1], self._scalars[1:2].view(_f32)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
         self.din_enc = e(cap, 32, dt=_f16)
-        self.alive_idx = e(cap, dt=torch.int32); self.alive_cnt = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.alive_idx = e(cap, dt=torch.int32)
         self.last_counter = self.sets[0].counter
         self.graphs = {}
 
@@ -132,10 +136,8 @@ class NGPTrainer:
         L.call_nostream("b2n_set_march_ctas_per_sm", self.march_ctas)    # grid size is baked into a captured graph
         if self._from_indices:
             # get_rays (datasets/ray_utils.py:152-175): rotate camera-frame directions, origin = camera centre
-            c2w = self.poses[s.img_idxs]
-            d = self.directions[s.pix_idxs]
-            torch.bmm(d[:, None], c2w[..., :3].transpose(1, 2), out=s.rays_d.view(-1, 1, 3))
-            s.rays_o.copy_(c2w[..., 3])
+            call("b2n_rays_from_indices", P(self.directions), P(self.poses), P(s.img_idxs), P(s.pix_idxs), n,
+                 P(s.rays_o), P(s.rays_d))
         call("b2n_ray_aabb_intersect", P(s.rays_o), P(s.rays_d), P(m.center), P(m.half_size), n, 1, 1,
              P(s.hits_cnt), P(s.hits_t), P(s.hits_idx))
         call("b2n_clamp_near", P(s.hits_t), n, NEAR_DISTANCE)
@@ -197,18 +199,11 @@ class NGPTrainer:
         """fp16 MLP weights -> UMMA canonical shared-memory image for the fused field kernels."""
         L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image))
 
-    def _train(self, p, prefetch):
-        """Train on sample set p; with prefetch, march set 1-p concurrently on the side stream (fork / join)."""
-        main = torch.cuda.current_stream()
-        if prefetch:
-            self.side.wait_stream(main)
-            with torch.cuda.stream(self.side):
-                self._march(self.sets[1 - p])
+    def _train(self, p):
+        """Forward, backward and (single rank) the optimiser on sample set p."""
         self._forward_backward(self.sets[p])
         if self.world == 1:
             self._optimizer()
-        if prefetch:
-            main.wait_stream(self.side)
 
     # ------------------------------------------------------------------ graphs
     def _run(self, key, fn):
@@ -257,6 +252,10 @@ class NGPTrainer:
         """Copy one batch (host pinned or device tensors) into sample set s.  batch = (rays_o, rays_d, rgb) or the
         reference's {img_idxs, pix_idxs, rgb} dict (datasets/base.py:28-33)."""
         from_idx = isinstance(batch, dict)
+        cur = torch.cuda.current_stream()
+        for t in (batch.values() if from_idx else batch):
+            if t.is_cuda:
+                t.record_stream(cur)                         # the copy may run on the side stream
         if from_idx != self._from_indices:
             self._from_indices, self.graphs = from_idx, {}
         if from_idx:
@@ -293,13 +292,24 @@ class NGPTrainer:
         if not s.marched:
             self._run(("march", p), lambda: self._march(s))
         prefetch = next_batch is not None and (self.step_count % self.S != 0)
+        main = torch.cuda.current_stream()
         if prefetch:
-            self._load(self.sets[1 - p], next_batch)
-        self._run(("train", p, prefetch), lambda: self._train(p, prefetch))
+            self._fork.record(main)
+        self._run(("train", p), lambda: self._train(p))      # issued first: the GPU starts on it while the host goes on
+        if prefetch:
+            # the next batch is loaded and marched on the side stream while this one trains: its copies and the march
+            # graph are ordered after everything issued before this step's training graph (the previous step's use of
+            # that sample set) and the main stream joins at the end of the step
+            self.side.wait_event(self._fork)
+            with torch.cuda.stream(self.side):
+                self._load(self.sets[1 - p], next_batch)
+                self._run(("march", 1 - p), lambda: self._march(self.sets[1 - p]))
         if self.world > 1:                                   # NCCL collectives stay outside the captured graphs
             self._reduce_grads()
             self._run(("opt",), self._optimizer)
             self._gather_params()
+        if prefetch:
+            main.wait_stream(self.side)
         s.marched = False
         self.last_counter = s.counter
         if next_batch is not None:

@@ -43,6 +43,12 @@ B2N_API int b2n_ray_sphere_intersect(const float *rays_o, const float *rays_d, c
 /* rendering.py:29 -- hits_t[(t1>=0)&(t1<near)] = near, in place on hits_t (n_rays,1,2). */
 B2N_API int b2n_clamp_near(float *hits_t, int64_t n_rays, float near_distance, void *stream);
 
+/* get_rays (datasets/ray_utils.py:152-175) of a batch drawn as indices (datasets/base.py:24-40; train.py:150-157):
+ * directions (H*W,3) camera-frame, poses (N_img,3,4) c2w, img_idxs / pix_idxs (n_rays) i64 (no bounds checks) ->
+ * rays_o, rays_d (n_rays,3). */
+B2N_API int b2n_rays_from_indices(const float *directions, const float *poses, const int64_t *img_idxs,
+                          const int64_t *pix_idxs, int64_t n_rays, float *rays_o, float *rays_d, void *stream);
+
 /* ---------------------------------------------------------------- vren: Morton / bitfield ------------ */
 /* vren.morton3D (models/networks.py:128,147): coords (n,3) i32 -> indices (n) i32. */
 B2N_API int b2n_morton3D(const int32_t *coords, int64_t n, int32_t *indices, void *stream);

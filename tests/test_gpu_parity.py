@@ -265,6 +265,21 @@ def test_composite_uniform_slab_closed_form(mods):
     assert abs(out[3][0, 1].item() - expect) < 1e-5 * expect
 
 
+def test_rays_from_indices(mods):
+    """b2n_rays_from_indices against get_rays (datasets/ray_utils.py:152-175) on the synthetic cameras."""
+    from google_nerf_b200 import _lib as L, synthetic as syn
+    K = syn.intrinsics(64, 48); dirs = syn.directions(64, 48, K).to(DEV).contiguous()
+    poses = syn.hemisphere_poses(7).to(DEV).contiguous()
+    g = torch.Generator().manual_seed(5)
+    n = 3001
+    ii = torch.randint(7, (n,), generator=g).to(DEV); pi = torch.randint(64 * 48, (n,), generator=g).to(DEV)
+    ro, rd = torch.empty(n, 3, device=DEV), torch.empty(n, 3, device=DEV)
+    L.call("b2n_rays_from_indices", L.ptr(dirs), L.ptr(poses), L.ptr(ii), L.ptr(pi), n, L.ptr(ro), L.ptr(rd))
+    ro_ref, rd_ref = syn.get_rays(dirs[pi].cpu().double(), poses[ii].cpu().double())
+    assert torch.equal(ro.cpu(), poses[ii][:, :, 3].cpu())
+    torch.testing.assert_close(rd.cpu().double(), rd_ref, rtol=0, atol=2e-7)
+
+
 # ------------------------------------------------------------------------------------------------ encodings
 def _layout_pair(mods, scale=0.5, log2_T=19, L=16):
     b = np.exp(np.log(2048 * scale / 16) / (L - 1))
