@@ -83,38 +83,57 @@ def run_reference(args, rank):
 
 # ---------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
-        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled from a thread every ~2 ms (the
+    timed region is tens of milliseconds, too short for an `nvidia-smi -lms` child to start), nvidia-smi as fallback."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.bits, self.max_mhz, self.err = index, [], 0, None, None
+        self._stop = threading.Event()
+        self.thread = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            try:
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons",
+                                  getattr(pynvml, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                        if get_reasons is not None:
+                            self.bits |= int(get_reasons(h))
+                    except Exception as e:                   # keep sampling; report the last error
+                        self.err = repr(e)
+                    time.sleep(0.002)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+        except Exception as e:
+            self.err = repr(e)
 
     def stop(self):
-        if self.proc is None:
-            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        if not self.sm:                                      # NVML unavailable: one nvidia-smi query after the fact
+            try:
+                out = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=20).stdout
+                a, b = [float(v) for v in out.strip().split(",")[:2]]
+                return dict(sm_mhz=a, sm_max_mhz=b, reasons=[], samples=0, note="NVML unavailable (%s); sampled after the "
+                            "timed region" % self.err)
+            except Exception:
+                return dict(sm_mhz=None, sm_max_mhz=None, reasons=["clock sampling unavailable: %s" % self.err], samples=0)
+        reasons = [name for bit, name in self.REASONS if self.bits & bit]
+        return dict(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.max_mhz, reasons=reasons, samples=len(self.sm))
 
 
 # ---------------------------------------------------------------------------------------------- kernel table
@@ -165,8 +184,6 @@ def profile_kernels(tr, reps=5):
         key = name
         if name == "b2n_mlp_fw" or name == "b2n_mlp_bw":
             key = f"{name}[{'rgb' if a[4 if name == 'b2n_mlp_fw' else 5] == 2 else 'sigma'}]"
-        if name == "b2n_adam_step":
-            key = f"{name}[{'xyz' if a[5] > 100000 else 'rgb'}]"
         d = out.setdefault(key, [0.0, 0])
         d[0] += e0.elapsed_time(e1); d[1] += 1
     return {k: v[0] / v[1] for k, v in out.items()}, len(rec) // reps
@@ -294,7 +311,7 @@ def main():
         base = top.split("[")[0]
         bound = costs.get(base, ("hbm", None))[0]
         if base == "b2n_adam_step":
-            alg = 34.0 * (tr.p_xyz.numel() if "xyz" in top else tr.p_rgb.numel())
+            alg = 34.0 * tr.shard                            # fp32 p,g,m,v read + p,g(zero),m,v written + fp16 copy
         elif base == "b2n_mlp_fw":
             alg = samples * (2 * (32 * 64 + 64 * 16) if "sigma" in top else 2 * (32 * 64 + 64 * 64 + 64 * 16))
         elif base == "b2n_mlp_bw":

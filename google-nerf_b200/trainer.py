@@ -47,7 +47,7 @@ class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
-                 march_ctas_per_sm=None):
+                 march_ctas_per_sm=None, comm_in_graph=False):
         if model.encoding != "HashGrid":
             raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
                              "render() + autograd")
@@ -78,27 +78,34 @@ class NGPTrainer:
         self.n_mlp = xe.mlp.n_params
         z = lambda t: torch.zeros_like(t)
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
-        n_xyz = xe.params.numel()
-        # Sharded optimiser (world > 1): the big flat parameter (MLP + hash table) is padded to world * shard; every
-        # rank reduce-scatters the gradient, runs Adam on ITS shard of the fp32 master / moments only, and the fp16
-        # working copy is all-gathered.  Less traffic than an all-reduce (fp32 RS + fp16 AG) and Adam's HBM sweep
-        # shrinks by the world size.  The model's Parameter is a view of the padded master buffer.
-        self.n_pad = -(-n_xyz // (8 * self.world)) * (8 * self.world)
+        n_xyz, n_rgb = xe.params.numel(), rn.params.numel()
+        # All trainable parameters live in ONE flat vector [xyz_encoder (MLP + hash table) | rgb_net | pad]: one Adam
+        # launch, and for world > 1 one collective each way.  Sharded optimiser (world > 1): the vector is padded to
+        # world * shard; every rank reduce-scatters the gradient, runs Adam on ITS shard of the fp32 master / moments
+        # only, and the fp16 working copy is all-gathered.  Less traffic than an all-reduce (fp32 RS + fp16 AG) and
+        # Adam's HBM sweep shrinks by the world size.  The model's Parameters are views of the master buffer.
+        assert n_xyz % 8 == 0
+        n_all = n_xyz + n_rgb
+        self.n_pad = -(-n_all // (8 * self.world)) * (8 * self.world)
         self.shard = self.n_pad // self.world
         p_pad = torch.zeros(self.n_pad, dtype=_f32, device=self.dev)
-        p_pad[:n_xyz].copy_(xe.params.data)
-        xe.params.data = p_pad[:n_xyz]
+        p_pad[:n_xyz].copy_(xe.params.data); p_pad[n_xyz:n_all].copy_(rn.params.data)
+        xe.params.data, rn.params.data = p_pad[:n_xyz], p_pad[n_xyz:n_all]
         self.p_pad = p_pad
         self.p_xyz, self.p_rgb = xe.params.data, rn.params.data
-        self.g_xyz, self.g_rgb = torch.zeros(self.n_pad, dtype=_f32, device=self.dev), z(self.p_rgb)
+        self.g_all = torch.zeros(self.n_pad, dtype=_f32, device=self.dev)
+        self.g_xyz, self.g_rgb = self.g_all[:n_xyz], self.g_all[n_xyz:n_all]
         lo = self.rank * self.shard
         self.p_shard = p_pad[lo:lo + self.shard]
-        self.g_shard = self.g_xyz if self.world == 1 else torch.zeros(self.shard, dtype=_f32, device=self.dev)
-        self.m_xyz, self.v_xyz = z(self.p_shard), z(self.p_shard)
-        self.m_rgb, self.v_rgb = z(self.p_rgb), z(self.p_rgb)
-        self.h_xyz = tc.cast_half(p_pad)
-        self.h_shard = self.h_xyz[lo:lo + self.shard]
-        self.h_rgb = tc.cast_half(self.p_rgb)
+        self.g_shard = self.g_all if self.world == 1 else torch.zeros(self.shard, dtype=_f32, device=self.dev)
+        self.m, self.v = z(self.p_shard), z(self.p_shard)
+        self.h_all = tc.cast_half(p_pad)
+        self.h_xyz, self.h_rgb = self.h_all[:n_xyz], self.h_all[n_xyz:n_all]
+        self.h_shard = self.h_all[lo:lo + self.shard]
+        # True captures the NCCL collectives into the training graph (world > 1).  Measured: 22 us/step faster at 2
+        # GPUs, but communicator teardown after captured collectives hung on this stack, so the default keeps them
+        # eager between two graphs.
+        self.comm_in_graph = comm_in_graph
         self.hyper = torch.zeros(2, dtype=torch.int32, device=self.dev)        # {float lr; int32 step}
         self.w_image = torch.empty(10240, dtype=_f16, device=self.dev)
         self._pack_weights()
@@ -172,27 +179,23 @@ class NGPTrainer:
              P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
 
     def _reduce_grads(self):
-        """world > 1: sum the gradients over ranks -- reduce-scatter for the big sharded parameter, all-reduce for the
-        29 KB colour-net one.  (NCCL; kept outside the captured graphs.)"""
-        dist.reduce_scatter_tensor(self.g_shard, self.g_xyz, op=dist.ReduceOp.SUM, group=self.pg)
-        dist.all_reduce(self.g_rgb, group=self.pg)
+        """world > 1: sum the gradients over ranks; every rank keeps its shard (NCCL reduce-scatter)."""
+        dist.reduce_scatter_tensor(self.g_shard, self.g_all, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _optimizer(self):
         P, call = L.ptr, L.call
         inv = 1.0 / (self.loss_scale * self.world)
         b1, b2 = self.betas
-        for p, g, m, v, h in ((self.p_shard, self.g_shard, self.m_xyz, self.v_xyz, self.h_shard),
-                              (self.p_rgb, self.g_rgb, self.m_rgb, self.v_rgb, self.h_rgb)):
-            call("b2n_adam_step", P(p), P(g), P(m), P(v), P(h), p.numel(), self.lr, b1, b2, self.eps, inv, 1,
-                 P(self.hyper))
+        call("b2n_adam_step", P(self.p_shard), P(self.g_shard), P(self.m), P(self.v), P(self.h_shard), self.shard,
+             self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
         if self.world == 1:
             self._pack_weights()
         else:
-            self.g_xyz.zero_()                               # Adam only zeroed this rank's reduced shard
+            self.g_all.zero_()                               # Adam only zeroed this rank's reduced shard
 
     def _gather_params(self):
         """world > 1: every rank receives the other shards of the fp16 working copy, then re-packs the MLP image."""
-        dist.all_gather_into_tensor(self.h_xyz, self.h_shard, group=self.pg)
+        dist.all_gather_into_tensor(self.h_all, self.h_shard, group=self.pg)
         self._pack_weights()
 
     def _pack_weights(self):
@@ -200,10 +203,15 @@ class NGPTrainer:
         L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image))
 
     def _train(self, p):
-        """Forward, backward and (single rank) the optimiser on sample set p."""
+        """Forward, backward and the optimiser on sample set p (world > 1: with the gradient reduce-scatter and the
+        parameter all-gather around the optimiser, unless the collectives are kept out of the graph)."""
         self._forward_backward(self.sets[p])
         if self.world == 1:
             self._optimizer()
+        elif self.comm_in_graph:
+            self._reduce_grads()
+            self._optimizer()
+            self._gather_params()
 
     # ------------------------------------------------------------------ graphs
     def _run(self, key, fn):
@@ -220,8 +228,7 @@ class NGPTrainer:
     def _capture(self, fn, touches_params, touches_grid=False):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
-        state_t = (self.p_pad, self.p_rgb, self.m_xyz, self.v_xyz, self.m_rgb, self.v_rgb, self.h_xyz, self.h_rgb,
-                   self.g_xyz, self.g_rgb, self.g_shard)
+        state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all, self.g_shard)
         if touches_grid:
             state_t, touches_params = (self.model.density_grid, self.model.density_bitfield), True
         saved = [t.clone() for t in state_t] if touches_params else None
@@ -304,7 +311,7 @@ class NGPTrainer:
             with torch.cuda.stream(self.side):
                 self._load(self.sets[1 - p], next_batch)
                 self._run(("march", 1 - p), lambda: self._march(self.sets[1 - p]))
-        if self.world > 1:                                   # NCCL collectives stay outside the captured graphs
+        if self.world > 1 and not self.comm_in_graph:        # collectives between two graphs
             self._reduce_grads()
             self._run(("opt",), self._optimizer)
             self._gather_params()

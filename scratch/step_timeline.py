@@ -41,6 +41,12 @@ def one(nb=True):
 for _ in range(n_pre):
     one()
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(64):
+    one()
+e1.record(); torch.cuda.synchronize()
+print("unprofiled: %.1f us/step, samples %d, alive %d" % (e0.elapsed_time(e1) / 64 * 1e3, tr.samples_last_step(), int(tr.alive_cnt.item())))
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(20):
         one()

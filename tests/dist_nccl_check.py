@@ -34,7 +34,7 @@ def main():
         m = NGP(0.5, log2_T=15).to(dev)
         m.density_bitfield.copy_(s["bitfield"])
         tr = NGPTrainer(m, n_rays=512, use_graph=True, samples_per_ray=200, grid_update_interval=8, warmup_steps=10 ** 9,
-                        seed=3, data_parallel=dp)
+                        seed=3, data_parallel=dp, comm_in_graph=os.environ.get("B2N_COMM_IN_GRAPH", "1") == "1")
         tr.fixed_noise = s["noise"].to(dev)
         losses = [float(tr.step(ro, rd, tgt).item()) for _ in range(24)]
         tr.sync_model()
