@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--pretrain", type=int, default=512,
                     help="untimed training steps before warm-up so that occupancy/density reach steady state")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--comm", default=None, choices=["p2p", "nccl"],
+                    help="N > 1: gradient/parameter exchange (default p2p = fused kernel over NVLink peer memory)")
     ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel event timing table to stderr")
@@ -211,7 +213,8 @@ def main():
     torch.manual_seed(1337)
     K = syn.intrinsics(W_IMG, H_IMG); dirs = syn.directions(W_IMG, H_IMG, K); poses = syn.hemisphere_poses(N_IMG)
     model = NGP(SCALE, encoding="HashGrid").to(dev)
-    tr = NGPTrainer(model, n_rays=N_RAYS, use_graph=not args.no_graph, seed=1234 + rank, samples_per_ray=128)
+    tr = NGPTrainer(model, n_rays=N_RAYS, use_graph=not args.no_graph, seed=1234 + rank, samples_per_ray=128,
+                    comm=args.comm)
     tr.set_dataset(dirs, poses)
     model.mark_invisible_cells(K.to(dev), poses.to(dev), (W_IMG, H_IMG))
 
@@ -255,14 +258,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---- pretrain (untimed) to steady-state occupancy; grow the sample capacity if it overflows
+    def overflowed():                     # collective: every rank re-captures its graphs together
+        f = torch.tensor([int(tr.overflowed())], device=dev)
+        if world > 1:
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+        return bool(f.item())
+
     for i in range(args.pretrain):
         dev_step()
-        if i % 32 == 31 and tr.overflowed():
+        if i % 32 == 31 and overflowed():
             tr.grow(1.5); primed[0] = False
     for _ in range(max(args.warmup, 3)):
         dev_step()
     barrier()
-    if tr.overflowed():
+    if overflowed():
         tr.grow(1.5); primed[0] = False
         for _ in range(3):
             dev_step()
@@ -287,6 +296,8 @@ def main():
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX); dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(ms.item()), float(ms_e2e.item())
+    if tr.peer is not None:
+        tr.peer.check()                   # a timed-out peer barrier would have invalidated the run
 
     # ---- every rank: gather the model (sharded optimiser) and time the occupancy-grid update (it max-reduces)
     tr.sync_model()
@@ -379,7 +390,7 @@ def main():
                     config=dict(workload=WORKLOAD, rays_per_gpu=N_RAYS, samples_per_step=samples,
                                 samples_per_ray=samples / N_RAYS, cuda_graph=not args.no_graph,
                                 l2="per-step working set (206 MB optimiser state + sample buffers) exceeds the 126 MB "
-                                   "L2; no explicit flush", parallelism=f"dp{world}"),
+                                   "L2; no explicit flush", parallelism=f"dp{world}", comm=tr.comm),
                     clocks=clk,
                     e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),

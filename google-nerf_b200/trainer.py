@@ -47,7 +47,7 @@ class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
-                 march_ctas_per_sm=None, comm_in_graph=False):
+                 march_ctas_per_sm=None, comm=None, comm_in_graph=False):
         if model.encoding != "HashGrid":
             raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
                              "render() + autograd")
@@ -93,13 +93,28 @@ class NGPTrainer:
         xe.params.data, rn.params.data = p_pad[:n_xyz], p_pad[n_xyz:n_all]
         self.p_pad = p_pad
         self.p_xyz, self.p_rgb = xe.params.data, rn.params.data
-        self.g_all = torch.zeros(self.n_pad, dtype=_f32, device=self.dev)
-        self.g_xyz, self.g_rgb = self.g_all[:n_xyz], self.g_all[n_xyz:n_all]
         lo = self.rank * self.shard
+        self.comm = (comm or "p2p") if self.world > 1 else "none"
+        if self.comm not in ("none", "p2p", "nccl"):
+            raise ValueError(f"unknown comm {comm!r}")
+        self.peer = None
+        if self.comm == "p2p":
+            # gradient vector and fp16 working copy live in NVLink peer memory: the fused reduce + Adam + broadcast
+            # kernel of every rank addresses all of them (peer.py / csrc/peer.cu)
+            from .peer import PeerBlock
+            self.peer = PeerBlock({"g": (_f32, self.n_pad), "h": (_f16, self.n_pad)}, self.dev, process_group)
+            self.g_all, self.h_all = self.peer.tensor("g"), self.peer.tensor("h")
+            self.h_all.copy_(tc.cast_half(p_pad))
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=process_group)
+        else:
+            self.g_all = torch.zeros(self.n_pad, dtype=_f32, device=self.dev)
+            self.h_all = tc.cast_half(p_pad)
+        self.g_xyz, self.g_rgb = self.g_all[:n_xyz], self.g_all[n_xyz:n_all]
         self.p_shard = p_pad[lo:lo + self.shard]
-        self.g_shard = self.g_all if self.world == 1 else torch.zeros(self.shard, dtype=_f32, device=self.dev)
+        self.g_shard = torch.zeros(self.shard, dtype=_f32, device=self.dev) if self.comm == "nccl" else \
+            self.g_all[lo:lo + self.shard]
         self.m, self.v = z(self.p_shard), z(self.p_shard)
-        self.h_all = tc.cast_half(p_pad)
         self.h_xyz, self.h_rgb = self.h_all[:n_xyz], self.h_all[n_xyz:n_all]
         self.h_shard = self.h_all[lo:lo + self.shard]
         # True captures the NCCL collectives into the training graph (world > 1).  Measured: 22 us/step faster at 2
@@ -179,10 +194,11 @@ class NGPTrainer:
              P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
 
     def _reduce_grads(self):
-        """world > 1: sum the gradients over ranks; every rank keeps its shard (NCCL reduce-scatter)."""
+        """comm == "nccl": sum the gradients over ranks; every rank keeps its shard (reduce-scatter)."""
         dist.reduce_scatter_tensor(self.g_shard, self.g_all, op=dist.ReduceOp.SUM, group=self.pg)
 
     def _optimizer(self):
+        """Adam on this rank's shard from the (already reduced, or local) gradient shard."""
         P, call = L.ptr, L.call
         inv = 1.0 / (self.loss_scale * self.world)
         b1, b2 = self.betas
@@ -191,11 +207,25 @@ class NGPTrainer:
         if self.world == 1:
             self._pack_weights()
         else:
-            self.g_all.zero_()                               # Adam only zeroed this rank's reduced shard
+            self.g_all.zero_()                               # Adam only zeroed this rank's (reduced) shard
 
     def _gather_params(self):
-        """world > 1: every rank receives the other shards of the fp16 working copy, then re-packs the MLP image."""
+        """comm == "nccl": every rank receives the other shards of the fp16 working copy, then re-packs the MLP image."""
         dist.all_gather_into_tensor(self.h_all, self.h_shard, group=self.pg)
+        self._pack_weights()
+
+    def _optimizer_peer(self):
+        """comm == "p2p": barrier, then ONE kernel that sums this rank's gradient slice over all ranks through NVLink
+        peer loads, runs Adam on the local master shard and stores the fp16 result into every rank's working copy;
+        barrier; clear the local gradient vector; re-pack the MLP image."""
+        P, call, pb = L.ptr, L.call, self.peer
+        inv = 1.0 / (self.loss_scale * self.world)
+        b1, b2 = self.betas
+        pb.barrier()
+        call("b2n_adam_step_peer", P(self.p_shard), P(self.m), P(self.v), pb.table("g"), pb.table("h"), self.world,
+             self.rank * self.shard, self.shard, self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
+        pb.barrier()
+        self.g_all.zero_()
         self._pack_weights()
 
     def _pack_weights(self):
@@ -208,6 +238,8 @@ class NGPTrainer:
         self._forward_backward(self.sets[p])
         if self.world == 1:
             self._optimizer()
+        elif self.comm == "p2p":
+            self._optimizer_peer()
         elif self.comm_in_graph:
             self._reduce_grads()
             self._optimizer()
@@ -228,7 +260,7 @@ class NGPTrainer:
     def _capture(self, fn, touches_params, touches_grid=False):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
-        state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all, self.g_shard)
+        state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all) + ((self.g_shard,) if self.comm == "nccl" else ())
         if touches_grid:
             state_t, touches_params = (self.model.density_grid, self.model.density_bitfield), True
         saved = [t.clone() for t in state_t] if touches_params else None
@@ -311,7 +343,7 @@ class NGPTrainer:
             with torch.cuda.stream(self.side):
                 self._load(self.sets[1 - p], next_batch)
                 self._run(("march", 1 - p), lambda: self._march(self.sets[1 - p]))
-        if self.world > 1 and not self.comm_in_graph:        # collectives between two graphs
+        if self.comm == "nccl" and not self.comm_in_graph:   # collectives between two graphs
             self._reduce_grads()
             self._run(("opt",), self._optimizer)
             self._gather_params()

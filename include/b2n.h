@@ -199,6 +199,33 @@ B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, con
                              b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx,
                              int64_t n_alloc, void *stream);
 
+/* ---------------------------------------------------------------- multi-GPU: NVLink peer memory ------ */
+/* Data-parallel training (ngp_pl/train.py:197-208: DDPPlugin -> one NCCL gradient all-reduce per step, every rank
+ * runs the whole optimiser) re-designed for one NVSwitch node: gradient reduce-scatter + Adam + parameter
+ * all-gather as ONE kernel over peer memory, bracketed by flag barriers (csrc/peer.cu).  One process per GPU.
+ *
+ * b2n_peer_alloc: cudaMalloc `bytes` (zero-filled) on the current device and return its CUDA-IPC handle (64 bytes)
+ * for the other ranks; b2n_peer_open maps another rank's handle (peer access enabled lazily); _close / _free undo. */
+B2N_API int b2n_peer_alloc(int64_t bytes, void **ptr, void *handle64);
+B2N_API int b2n_peer_open(const void *handle64, void **ptr);
+B2N_API int b2n_peer_close(void *ptr);
+B2N_API int b2n_peer_free(void *ptr);
+/* Barrier across the `world` ranks.  flag_ptrs: HOST array of `world` device pointers, entry r = rank r's flag
+ * block (>= 16 u32, zero-initialised, peer-mapped).  state: 2 local u32 {completed epoch, sticky error (1 + the
+ * rank that timed out)}.  Everything the ranks wrote before the barrier (also into peer memory) is visible to
+ * kernels launched after it.  A peer that does not arrive within timeout_s sets the error word; no hang. */
+B2N_API int b2n_peer_barrier(void *const *flag_ptrs, int rank, int world, uint32_t *state, double timeout_s,
+                             void *stream);
+/* The fused step for this rank's shard [shard_first, shard_first + shard_n) of the flat parameter vector:
+ * grad = sum_r grad_ptrs[r][i] (rank order), FusedAdam update (see b2n_adam_step) of param_shard / exp_avg /
+ * exp_avg_sq (local, shard_n elements), fp16 result stored to half_ptrs[r][i] for every r.  grad_ptrs / half_ptrs:
+ * HOST arrays of `world` device pointers to each rank's full fp32 gradient / fp16 parameter vector.  Gradients are
+ * left untouched (their holder clears them after the closing barrier). */
+B2N_API int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_avg_sq, void *const *grad_ptrs,
+                               void *const *half_ptrs, int world, int64_t shard_first, int64_t shard_n, float lr,
+                               float beta1, float beta2, float eps, float inv_scale, int step,
+                               const void *hyper_dev, void *stream);
+
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
  * over one flat fp32 parameter; grad is multiplied by inv_scale, then ZEROED; half_copy (may be NULL)

@@ -2,6 +2,7 @@
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/dist_nccl_check.py
 
+B2N_COMM=p2p (default: fused reduce + Adam + broadcast over NVLink peer memory) or nccl.
 Checks that data-parallel training with the sharded optimiser (reduce-scatter -> Adam on a shard -> fp16 all-gather)
 follows the single-GPU trajectory when every rank is fed the SAME batch and jitter (averaged gradients == local
 gradients), that the gathered fp32 master parameters agree across ranks, and that the density grid max-reduce leaves
@@ -34,10 +35,13 @@ def main():
         m = NGP(0.5, log2_T=15).to(dev)
         m.density_bitfield.copy_(s["bitfield"])
         tr = NGPTrainer(m, n_rays=512, use_graph=True, samples_per_ray=200, grid_update_interval=8, warmup_steps=10 ** 9,
-                        seed=3, data_parallel=dp, comm_in_graph=os.environ.get("B2N_COMM_IN_GRAPH", "1") == "1")
+                        seed=3, data_parallel=dp, comm=os.environ.get("B2N_COMM", "p2p"),
+                        comm_in_graph=os.environ.get("B2N_COMM_IN_GRAPH", "0") == "1")
         tr.fixed_noise = s["noise"].to(dev)
         losses = [float(tr.step(ro, rd, tgt).item()) for _ in range(24)]
         tr.sync_model()
+        if tr.peer is not None:
+            tr.peer.check()
         out[dp] = (losses, m.xyz_encoder.params.detach().clone(), m.rgb_net.params.detach().clone(),
                    m.density_bitfield.clone())
     l1, p1, r1, b1 = out[False]; l2, p2, r2, b2 = out[True]
@@ -55,7 +59,7 @@ def main():
         ref = t.clone(); dist.broadcast(ref, src=0)
         assert torch.equal(ref, t), "ranks disagree"
     if rank == 0:
-        print("dist_nccl_check ok: world", dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1])
+        print("dist_nccl_check ok (comm %s): world" % os.environ.get("B2N_COMM", "p2p"), dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1])
     dist.barrier(); dist.destroy_process_group()
 
 
