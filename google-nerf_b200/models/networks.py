@@ -185,12 +185,36 @@ class NGP(nn.Module):
                 self.density_grid[c, indices[i:i + chunk]] = torch.where(valid, 0., -1.)
 
     @torch.no_grad()
-    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False):
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False, shard=None, reduce_tmp=None):
         """EMA-max update of the cascaded density grid from fresh field samples, then re-pack the bitfield
-        (networks.py:216-252).  The mean/threshold stays on the device (no .item() sync)."""
+        (networks.py:216-252).  The mean/threshold stays on the device (no .item() sync).
+
+        Data parallel (SURVEY 8e "occupancy update"): shard=(rank, world) makes this rank evaluate 1/world of the
+        cells and reduce_tmp(tmp) must max-reduce the sampled densities over the ranks before they are merged, so
+        that all ranks keep identical grids while the field evaluations are shared out."""
+        self._grid_eval(warmup, shard)
+        if reduce_tmp is not None:
+            reduce_tmp(self._grid_tmp)
+        self._grid_commit(density_threshold, decay, erode)
+
+    @torch.no_grad()
+    def _grid_eval(self, warmup, shard=None):
+        """Densities at jittered positions inside the selected cells -> self._grid_tmp (0 where not sampled)."""
         G = self.grid_size
-        tmp = torch.zeros_like(self.density_grid)
-        cells = self.get_all_cells() if warmup else self.sample_uniform_and_occupied_cells(G ** 3 // 4)
+        rank, world = shard if shard is not None else (0, 1)
+        if getattr(self, "_grid_tmp", None) is None or self._grid_tmp.shape != self.density_grid.shape \
+                or self._grid_tmp.device != self.density_grid.device:
+            self._grid_tmp = torch.zeros_like(self.density_grid)
+        tmp = self._grid_tmp
+        tmp.zero_()
+        if warmup:
+            cells = self.get_all_cells()
+            if world > 1:                                    # a contiguous slice of all cells per rank
+                n = G ** 3
+                lo_i, hi_i = rank * n // world, (rank + 1) * n // world
+                cells = [(i[lo_i:hi_i], c[lo_i:hi_i]) for i, c in cells]
+        else:
+            cells = self.sample_uniform_and_occupied_cells(-(-(G ** 3 // 4) // world))
         lo, hi = -float(self.scale), float(self.scale)
         for c in range(self.cascades):
             indices, coords = cells[c]
@@ -204,6 +228,11 @@ class NGP(nn.Module):
             else:
                 sigmas = torch.exp(self.xyz_encoder(xyz01)[:, 0].float())
             L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]))
+
+    @torch.no_grad()
+    def _grid_commit(self, density_threshold, decay=0.95, erode=False):
+        """grid = max(decay * grid, tmp) where grid >= 0, optional erosion, threshold, bitfield."""
+        G, tmp = self.grid_size, self._grid_tmp
         if not self.density_grid.is_contiguous():
             self.density_grid = self.density_grid.contiguous()
         L.call("b2n_grid_ema", L.ptr(self.density_grid), L.ptr(tmp), self.density_grid.numel(), float(decay))

@@ -253,7 +253,7 @@ class NGPTrainer:
             return
         g = self.graphs.get(key)
         if g is None:
-            g = self._capture(fn, touches_params=key[0] in ("train", "opt"), touches_grid=key[0] == "grid")
+            g = self._capture(fn, touches_params=key[0] in ("train", "opt"), touches_grid=key[0].startswith("grid"))
             self.graphs[key] = g
         g.replay()
 
@@ -262,7 +262,9 @@ class NGPTrainer:
         # count as a training step; then capture
         state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all) + ((self.g_shard,) if self.comm == "nccl" else ())
         if touches_grid:
-            state_t, touches_params = (self.model.density_grid, self.model.density_bitfield), True
+            if getattr(self.model, "_grid_tmp", None) is None:        # the persistent scratch grid of the update
+                self.model._grid_tmp = torch.zeros_like(self.model.density_grid)
+            state_t, touches_params = (self.model.density_grid, self.model.density_bitfield, self.model._grid_tmp), True
         saved = [t.clone() for t in state_t] if touches_params else None
         warm = torch.cuda.Stream(device=self.dev)
         warm.wait_stream(torch.cuda.current_stream())
@@ -368,20 +370,19 @@ class NGPTrainer:
 
     @torch.no_grad()
     def update_density_grid(self, warmup=False):
-        """train.py:145-148: threshold 0.01*MAX_SAMPLES/sqrt(3); all ranks end with the same grid.  The update has no
-        host synchronisation, so it is replayed as a CUDA graph as well (it is ~25 small launches)."""
+        """train.py:145-148: threshold 0.01*MAX_SAMPLES/sqrt(3).  The update has no host synchronisation, so it is
+        replayed as CUDA graphs as well (it is ~25 small launches).  world > 1: the sampled cells are shared out over
+        the ranks (each evaluates 1/world of them), the sampled densities are max-reduced and every rank merges the
+        same values, so all ranks keep the same grid and march the same bitfield."""
+        thr = 0.01 * MAX_SAMPLES / 3 ** 0.5
+        m, w = self.model, bool(warmup)
         self.sync_model_half()
-        self._run(("grid", bool(warmup)), lambda: self._update_density_grid_body(warmup))
-        if self.world > 1:
-            m = self.model
-            dist.all_reduce(m.density_grid, op=dist.ReduceOp.MAX, group=self.pg)
-            ws = torch.empty(3, dtype=torch.float64, device=self.dev); stats = torch.empty(3, device=self.dev)
-            L.call("b2n_grid_threshold", L.ptr(m.density_grid), m.density_grid.numel(),
-                   float(0.01 * MAX_SAMPLES / 3 ** 0.5), L.ptr(ws), L.ptr(stats))
-            vren.packbits(m.density_grid, 0.0, m.density_bitfield, threshold_dev=stats)
-
-    def _update_density_grid_body(self, warmup):
-        self.model.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=warmup, erode=False)
+        if self.world == 1:
+            self._run(("grid", w), lambda: m.update_density_grid(thr, warmup=w, erode=False))
+            return
+        self._run(("grid_eval", w), lambda: m._grid_eval(w, (self.rank, self.world)))
+        dist.all_reduce(m._grid_tmp, op=dist.ReduceOp.MAX, group=self.pg)
+        self._run(("grid_commit",), lambda: m._grid_commit(thr, 0.95, False))
 
     def sync_model_half(self):
         """Hand the fp16 working copies (always current) to the nn.Module view; no communication."""

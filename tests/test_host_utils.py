@@ -1,0 +1,62 @@
+"""losses / metrics / checkpoint helpers (CPU): behaviour of ngp_pl/losses.py, metrics.py, utils.py."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_ssi_depth_loss_is_shift_scale_invariant():
+    from google_nerf_b200.losses import shiftscale_inv_depthloss
+    g = torch.Generator().manual_seed(0)
+    d = torch.rand(1001, generator=g) + 0.1
+    # an affine map of the prediction (positive scale) leaves the loss at zero
+    assert shiftscale_inv_depthloss(3.0 * d + 0.7, d).abs().max() < 1e-9 + 1e-5
+    a = shiftscale_inv_depthloss(d, d.flip(0))
+    b = shiftscale_inv_depthloss(5.0 * d - 2.0, 0.5 * d.flip(0) + 4.0)
+    torch.testing.assert_close(a, b, rtol=1e-4, atol=1e-5)
+    # explicit formula (losses.py:15-23) on a tiny case: median of an odd-length vector is its middle element
+    p, q = torch.tensor([1.0, 2.0, 6.0]), torch.tensor([0.0, 1.0, 2.0])
+    pn = (p - 2.0) / ((p - 2.0).abs().mean()); qn = (q - 1.0) / ((q - 1.0).abs().mean())
+    torch.testing.assert_close(shiftscale_inv_depthloss(p, q), (pn - qn) ** 2)
+
+
+def test_nerf_loss_matches_oracle_and_fused_terms():
+    from google_nerf_b200.losses import NeRFLoss
+    from oracle import ngp_ref
+    g = torch.Generator().manual_seed(1)
+    res = {"rgb": torch.rand(64, 3, generator=g), "opacity": torch.rand(64, generator=g)}
+    tgt = {"rgb": torch.rand(64, 3, generator=g)}
+    d = NeRFLoss()(res, tgt)
+    assert set(d) == {"rgb", "opacity"} and d["rgb"].shape == (64, 3) and d["opacity"].shape == (64,)
+    total = sum(v.mean() for v in d.values())                 # train.py:160
+    torch.testing.assert_close(total, ngp_ref.nerf_loss(res, tgt["rgb"]))
+
+
+def test_psnr():
+    from google_nerf_b200.metrics import mse, psnr
+    a, b = torch.zeros(4, 3), torch.full((4, 3), 0.1)
+    assert abs(float(mse(a, b)) - 0.01) < 1e-8 and abs(float(psnr(a, b)) - 20.0) < 1e-4
+    m = torch.tensor([True, False, True, False])
+    assert mse(a, b, m, reduction="none").shape == (2, 3)
+
+
+def test_checkpoint_helpers(tmp_path):
+    from google_nerf_b200.utils import extract_model_state_dict, load_ckpt, slim_ckpt
+    lin = torch.nn.Linear(3, 2)
+    sd = {"model." + k: v.clone() + 1 for k, v in lin.state_dict().items()}
+    sd.update({"directions": torch.zeros(4, 3), "poses": torch.zeros(2, 3, 4), "model.density_grid": torch.zeros(8),
+               "model.grid_coords": torch.zeros(8, 3), "val_lpips.net.w": torch.zeros(1), "model.skip.me": torch.ones(1)})
+    path = os.path.join(tmp_path, "c.ckpt")
+    torch.save({"state_dict": sd, "epoch": 3}, path)
+    got = extract_model_state_dict(path, prefixes_to_ignore=["skip", "density_grid", "grid_coords"])
+    assert set(got) == {"weight", "bias"}
+    before = lin.weight.detach().clone()
+    load_ckpt(lin, path, prefixes_to_ignore=["skip", "density_grid", "grid_coords"])
+    torch.testing.assert_close(lin.weight.detach(), before + 1)
+    slim = slim_ckpt(path)
+    assert set(slim) == {"model.weight", "model.bias", "model.skip.me"}
+    assert "poses" in slim_ckpt(path, save_poses=True)
+    load_ckpt(lin, "")                                        # empty path is a no-op
