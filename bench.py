@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--comm", default=None, choices=["p2p", "nccl"],
                     help="N > 1: gradient/parameter exchange (default p2p = fused kernel over NVLink peer memory)")
-    ap.add_argument("--cpu-rays", type=int, default=1024, help="rays per step of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel event timing table to stderr")
     return ap.parse_args()
@@ -72,8 +72,11 @@ def cpu_baseline(n_rays, steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
-    cb, sec = cpu_baseline(args.cpu_rays, steps, warmup)
+    # exactly K timed steps after W warm-up steps; each step is a bounded sample of the workload (a CPU step over 1024
+    # rays takes ~0.6 s on 16 cores), shrunk further when K + W is large so that the arm ends within a few minutes
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    n_rays = 1024 if steps + warmup <= 300 else max(128, int(1024 * 300 / (steps + warmup)) // 128 * 128)
+    cb, sec = cpu_baseline(n_rays, steps, warmup)
     line = dict(impl="reference", metric="train_rays_per_s", value=cb["value"], unit="rays/s", n_gpus=args.gpus,
                 steps=steps, warmup=warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f16", data="synthetic", config=dict(workload=WORKLOAD),
@@ -305,6 +308,26 @@ def main():
     for _ in range(3):
         tr.update_density_grid(warmup=False)
     torch.cuda.synchronize(); grid_update_ms = (time.perf_counter() - t0) / 3 * 1e3
+    # ---- every rank: test-time render of full 800x800 frames (BASELINE.json configs[2]), sharded over the ranks in
+    # round-robin row tiles (dist_utils.render_sharded); the time is the max over ranks and includes the all-gather
+    from google_nerf_b200.models.rendering import render
+    from google_nerf_b200.dist_utils import render_sharded
+    frames, render_samples = [], 0
+    with torch.no_grad():
+        for f in range(4):
+            ro, rd = syn.get_rays(dd, pp[f % N_IMG])
+            barrier(); t0 = time.perf_counter()
+            res = render_sharded(lambda o, d, **kw: render(model, o, d, **kw), ro, rd, tile=W_IMG, test_time=True,
+                                 T_threshold=1e-2)
+            torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            frames.append(float(dt.item())); render_samples = int(res["total_samples"])
+    render_info = dict(mrays_per_s=W_IMG * H_IMG / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
+                       rays=W_IMG * H_IMG, samples_per_ray=render_samples / (W_IMG * H_IMG), n_gpus=world,
+                       note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 as in "
+                            "test.ipynb; N > 1: row tiles dealt round-robin to the ranks, max over ranks, all-gather of "
+                            "rgb/depth/opacity included")
     if rank == 0:
         # ---- per-kernel table + roofline of the dominant kernel (eager replays of the same step)
         tr.use_graph = False
@@ -362,25 +385,38 @@ def main():
         t_m = (table.get("b2n_raymarching_train_count", 0) + table.get("b2n_raymarching_train_write", 0)) * 1e-3
         marcher = dict(samples_per_s=samples / t_m if t_m else None, rays_per_s=N_RAYS / t_m if t_m else None,
                        gbs=(120 * N_RAYS + 32 * samples) / t_m / 1e9 if t_m else None)
-        # ---- test-time render of full 800x800 frames (BASELINE.json configs[2]); tile-sharded when world > 1 happens
-        # in the N-GPU run via dist_utils.render_sharded (here: rank 0's local share of the frame)
-        from google_nerf_b200.models.rendering import render
-        from google_nerf_b200.dist_utils import shard_bounds
-        lo, hi = shard_bounds(W_IMG * H_IMG, world, rank)
-        frames = []
-        with torch.no_grad():
-            for f in range(3):
-                ro, rd = syn.get_rays(dd[lo:hi], pp[f % N_IMG])
-                torch.cuda.synchronize(); t0 = time.perf_counter()
-                res = render(model, ro, rd, test_time=True, T_threshold=1e-2)
-                torch.cuda.synchronize(); frames.append(time.perf_counter() - t0)
-        render_info = dict(mrays_per_s=(hi - lo) * world / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
-                           rays=W_IMG * H_IMG, samples_per_ray=float(res["total_samples"]) / (hi - lo),
-                           note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 "
-                                "as in test.ipynb; per-rank share of the frame, no gather in this number")
+        # ---- SURVEY 8d extras: hash encode against HBM at the C5 table size (T = 2^22, 185 MiB fp16: not L2-resident),
+        # compositing bandwidth, field-MLP tensor throughput
+        from google_nerf_b200 import tinycudann as tcnn_b
+        lay5 = tcnn_b.hashgrid_layout(16, 2, 22, 16, float(np.exp(np.log(2048 * 16 / 16) / 15)))
+        tab5 = (torch.rand(lay5.n_params, device=dev) * 2e-4 - 1e-4).half()
+        n5 = 1 << 20
+        x5 = torch.rand(n5, 3, device=dev); enc5 = torch.empty(n5, 32, dtype=torch.float16, device=dev)
+        t5 = []
+        for _ in range(4):
+            a5, b5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a5.record(); LL.call("b2n_hashgrid_fw", LL.ptr(x5), LL.ptr(tab5), lay5, n5, None, LL.ptr(enc5), 32); b5.record()
+            torch.cuda.synchronize(); t5.append(a5.elapsed_time(b5) * 1e-3)
+        # uniformly random points: every fine-level gather pulls a distinct 32-byte sector from HBM
+        hash_encode["c5_T22_random_points"] = dict(
+            fw_gbs=588 * n5 / min(t5[1:]) / 1e9, table_mib=lay5.n_params * 2 / 2 ** 20, points=n5,
+            sector_gbs=(12 + 64 + 16 * 8 * 32) * n5 / min(t5[1:]) / 1e9, frac_of_hbm_sectors=((12 + 64 + 16 * 8 * 32) * n5 /
+                                                                                     min(t5[1:]) / 1e9) / hbm_peak,
+            note="T=2^22 (SURVEY C5): algorithmic 588 B/point; sector_gbs counts one 32-B sector per 4-B gather (upper "
+                 "bound of the DRAM traffic, coarse levels hit in cache)")
+        del tab5, x5, enc5
+        t_c = table.get("b2n_composite_loss_fwbw", 0) * 1e-3
+        compositing = dict(gbs=(40 * samples + 76 * N_RAYS) / t_c / 1e9 if t_c else None,
+                           note="fused fw + loss + bw launch; algorithmic 40 B/sample + 76 B/ray; latency-bound at 8192 rays")
+        t_f, t_b = table.get("b2n_field_mlp_fw", 0) * 1e-3, table.get("b2n_field_mlp_bw", 0) * 1e-3
+        mlp = dict(fw_tflops=20480 * samples / t_f / 1e12 if t_f else None,
+                   bw_tflops=40960 * samples / t_b / 1e12 if t_b else None, tensor_peak_tflops=tf_peak,
+                   fw_frac_of_tensor_peak=20480 * samples / t_f / 1e12 / tf_peak if t_f else None,
+                   note="tcgen05 kind::f16; the MLPs are 64 wide: activation traffic and dependency latency bound them, "
+                        "not the tensor pipe (ncu sm__pipe_tensor_cycles_active in profiles/)")
         cb = None
         if not args.skip_cpu:
-            cb, _ = cpu_baseline(args.cpu_rays, 2, 1)
+            cb, _ = cpu_baseline(args.cpu_rays, 4, 1)          # ~10 s of CPU work on 16 host cores
         rays = N_RAYS * world * args.steps
         n_updates = sum(1 for s in range(args.steps) if s % tr.S == 0)
         line = dict(metric="train_rays_per_s", value=rays / (ms * 1e-3), unit="rays/s", n_gpus=world, steps=args.steps,
@@ -395,7 +431,7 @@ def main():
                     e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
                     gpu_launches=launches_per_step * args.steps + 12 * n_updates,
-                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, render=render_info, grid_update_ms=grid_update_ms,
+                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, compositing=compositing, mlp=mlp, render=render_info, grid_update_ms=grid_update_ms,
                     kernels_us={k: round(v * 1e3, 1) for k, v in table.items()})
         print(json.dumps(line), flush=True)
     if world > 1:

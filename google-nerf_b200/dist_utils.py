@@ -51,25 +51,42 @@ def broadcast_model_(model, src=0, group=None):
     return model
 
 
-def render_sharded(render_fn, rays_o, rays_d, group=None, **kwargs):
-    """Tile-sharded test-time render: rank r renders rays [start_r, end_r) and the (rgb, depth, opacity) bands
-    are all-gathered.  `render_fn(rays_o, rays_d, **kwargs)` -> dict with those three keys (+ total_samples)."""
+def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
+    """Tile-sharded test-time render; the (rgb, depth, opacity) parts are all-gathered and put back in ray order.
+    `render_fn(rays_o, rays_d, **kwargs)` -> dict with those three keys (+ total_samples).
+
+    tile=None: rank r renders the contiguous band [start_r, end_r).  tile=T: rays are cut into tiles of T consecutive
+    rays dealt round-robin to the ranks (tile t -> rank t % world) -- empty-space rays are cheap, so contiguous bands of
+    an image are badly balanced; T = one image row keeps each rank's rays coherent."""
     rank, world = world_info(group)
     n = rays_o.shape[0]
-    s, e = shard_bounds(n, world, rank)
-    res = render_fn(rays_o[s:e], rays_d[s:e], **kwargs)
+    if tile is None:
+        owners = None
+        s, e = shard_bounds(n, world, rank)
+        sel = slice(s, e)
+        counts = [b - a for a, b in (shard_bounds(n, world, r) for r in range(world))]
+    else:
+        owners = (torch.arange(n, device=rays_o.device) // int(tile)) % world
+        sel = (owners == rank).nonzero(as_tuple=True)[0]
+        counts = [int(c) for c in torch.bincount(owners, minlength=world).tolist()]
+    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **kwargs)
     if world == 1:
         return res
     out = {}
-    sizes = [shard_bounds(n, world, r) for r in range(world)]
-    longest = max(b - a for a, b in sizes)
+    longest = max(counts)
     for k in ("rgb", "depth", "opacity"):
         v = res[k].contiguous()
-        if v.shape[0] < longest:                              # all_gather needs equal shapes: pad the short bands
+        if v.shape[0] < longest:                              # all_gather needs equal shapes: pad the short parts
             v = torch.cat([v, v.new_zeros((longest - v.shape[0],) + tuple(v.shape[1:]))], 0)
-        parts = [torch.empty_like(v) for _ in sizes]
+        parts = [torch.empty_like(v) for _ in counts]
         dist.all_gather(parts, v, group=group)
-        out[k] = torch.cat([p[:b - a] for p, (a, b) in zip(parts, sizes)], 0)
+        if owners is None:
+            out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
+        else:
+            full = v.new_empty((n,) + tuple(v.shape[1:]))
+            for r, (p, c) in enumerate(zip(parts, counts)):
+                full[owners == r] = p[:c]
+            out[k] = full
     ts = torch.as_tensor(res["total_samples"], device=out["rgb"].device, dtype=torch.int64).reshape(1).clone()
     dist.all_reduce(ts, group=group)
     out["total_samples"] = int(ts.item())

@@ -29,6 +29,13 @@ def _worker(rank, world, port, n):
     for k in ("rgb", "depth", "opacity"):
         assert torch.equal(out[k], full[k]), k
     assert out["total_samples"] == full["total_samples"]
+    # round-robin tiles (load-balanced partition): same pixels back in ray order, ragged last tile included
+    for tile in (1, 7, 64, 5000):
+        out = D.render_sharded(_fake_render, ro, rd, tile=tile)
+        for k in ("rgb", "depth", "opacity"):
+            # (sigmoid's vectorised and tail code paths differ in the last ulp, and the subsets change which is used)
+            torch.testing.assert_close(out[k], full[k], rtol=1e-6, atol=1e-7, msg=lambda m: f"{k} tile {tile}: {m}")
+        assert out["total_samples"] == full["total_samples"]
     # bands cover the rays exactly once
     bounds = [D.shard_bounds(n, world, r) for r in range(world)]
     assert bounds[0][0] == 0 and bounds[-1][1] == n and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
