@@ -357,11 +357,14 @@ def main():
             ach, peak, unit = alg / dur_s / 1e9, hbm_peak, "GB/s"
         else:
             ach, peak, unit = alg / dur_s / 1e12, tf_peak, "TFLOP/s"
-        ncu_traffic_per_sample = {"b2n_field_mlp_bw": 615.0, "b2n_field_mlp_fw": 451.0, "b2n_hashgrid_fw": 83.0,
-                                  "b2n_hashgrid_bw": 147.0}          # profiles/r01b_ncu_summary.md (dram read+write / samples)
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed capture
+        # profiles/r01d_ncu_summary.md (580k samples, 11.43 M parameters), scaled to this run's units
+        ncu_traffic_per_sample = {"b2n_field_mlp_bw": 629.0, "b2n_field_mlp_fw": 441.0, "b2n_hashgrid_fw": 55.0,
+                                  "b2n_hashgrid_bw": 156.0, "b2n_composite_loss_fwbw": 27.0}
         traffic = ncu_traffic_per_sample.get(base)
+        traffic = traffic * samples if traffic else (29.07 * tr.shard if base == "b2n_adam_step" else None)
         roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
-                        traffic=traffic * samples if traffic else None,
+                        traffic=traffic,
                         peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
                         ms_per_launch=table[top], share_of_step=table[top] / sum(table.values()),
                         algorithmic_per_launch=alg)

@@ -32,7 +32,7 @@ def launch_list():
     tot = sum(v[0] for v in agg.values())
     with open(os.path.join(ROOT, "profiles", f"{R}_launch_list_summary.md"), "w") as f:
         f.write(f"# {R}: ncu launch list (`--metrics gpu__time_duration.sum --clock-control none`, see profiles/run_ncu.sh)\n\n"
-                "Command: `python bench.py --steps 6 --warmup 3 --pretrain 48 --no-graph --skip-cpu` (early training, ~620k samples/step,\n"
+                "Command: `python bench.py --steps 6 --warmup 3 --pretrain 96 --no-graph --skip-cpu` (early training, ~580k samples/step,\n"
                 "dense gradients; per-launch times are cold-cache and serialised -- compare SHARES with bench.py's `kernels_us`).\n\n"
                 "| kernel | launches | total us | us/launch | share |\n|---|---|---|---|---|\n")
         for k, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
