@@ -320,29 +320,80 @@ __global__ void __launch_bounds__(256) composite_loss_fwbw_kernel(
 }
 
 // Test-time compositor: one thread per alive ray, serial over its <= 64 new samples (in place).
+// Device-driven form (ctl != nullptr): ray count / samples per ray come from ctl[0] / ctl[1]; rays that stay alive are
+// appended to alive_next (warp-aggregated atomicAdd on ctl[4]) so that the host never compacts the list, and the
+// samples consumed are added to the 64-bit counter at ctl[6..7].
 __global__ void __launch_bounds__(256) composite_test_fw_kernel(
     const float *__restrict__ sigmas, const float *__restrict__ rgbs, const float *__restrict__ deltas,
     const float *__restrict__ ts, int64_t *alive_indices, float T_threshold,
     const int32_t *__restrict__ n_eff, int n_samples, int64_t n_alive, float *opacity, float *depth,
-    float *rgb) {
-    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_alive) return;
-    const int ne = n_eff[n];
-    if (ne == 0) { alive_indices[n] = -1; return; }
-    const int64_t r = alive_indices[n];
-    float op = opacity[r], dp = depth[r], cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
-    float T = 1.0f - op;
-    for (int s = 0; s < ne; ++s) {
-        const int64_t k = n * n_samples + s;
-        const float a = 1.0f - expf(-__ldg(sigmas + k) * __ldg(deltas + k));
-        const float w = a * T;
-        cr += w * __ldg(rgbs + 3 * k); cg += w * __ldg(rgbs + 3 * k + 1); cb += w * __ldg(rgbs + 3 * k + 2);
-        dp += w * __ldg(ts + k);
-        op += w;
-        T *= 1.0f - a;
-        if (T <= T_threshold) { alive_indices[n] = -1; break; }
+    float *rgb, int32_t *ctl, int64_t *alive_next) {
+    if (ctl != nullptr) {
+        n_alive = ctl[0];
+        n_samples = ctl[1];
     }
-    opacity[r] = op; depth[r] = dp; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+    const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t keep = -1;
+    int used = 0;
+    if (n < n_alive) {
+        const int ne = n_eff[n];
+        used = ne;
+        if (ne == 0) {
+            alive_indices[n] = -1;
+        } else {
+            const int64_t r = alive_indices[n];
+            keep = r;
+            float op = opacity[r], dp = depth[r], cr = rgb[3 * r], cg = rgb[3 * r + 1], cb = rgb[3 * r + 2];
+            float T = 1.0f - op;
+            for (int s = 0; s < ne; ++s) {
+                const int64_t k = n * n_samples + s;
+                const float a = 1.0f - expf(-__ldg(sigmas + k) * __ldg(deltas + k));
+                const float w = a * T;
+                cr += w * __ldg(rgbs + 3 * k); cg += w * __ldg(rgbs + 3 * k + 1); cb += w * __ldg(rgbs + 3 * k + 2);
+                dp += w * __ldg(ts + k);
+                op += w;
+                T *= 1.0f - a;
+                if (T <= T_threshold) { alive_indices[n] = -1; keep = -1; break; }
+            }
+            opacity[r] = op; depth[r] = dp; rgb[3 * r] = cr; rgb[3 * r + 1] = cg; rgb[3 * r + 2] = cb;
+        }
+    }
+    if (ctl != nullptr) {                                    // (all threads of the warp reach this point)
+        const int lane = threadIdx.x & 31;
+        const uint32_t keep_m = __ballot_sync(FULL, keep >= 0);
+        int base = 0;
+        if (lane == 0 && keep_m) base = atomicAdd(ctl + 4, __popc(keep_m));
+        base = __shfl_sync(FULL, base, 0);
+        if (keep >= 0) alive_next[base + __popc(keep_m & ((1u << lane) - 1))] = keep;
+        int tot = used;
+        #pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+        if (lane == 0 && tot) atomicAdd(reinterpret_cast<unsigned long long *>(ctl + 6), (unsigned long long)tot);
+    }
+}
+
+// Round controller of the device-driven render loop (one thread).  ctl (8 x i32, 8-byte aligned):
+// [0] live rays this round, [1] samples per ray, [2] slots = [0]*[1], [3] samples marched per ray so far,
+// [4] live rays found by the compositor (input of the next round), [5] rounds run, [6..7] u64 samples consumed.
+// The schedule is the reference's (rendering.py:68-71): N_samples = max(min(N_rays // N_alive, 64), min_samples),
+// stop once max_samples have been marched.
+__global__ void render_schedule_kernel(int32_t *ctl, int n_rays, int min_samples, int max_samples) {
+    int alive = ctl[4];
+    if (ctl[3] >= max_samples) alive = 0;
+    int s = 0;
+    if (alive > 0) {
+        s = n_rays / alive;
+        s = s < 64 ? s : 64;
+        s = s > min_samples ? s : min_samples;
+    }
+    ctl[0] = alive; ctl[1] = s; ctl[2] = alive * s; ctl[3] += s; ctl[4] = 0; ctl[5] += 1;
+}
+
+extern "C" int b2n_render_schedule(int32_t *ctl, int64_t n_rays, int min_samples, int max_samples, void *stream) {
+    B2N_CHECK_ARG(ctl != nullptr && n_rays >= 0 && n_rays < (1ll << 31) && min_samples >= 1, "bad arguments");
+    render_schedule_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(ctl, (int)n_rays, min_samples, max_samples);
+    B2N_LAUNCH_CHECK();
+    return 0;
 }
 
 static inline unsigned warp_grid(int64_t n_warps) { return b2n_grid((n_warps + 7) / 8, 8); }
@@ -397,14 +448,27 @@ extern "C" int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, c
     return 0;
 }
 
-extern "C" int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas,
-                                     const float *ts, const float *hits_t, int64_t *alive_indices,
+extern "C" int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                                     const float *hits_t, int64_t *alive_indices,
                                      float T_threshold, const int32_t *n_eff, int n_samples,
                                      int64_t n_alive, float *opacity, float *depth, float *rgb, void *stream) {
     (void)hits_t;
     if (n_alive <= 0) return 0;
     composite_test_fw_kernel<<<b2n_blocks(n_alive, 256), 256, 0, (cudaStream_t)stream>>>(
-        sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff, n_samples, n_alive, opacity, depth, rgb);
+        sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff, n_samples, n_alive, opacity, depth, rgb, nullptr,
+        nullptr);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_composite_test_fw_dev(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                                         int64_t *alive_indices, int64_t *alive_next, float T_threshold,
+                                         const int32_t *n_eff, int64_t max_alive, int32_t *ctl, float *opacity,
+                                         float *depth, float *rgb, void *stream) {
+    B2N_CHECK_ARG(ctl != nullptr && alive_next != nullptr, "ctl and alive_next are required");
+    if (max_alive <= 0) return 0;
+    composite_test_fw_kernel<<<b2n_blocks(max_alive, 256), 256, 0, (cudaStream_t)stream>>>(
+        sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff, 1, max_alive, opacity, depth, rgb, ctl, alive_next);
     B2N_LAUNCH_CHECK();
     return 0;
 }

@@ -415,7 +415,11 @@ __global__ void __launch_bounds__(256) march_test_kernel(const float *__restrict
                                                          const int64_t *__restrict__ alive, const __grid_constant__ MarchParams p,
                                                          int n_samples, int64_t n_alive, float *xyzs,
                                                          float *dirs, float *deltas, float *ts,
-                                                         int32_t *n_eff) {
+                                                         int32_t *n_eff, const int32_t *__restrict__ ctl) {
+    if (ctl != nullptr) {  // device-driven render loop: this round's ray count and samples per ray
+        n_alive = ctl[0];
+        n_samples = ctl[1];
+    }
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_alive; n += warps) {
@@ -440,11 +444,10 @@ __global__ void __launch_bounds__(256) march_test_kernel(const float *__restrict
     }
 }
 
-extern "C" int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,
-                                    const int64_t *alive_indices, const uint8_t *density_bitfield,
-                                    int cascades, float scale, float exp_step_factor, int grid_size,
-                                    int max_samples, int n_samples, int64_t n_alive, float *xyzs,
-                                    float *dirs, float *deltas, float *ts, int32_t *n_eff, void *stream) {
+static int launch_march_test(const float *rays_o, const float *rays_d, float *hits_t, const int64_t *alive_indices,
+                             const uint8_t *density_bitfield, int cascades, float scale, float exp_step_factor,
+                             int grid_size, int max_samples, int n_samples, int64_t n_alive, float *xyzs, float *dirs,
+                             float *deltas, float *ts, int32_t *n_eff, const int32_t *ctl, void *stream) {
     MarchParams p;
     if (fill_params(p, density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples)) return 1;
     B2N_CHECK_ARG(n_samples >= 1, "n_samples < 1");
@@ -452,10 +455,31 @@ extern "C" int b2n_raymarching_test(const float *rays_o, const float *rays_d, fl
     cudaStream_t st = (cudaStream_t)stream;
     if (exp_step_factor == 0.0f)
         march_test_kernel<true><<<march_grid(n_alive), 256, 0, st>>>(
-            rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff);
+            rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff, ctl);
     else
         march_test_kernel<false><<<march_grid(n_alive), 256, 0, st>>>(
-            rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff);
+            rays_o, rays_d, hits_t, alive_indices, p, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff, ctl);
     B2N_LAUNCH_CHECK();
     return 0;
+}
+
+extern "C" int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,
+                                    const int64_t *alive_indices, const uint8_t *density_bitfield,
+                                    int cascades, float scale, float exp_step_factor, int grid_size,
+                                    int max_samples, int n_samples, int64_t n_alive, float *xyzs,
+                                    float *dirs, float *deltas, float *ts, int32_t *n_eff, void *stream) {
+    return launch_march_test(rays_o, rays_d, hits_t, alive_indices, density_bitfield, cascades, scale, exp_step_factor,
+                             grid_size, max_samples, n_samples, n_alive, xyzs, dirs, deltas, ts, n_eff, nullptr, stream);
+}
+
+// Device-driven form: the number of live rays and the samples per ray of this round are read from ctl[0], ctl[1]
+// (written by b2n_render_schedule); max_alive only sizes the grid.
+extern "C" int b2n_raymarching_test_dev(const float *rays_o, const float *rays_d, float *hits_t,
+                                        const int64_t *alive_indices, const uint8_t *density_bitfield, int cascades,
+                                        float scale, float exp_step_factor, int grid_size, int max_samples,
+                                        int64_t max_alive, const int32_t *ctl, float *xyzs, float *dirs,
+                                        float *deltas, float *ts, int32_t *n_eff, void *stream) {
+    B2N_CHECK_ARG(ctl != nullptr, "ctl is required");
+    return launch_march_test(rays_o, rays_d, hits_t, alive_indices, density_bitfield, cascades, scale, exp_step_factor,
+                             grid_size, max_samples, 1, max_alive, xyzs, dirs, deltas, ts, n_eff, ctl, stream);
 }

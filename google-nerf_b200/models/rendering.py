@@ -45,6 +45,8 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 
     samples = total_samples = 0
     fused = getattr(model, "encoding", None) == "HashGrid" and hasattr(model, "_forward_fused")
+    if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
+        return _DeviceLoop.get(model, N_rays, exp_step_factor, T_threshold).run(rays_o, rays_d, hits)
     alive_indices = torch.arange(N_rays, device=device)
     min_samples = 1 if exp_step_factor == 0 else 4
     while samples < MAX_SAMPLES:
@@ -78,6 +80,92 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 
     rgb = rgb + _background(exp_step_factor, device) * (1 - opacity)[:, None]
     return {"opacity": opacity, "depth": depth, "rgb": rgb, "total_samples": total_samples}
+
+
+class _DeviceLoop:
+    """The loop of rendering.py:64-102 driven from the device.  One round = schedule -> march -> hash-grid gather ->
+    fused field MLP -> composite (+ compaction of the alive list); ray counts, samples per ray and the alive list
+    stay on the GPU, every launch has a fixed grid, so two rounds (the alive list ping-pongs) are captured as ONE CUDA
+    graph and replayed; the host looks at the live-ray count once per ROUNDS_PER_SYNC rounds instead of twice per
+    round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
+    per-ray arithmetic as the host loop, so the images are identical."""
+    ROUNDS_PER_SYNC = 6
+
+    @classmethod
+    def get(cls, model, n_rays, esf, T_threshold):
+        p16, image = model._fused_state(model.center.device)
+        key = (n_rays, float(esf), float(T_threshold), p16.data_ptr(), image.data_ptr(), model.density_bitfield.data_ptr())
+        st = getattr(model, "_device_loop", None)
+        if st is None or st.key != key:
+            st = cls(model, n_rays, float(esf), float(T_threshold), key)
+            model._device_loop = st
+        return st
+
+    def __init__(self, model, n, esf, T_threshold, key):
+        self.key, self.model, self.n, self.esf, self.T = key, model, n, esf, T_threshold
+        dev = model.center.device
+        self.min_samples = 1 if esf == 0 else 4
+        cap = self.cap = n * self.min_samples            # slots per round never exceed max(N_rays, N_alive*min_samples)
+        f = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.rays_o, self.rays_d, self.hits = f(n, 3), f(n, 3), f(n, 2)
+        self.alive = f(2, n, dt=torch.int64); self.arange = torch.arange(n, device=dev)
+        self.n_eff = f(n, dt=torch.int32)
+        self.xyzs, self.dirs, self.deltas, self.ts = f(cap, 3), f(cap, 3), f(cap), f(cap)
+        self.enc = f(cap, 32, dt=torch.float16); self.sigmas, self.rgbs = f(cap), f(cap, 3)
+        self.opacity, self.depth, self.rgb = f(n), f(n), f(n, 3)
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=dev)
+        self.ctl_init = torch.tensor([0, 0, 0, 0, n, 0, 0, 0], dtype=torch.int32, device=dev)
+        self.ctl_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.graph = None
+
+    def _reset(self):
+        self.alive[0].copy_(self.arange)
+        self.opacity.zero_(); self.depth.zero_(); self.rgb.zero_()
+        self.ctl.copy_(self.ctl_init)
+
+    def _round(self, cur):
+        from .. import _lib as L
+        m, P, call, n, cap = self.model, L.ptr, L.call, self.n, self.cap
+        p16, image = m._fused_state(m.center.device)
+        slots = self.ctl[2:]
+        call("b2n_render_schedule", P(self.ctl), n, self.min_samples, MAX_SAMPLES)
+        call("b2n_raymarching_test_dev", P(self.rays_o), P(self.rays_d), P(self.hits), P(self.alive[cur]),
+             P(m.density_bitfield), m.cascades, float(m.scale), self.esf, m.grid_size, MAX_SAMPLES, n, P(self.ctl),
+             P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts), P(self.n_eff))
+        call("b2n_hashgrid_fw", P(self.xyzs), P(p16[m.xyz_encoder.mlp.n_params:]), m._layout, cap, P(slots), P(self.enc), 32)
+        call("b2n_field_mlp_fw", P(self.enc), P(self.dirs), P(image), cap, P(slots), P(self.sigmas), P(self.rgbs),
+             None, None, None)
+        call("b2n_composite_test_fw_dev", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.alive[cur]),
+             P(self.alive[1 - cur]), self.T, P(self.n_eff), n, P(self.ctl), P(self.opacity), P(self.depth), P(self.rgb))
+
+    def _two_rounds(self):
+        self._round(0); self._round(1)
+
+    def run(self, rays_o, rays_d, hits):
+        self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.hits.copy_(hits)
+        if self.graph is None:
+            self._reset()
+            side = torch.cuda.Stream(device=rays_o.device)   # eager warm-up, then capture
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._two_rounds()
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._two_rounds()
+            self.hits.copy_(hits)                            # the warm-up rounds advanced the rays
+        self._reset()
+        while True:
+            for _ in range(self.ROUNDS_PER_SYNC // 2):
+                self.graph.replay()
+            self.ctl_host.copy_(self.ctl, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            c = self.ctl_host
+            if int(c[4]) == 0 or int(c[3]) >= MAX_SAMPLES:
+                break
+        total = (int(c[7]) << 32) | (int(c[6]) & 0xffffffff)
+        rgb = self.rgb + _background(self.esf, self.rgb.device) * (1 - self.opacity)[:, None]
+        return {"opacity": self.opacity.clone(), "depth": self.depth.clone(), "rgb": rgb, "total_samples": total}
 
 
 def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):

@@ -90,6 +90,26 @@ B2N_API int b2n_raymarching_test(const float *rays_o, const float *rays_d, float
                          int n_samples, int64_t n_alive, float *xyzs, float *dirs, float *deltas,
                          float *ts, int32_t *n_eff, void *stream);
 
+/* Device-driven test-time loop (the body of models/rendering.py:64-102 without its per-iteration host syncs).
+ * ctl: 8 x i32 on the device, 8-byte aligned: [0] live rays this round, [1] samples per ray, [2] slots = [0]*[1],
+ * [3] samples marched per ray so far, [4] live rays left by the compositor (the next round's [0]; the caller seeds it
+ * with n_rays), [5] rounds run, [6..7] u64 samples consumed.  One round = b2n_render_schedule ->
+ * b2n_raymarching_test_dev -> field kernels with n_dev = ctl + 2 -> b2n_composite_test_fw_dev; the alive list
+ * ping-pongs between two buffers.  Every launch has a fixed grid, so a round is CUDA-graph replayable and rounds
+ * after the last ray died are no-ops.  b2n_render_schedule applies rendering.py:68-71:
+ * N_samples = max(min(n_rays // N_alive, 64), min_samples), stop after max_samples. */
+B2N_API int b2n_render_schedule(int32_t *ctl, int64_t n_rays, int min_samples, int max_samples, void *stream);
+B2N_API int b2n_raymarching_test_dev(const float *rays_o, const float *rays_d, float *hits_t,
+                             const int64_t *alive_indices, const uint8_t *density_bitfield, int cascades,
+                             float scale, float exp_step_factor, int grid_size, int max_samples,
+                             int64_t max_alive, const int32_t *ctl, float *xyzs, float *dirs, float *deltas,
+                             float *ts, int32_t *n_eff, void *stream);
+/* as b2n_composite_test_fw; rays that stay alive are appended to alive_next (count in ctl[4]). */
+B2N_API int b2n_composite_test_fw_dev(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
+                              int64_t *alive_indices, int64_t *alive_next, float T_threshold,
+                              const int32_t *n_eff, int64_t max_alive, int32_t *ctl, float *opacity, float *depth,
+                              float *rgb, void *stream);
+
 /* ---------------------------------------------------------------- vren: compositing ------------------ */
 /* vren.composite_train_fw (models/custom_functions.py:140-142).  n_total_dev (device i32, may be NULL)
  * is unused by the math; rays_a drives everything.  Outputs indexed by rays_a[:,0]. */

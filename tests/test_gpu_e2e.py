@@ -88,6 +88,22 @@ def test_render_test_time(pair):
     assert not cpu["rgb"].is_cuda
 
 
+@pytest.mark.parametrize("esf,thr", [(0.0, 1e-2), (0.0, 1e-4), (1.0 / 256, 1e-3)])
+def test_render_device_loop_equals_host_loop(pair, esf, thr):
+    """The graph-replayed device-driven loop (alive list, ray counts and samples per ray on the GPU) produces the very
+    same image and sample count as the reference-style host loop of rendering.py:42-114, also when called again on
+    other rays (buffers and graph are reused)."""
+    from google_nerf_b200.models.rendering import render
+    ref, model, s = pair
+    for lo, hi in ((0, 700), (68, 768)):
+        ro, rd = s["rays_o"][lo:hi].to(DEV), s["rays_d"][lo:hi].to(DEV)
+        a = render(model, ro, rd.clone(), test_time=True, T_threshold=thr, exp_step_factor=esf, device_loop=False)
+        b = render(model, ro, rd.clone(), test_time=True, T_threshold=thr, exp_step_factor=esf)
+        assert int(a["total_samples"]) == int(b["total_samples"]) > 0
+        for k in ("opacity", "depth", "rgb"):
+            assert torch.equal(a[k], b[k]), k
+
+
 def test_frequency_variant_forward(pair):
     from google_nerf_b200.models.networks import NGP
     from oracle import ngp_ref as O
