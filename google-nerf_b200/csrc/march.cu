@@ -25,6 +25,7 @@
 #define MAX_MIPS 16
 #define WS_WORDS 64          // workspace words per ray: [0] = n_chunks | overflow << 31, [1..63] = chunk masks
 #define MAX_CHUNKS (WS_WORDS - 1)
+#define SERIAL_MIN_RAYS 16384  // test marcher: at or above this many live rays, thread-per-ray; below, warp-per-ray
 
 struct MarchParams {
     const uint8_t *bitfield;
@@ -419,6 +420,41 @@ __global__ void __launch_bounds__(256) march_test_kernel(const float *__restrict
     if (ctl != nullptr) {  // device-driven render loop: this round's ray count and samples per ray
         n_alive = ctl[0];
         n_samples = ctl[1];
+    }
+    if (n_alive >= SERIAL_MIN_RAYS) {
+        // Many live rays (full frames): one THREAD per ray running the reference's serial loop.  With enough rays to
+        // fill the machine this does ~10x less work than the warp form -- a thread touches one rung per voxel it
+        // crosses and stops right after its few samples, where a warp probes 32 rungs at a time -- and neighbouring
+        // pixels keep the lanes of a warp on similar paths.  Same ladder, same probe: bit-identical samples.
+        for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_alive; n += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t r = alive[n];
+            const Ray q = load_ray(rays_o, rays_d, r);
+            float t = hits_t[2 * r];
+            const float t2 = hits_t[2 * r + 1];
+            const PackedSink sink{xyzs, dirs, deltas, ts, n * n_samples};
+            int s = 0;
+            while (t < t2 && s < n_samples) {
+                float dt, x, y, z, target;
+                if (probe(q, t, p, dt, x, y, z, target)) {
+                    sink.put(s, x, y, z, t, dt, q);
+                    t = t + dt;
+                    hits_t[2 * r] = t;
+                    ++s;
+                } else {
+                    do {
+                        t = t + (ESF_ZERO ? p.dt0 : calc_dt(t, p));
+                    } while (t < target);
+                }
+            }
+            for (int k = s; k < n_samples; ++k) {            // unused slots stay zero (rendering.py:87)
+                const int64_t o = n * n_samples + k;
+                xyzs[3 * o] = 0.f; xyzs[3 * o + 1] = 0.f; xyzs[3 * o + 2] = 0.f;
+                dirs[3 * o] = 0.f; dirs[3 * o + 1] = 0.f; dirs[3 * o + 2] = 0.f;
+                ts[o] = 0.f; deltas[o] = 0.f;
+            }
+            n_eff[n] = s;
+        }
+        return;
     }
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;

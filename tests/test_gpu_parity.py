@@ -140,9 +140,12 @@ def test_raymarching_train_capacity_clamp(mods, scene05):
         assert torch.equal(deltas.cpu(), full[3][:cap]) and torch.equal(dirs.cpu(), full[2][:cap])
 
 
-@pytest.mark.parametrize("scale,esf", [(0.5, 0.0), (4.0, 1 / 256)])
-def test_raymarching_test_and_composite_test(mods, scale, esf):
-    s = make_scene(scale, 1024, seed=7)
+@pytest.mark.parametrize("scale,esf,n_rays", [(0.5, 0.0, 1024), (4.0, 1 / 256, 1024), (0.5, 0.0, 20000),
+                                               (4.0, 1 / 256, 17000)])
+def test_raymarching_test_and_composite_test(mods, scale, esf, n_rays):
+    # >= 16384 live rays take the marcher's thread-per-ray path, fewer the warp-per-ray one (rounds of the same run
+    # cross over as rays die)
+    s = make_scene(scale, n_rays, seed=7)
     n = s["rays_o"].shape[0]
     hA = hits_of(mods, s)[:, 0].contiguous(); hB = hA.clone().to(DEV)
     d = cu(s)
