@@ -48,6 +48,7 @@ _SIGS = {
     "b2n_morton3D_invert": [_P, _L, _P, _P],
     "b2n_packbits": [_P, _L, _F, _P, _P, _P],
     "b2n_raymarching_train_count": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _L, _P, _P, _P, _P],
+    "b2n_raymarching_train_count_serial": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _L, _P, _P, _P, _P],
     "b2n_raymarching_train_write": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
     "b2n_set_march_ctas_per_sm": [_I],
     "b2n_raymarching_test": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],

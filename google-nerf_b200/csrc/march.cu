@@ -283,6 +283,58 @@ __global__ void __launch_bounds__(256) march_train_kernel(const float *__restric
     }
 }
 
+// Count pass, one THREAD per ray: the reference's serial loop, recording the emission mask of every 32-rung chunk of
+// the ladder (same workspace format as the warp form, so the write pass replays it unchanged).  It takes longer per
+// ray than a warp, but ~10x fewer issue slots: the trainer runs it on the side stream for the NEXT batch, where its
+// latency is hidden and what matters is how little it takes away from the kernels of the current step.
+// The workspace must be zero on entry (chunks without a sample are not written).
+template <bool ESF_ZERO>
+__global__ void __launch_bounds__(128) march_train_count_serial_kernel(const float *__restrict__ rays_o,
+                                                                       const float *__restrict__ rays_d,
+                                                                       const float *__restrict__ hits_t,
+                                                                       const float *__restrict__ noise,
+                                                                       const __grid_constant__ MarchParams p,
+                                                                       int64_t n_rays, int64_t *rays_a,
+                                                                       uint32_t *workspace) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_rays; r += (int64_t)gridDim.x * blockDim.x) {
+        const Ray q = load_ray(rays_o, rays_d, r);
+        float t = __ldg(hits_t + 2 * r);
+        const float t2 = __ldg(hits_t + 2 * r + 1);
+        uint32_t *ws = workspace + r * WS_WORDS;
+        int n = 0;
+        uint32_t head = 0;
+        if (t >= 0.0f) {
+            t += calc_dt(t, p) * __ldg(noise + r);
+            if (t < t2) {
+                uint32_t k = 0, word = 0, mask = 0;          // rung index on the ladder, its chunk, the chunk's mask
+                bool overflow = false;
+                while (t < t2 && n < p.max_samples) {
+                    float dt, x, y, z, target;
+                    if (probe(q, t, p, dt, x, y, z, target)) {
+                        if ((k >> 5) != word) {
+                            if (mask) { if (word < MAX_CHUNKS) ws[1 + word] = mask; else overflow = true; }
+                            word = k >> 5; mask = 0;
+                        }
+                        mask |= 1u << (k & 31);
+                        ++n;
+                        t = t + dt; ++k;
+                    } else {
+                        do {
+                            t = t + (ESF_ZERO ? p.dt0 : calc_dt(t, p)); ++k;
+                        } while (t < target);
+                    }
+                }
+                if (mask) { if (word < MAX_CHUNKS) ws[1 + word] = mask; else overflow = true; }
+                const uint32_t chunks = n ? word + 1 : 0;
+                head = (chunks < MAX_CHUNKS ? chunks : MAX_CHUNKS) | (overflow ? 0x80000000u : 0u);
+            }
+        }
+        ws[0] = head;
+        rays_a[3 * r] = r;
+        rays_a[3 * r + 2] = n;
+    }
+}
+
 // Exclusive scan of the per-ray counts in ray order (deterministic packing) + capacity clamp.  One CTA:
 // n_rays is a batch (8192 ... a few 100k), the scan reads 8 B/ray and is latency-bound.
 __global__ void __launch_bounds__(1024) march_scan_kernel(int64_t *rays_a, int64_t n_rays, int64_t capacity,
@@ -382,6 +434,32 @@ extern "C" int b2n_raymarching_train_count(const float *rays_o, const float *ray
         else
             march_train_kernel<false, false><<<march_grid(n_rays, g_march_ctas_per_sm), 256, 0, st>>>(
                 rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr, workspace);
+        B2N_LAUNCH_CHECK();
+    }
+    march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, capacity, counter);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b2n_raymarching_train_count_serial(const float *rays_o, const float *rays_d, const float *hits_t,
+                                                  const uint8_t *density_bitfield, int cascades, float scale,
+                                                  float exp_step_factor, const float *noise, int grid_size,
+                                                  int max_samples, int64_t n_rays, int64_t capacity,
+                                                  int64_t *rays_a, int32_t *counter, uint32_t *workspace,
+                                                  void *stream) {
+    MarchParams p;
+    if (fill_params(p, density_bitfield, cascades, scale, exp_step_factor, grid_size, max_samples)) return 1;
+    B2N_CHECK_ARG(n_rays >= 0 && workspace != nullptr, "n_rays < 0 or no workspace");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_rays > 0) {
+        cudaMemsetAsync(workspace, 0, (size_t)n_rays * WS_WORDS * sizeof(uint32_t), st);
+        const unsigned grid = b2n_grid(b2n_blocks(n_rays, 128), 16);
+        if (exp_step_factor == 0.0f)
+            march_train_count_serial_kernel<true><<<grid, 128, 0, st>>>(rays_o, rays_d, hits_t, noise, p, n_rays, rays_a,
+                                                                        workspace);
+        else
+            march_train_count_serial_kernel<false><<<grid, 128, 0, st>>>(rays_o, rays_d, hits_t, noise, p, n_rays, rays_a,
+                                                                         workspace);
         B2N_LAUNCH_CHECK();
     }
     march_scan_kernel<<<1, 1024, 0, st>>>(rays_a, n_rays, capacity, counter);

