@@ -240,8 +240,8 @@ extern "C" int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(out_stride >= 2 * g.n_levels && out_stride % 2 == 0, "out_stride too small / odd");
     if (n <= 0) return 0;
-    hashgrid_fw_kernel<<<b2n_grid(b2n_blocks(2 * n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
-        x, (const __half2 *)table, g, n, n_dev, (__half *)out, out_stride);
+    b2n_launch(hashgrid_fw_kernel, b2n_grid(b2n_blocks(2 * n, 128), 16), 128, (cudaStream_t)stream,
+               x, (const __half2 *)table, g, n, n_dev, (__half *)out, out_stride);
     B2N_LAUNCH_CHECK();
     return 0;
 }
@@ -253,8 +253,8 @@ extern "C" int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_s
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(dy_stride >= 2 * g.n_levels && dy_stride % 2 == 0, "dy_stride too small / odd");
     if (n <= 0) return 0;
-    hashgrid_bw_kernel<<<b2n_grid(b2n_blocks(n, 128), 16), 128, 0, (cudaStream_t)stream>>>(
-        x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table, sample_idx);
+    b2n_launch(hashgrid_bw_kernel, b2n_grid(b2n_blocks(n, 128), 16), 128, (cudaStream_t)stream,
+               x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table, sample_idx);
     B2N_LAUNCH_CHECK();
     return 0;
 }

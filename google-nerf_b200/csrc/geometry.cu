@@ -8,6 +8,37 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+static cudaAccessPolicyWindow g_l2_window;
+static bool g_l2_window_on = false;
+bool b2n_l2_window(cudaAccessPolicyWindow *out) {
+    if (g_l2_window_on) *out = g_l2_window;
+    return g_l2_window_on;
+}
+
+extern "C" int b2n_set_l2_persist(void *base, int64_t bytes) {
+    if (base == nullptr || bytes <= 0) {                    // switch off and give the carve-out back
+        g_l2_window_on = false;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
+        return 0;
+    }
+    int dev = 0, max_persist = 0, max_window = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+    if (max_persist <= 0 || max_window <= 0) { g_l2_window_on = false; return 0; }   // not supported: stay off
+    const size_t carve = (size_t)bytes < (size_t)max_persist ? (size_t)bytes : (size_t)max_persist;
+    const cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    if (e != cudaSuccess) { b2n_set_error("b2n_set_l2_persist: %s", cudaGetErrorString(e)); return 2; }
+    const size_t span = (size_t)bytes < (size_t)max_window ? (size_t)bytes : (size_t)max_window;
+    g_l2_window.base_ptr = base;
+    g_l2_window.num_bytes = span;
+    g_l2_window.hitRatio = carve >= span ? 1.0f : (float)carve / (float)span;
+    g_l2_window.hitProp = cudaAccessPropertyPersisting;
+    g_l2_window.missProp = cudaAccessPropertyStreaming;
+    g_l2_window_on = true;
+    return 0;
+}
+
 void b2n_set_error(const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

@@ -254,6 +254,12 @@ B2N_API int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_av
                                float beta1, float beta2, float eps, float inv_scale, int step,
                                const void *hyper_dev, void *stream);
 
+/* Performance hint (process-wide, per current device): keep [base, base + bytes) -- the gradient vector and the
+ * fp16 parameter copy -- resident in L2 across the training step.  Sets the persisting-L2 carve-out and makes
+ * b2n_hashgrid_fw/_bw and b2n_adam_step launch with a matching access-policy window.  base == NULL switches it off.
+ * No effect on results. */
+B2N_API int b2n_set_l2_persist(void *base, int64_t bytes);
+
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
  * over one flat fp32 parameter; grad is multiplied by inv_scale, then ZEROED; half_copy (may be NULL)
