@@ -43,7 +43,8 @@ _SIGS = {
     "b2n_peer_close": [_P],
     "b2n_peer_free": [_P],
     "b2n_peer_barrier": [_P, _I, _I, _P, _D, _P],
-    "b2n_adam_step_peer": [_P, _P, _P, _P, _P, _I, _L, _L, _F, _F, _F, _F, _F, _I, _P, _P],
+    "b2n_adam_step_peer": [_P, _P, _P, _P, _P, _L, _L, _P, _I, _L, _L, _F, _F, _F, _F, _F, _I, _P, _P],
+    "b2n_grad_pack_half": [_P, _P, _L, _L, _P],
     "b2n_rays_from_indices": [_P, _P, _P, _P, _L, _P, _P, _P],
     "b2n_morton3D": [_P, _L, _P, _P],
     "b2n_morton3D_invert": [_P, _L, _P, _P],

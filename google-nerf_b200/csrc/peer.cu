@@ -111,11 +111,43 @@ extern "C" int b2n_peer_barrier(void *const *flag_ptrs, int rank, int world, uin
 }
 
 // ------------------------------------------------------------------------------------------------ fused optimiser
+// Optional fp16 wire format for the hash-table gradients: each rank converts the [lo, hi) part of its (loss-scaled) fp32
+// gradient vector to fp16 once (saturating), clearing that part of the fp32 vector in the same pass, and the owners
+// read the fp16 copies -- half the NVLink bytes of the dominant term.  tiny-cuda-nn itself keeps per-rank table
+// gradients in fp16 at the same loss scale, so this loses nothing against the reference's DDP.  The few MLP weights
+// outside [lo, hi) stay fp32 on the wire (Adam turns their rounding into visible trajectory differences).
+__global__ void __launch_bounds__(256) grad_pack_half_kernel(float4 *__restrict__ g, uint2 *__restrict__ g16, int64_t lo4,
+                                                             int64_t hi4) {
+    for (int64_t i = lo4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 v = g[i];
+        v.x = fminf(fmaxf(v.x, -65504.f), 65504.f); v.y = fminf(fmaxf(v.y, -65504.f), 65504.f);
+        v.z = fminf(fmaxf(v.z, -65504.f), 65504.f); v.w = fminf(fmaxf(v.w, -65504.f), 65504.f);
+        const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t *>(&a);
+        o.y = *reinterpret_cast<const uint32_t *>(&b);
+        g16[i] = o;
+        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+extern "C" int b2n_grad_pack_half(float *grad, b2n_half *grad16, int64_t lo, int64_t hi, void *stream) {
+    B2N_CHECK_ARG(lo % 4 == 0 && hi % 4 == 0 && lo <= hi, "range bounds must be multiples of 4");
+    if (lo == hi) return 0;
+    grad_pack_half_kernel<<<b2n_grid(b2n_blocks((hi - lo) / 4, 256), 8), 256, 0, (cudaStream_t)stream>>>(
+        (float4 *)grad, (uint2 *)grad16, lo / 4, hi / 4);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
 // Per owned parameter: W gradient reads (W-1 of them over NVLink), p/m/v read + written locally, W fp16 writes
-// (W-1 over NVLink).  The gradients are left as they are: each rank clears its own vector with one memset after the
+// (W-1 over NVLink).  fp32 gradients are left as they are: each rank clears its own vector with one memset after the
 // closing barrier (a local HBM fill is cheaper than W-1 remote zero stores per element).
+template <bool HALF_GRAD>
 __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, float4 *__restrict__ m,
                                                         float4 *__restrict__ v, const __grid_constant__ PeerPtrs g,
+                                                        const __grid_constant__ PeerPtrs g16, int64_t half_lo4,
+                                                        int64_t half_hi4,
                                                         const __grid_constant__ PeerPtrs h, int world, int64_t first4,
                                                         int64_t n4, float lr, float b1, float b2, float eps,
                                                         float inv_scale, int step, const void *__restrict__ hyper) {
@@ -126,10 +158,18 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, 
     const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
-        #pragma unroll 4
+        const bool use16 = HALF_GRAD && first4 + i >= half_lo4 && first4 + i < half_hi4;
+        #pragma unroll 8
         for (int r = 0; r < world; ++r) {                    // fixed order: the sum does not depend on timing
-            const float4 t = reinterpret_cast<const float4 *>(g.p[r])[first4 + i];
-            gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+            if (use16) {
+                const uint2 t = reinterpret_cast<const uint2 *>(g16.p[r])[first4 + i];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&t.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&t.y));
+                gg.x += a.x; gg.y += a.y; gg.z += b.x; gg.w += b.y;
+            } else {
+                const float4 t = reinterpret_cast<const float4 *>(g.p[r])[first4 + i];
+                gg.x += t.x; gg.y += t.y; gg.z += t.z; gg.w += t.w;
+            }
         }
         float4 pp = p[i], mm = m[i], vv = v[i];
         float *P = &pp.x, *G = &gg.x, *M = &mm.x, *V = &vv.x;
@@ -150,21 +190,29 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, 
 }
 
 extern "C" int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_avg_sq, void *const *grad_ptrs,
-                                  void *const *half_ptrs, int world, int64_t shard_first, int64_t shard_n, float lr,
-                                  float beta1, float beta2, float eps, float inv_scale, int step,
-                                  const void *hyper_dev, void *stream) {
+                                  void *const *grad16_ptrs, int64_t half_lo, int64_t half_hi, void *const *half_ptrs,
+                                  int world, int64_t shard_first, int64_t shard_n, float lr, float beta1, float beta2,
+                                  float eps, float inv_scale, int step, const void *hyper_dev, void *stream) {
     B2N_CHECK_ARG(world >= 1 && world <= PEER_MAX_WORLD, "bad world size");
     B2N_CHECK_ARG(shard_n % 4 == 0 && shard_first % 4 == 0, "shard bounds must be multiples of 4");
+    B2N_CHECK_ARG(half_lo % 4 == 0 && half_hi % 4 == 0, "fp16 range bounds must be multiples of 4");
     B2N_CHECK_ARG(step >= 1 || hyper_dev != nullptr, "step is 1-based");
     if (shard_n == 0) return 0;
-    PeerPtrs g, h;
+    PeerPtrs g, g16, h;
     for (int r = 0; r < PEER_MAX_WORLD; ++r) {
         g.p[r] = r < world ? grad_ptrs[r] : nullptr;
+        g16.p[r] = (r < world && grad16_ptrs != nullptr) ? grad16_ptrs[r] : nullptr;
         h.p[r] = r < world ? half_ptrs[r] : nullptr;
     }
-    adam_peer_kernel<<<b2n_grid(b2n_blocks(shard_n / 4, 256), 8), 256, 0, (cudaStream_t)stream>>>(
-        (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, h, world, shard_first / 4, shard_n / 4, lr,
-        beta1, beta2, eps, inv_scale, step, hyper_dev);
+    const unsigned grid = b2n_grid(b2n_blocks(shard_n / 4, 256), 8);
+    if (grad16_ptrs != nullptr && half_hi > half_lo)
+        adam_peer_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, g16, half_lo / 4, half_hi / 4, h, world,
+            shard_first / 4, shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+    else
+        adam_peer_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, g16, 0, 0, h, world, shard_first / 4,
+            shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
     B2N_LAUNCH_CHECK();
     return 0;
 }

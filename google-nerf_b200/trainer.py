@@ -49,7 +49,7 @@ class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
-                 march_ctas_per_sm=None, comm=None, comm_in_graph=False):
+                 march_ctas_per_sm=None, comm=None, comm_in_graph=False, grad_fp16=None):
         if model.encoding != "HashGrid":
             raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
                              "render() + autograd")
@@ -102,12 +102,19 @@ class NGPTrainer:
         self.comm = (comm or "p2p") if self.world > 1 else "none"
         if self.comm not in ("none", "p2p", "nccl"):
             raise ValueError(f"unknown comm {comm!r}")
-        self.peer = None
+        self.peer, self.grad_fp16 = None, False
         if self.comm == "p2p":
             # gradient vector and fp16 working copy live in NVLink peer memory: the fused reduce + Adam + broadcast
             # kernel of every rank addresses all of them (peer.py / csrc/peer.cu)
             from .peer import PeerBlock
-            self.peer = PeerBlock({"g": (_f32, self.n_pad), "h": (_f16, self.n_pad)}, self.dev, process_group)
+            # wire format of the gradients: fp16 copies halve the NVLink bytes of the exchange at the price of one
+            # local pack pass (which also clears the fp32 vector); measured to pay from 4 ranks up
+            self.grad_fp16 = os.environ.get("B2N_GRAD_FP16", "1" if self.world >= 4 else "0") == "1" \
+                if grad_fp16 is None else bool(grad_fp16)
+            regions = {"g": (_f32, self.n_pad), "h": (_f16, self.n_pad)}
+            if self.grad_fp16:
+                regions["g16"] = (_f16, self.n_pad)
+            self.peer = PeerBlock(regions, self.dev, process_group)
             self.g_all, self.h_all = self.peer.tensor("g"), self.peer.tensor("h")
             self.h_all.copy_(tc.cast_half(p_pad))
             torch.cuda.synchronize(self.dev)
@@ -237,11 +244,18 @@ class NGPTrainer:
         P, call, pb = L.ptr, L.call, self.peer
         inv = 1.0 / (self.loss_scale * self.world)
         b1, b2 = self.betas
+        lo16, hi16 = self.n_mlp, self.p_xyz.numel()           # the hash table; the MLP weights stay fp32 on the wire
+        if self.grad_fp16:
+            call("b2n_grad_pack_half", P(self.g_all), P(pb.tensor("g16")), lo16, hi16)
         pb.barrier()
-        call("b2n_adam_step_peer", P(self.p_shard), P(self.m), P(self.v), pb.table("g"), pb.table("h"), self.world,
-             self.rank * self.shard, self.shard, self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
+        call("b2n_adam_step_peer", P(self.p_shard), P(self.m), P(self.v), pb.table("g"),
+             pb.table("g16") if self.grad_fp16 else None, lo16, hi16 if self.grad_fp16 else lo16, pb.table("h"),
+             self.world, self.rank * self.shard, self.shard, self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
         pb.barrier()
-        self.g_all.zero_()
+        if self.grad_fp16:
+            self.g_all[:lo16].zero_(); self.g_all[hi16:].zero_()
+        else:
+            self.g_all.zero_()
         self._pack_weights()
 
     def _pack_weights(self):

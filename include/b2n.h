@@ -245,14 +245,18 @@ B2N_API int b2n_peer_free(void *ptr);
 B2N_API int b2n_peer_barrier(void *const *flag_ptrs, int rank, int world, uint32_t *state, double timeout_s,
                              void *stream);
 /* The fused step for this rank's shard [shard_first, shard_first + shard_n) of the flat parameter vector:
- * grad = sum_r grad_ptrs[r][i] (rank order), FusedAdam update (see b2n_adam_step) of param_shard / exp_avg /
- * exp_avg_sq (local, shard_n elements), fp16 result stored to half_ptrs[r][i] for every r.  grad_ptrs / half_ptrs:
- * HOST arrays of `world` device pointers to each rank's full fp32 gradient / fp16 parameter vector.  Gradients are
- * left untouched (their holder clears them after the closing barrier). */
+ * grad = sum_r grad[r][i] (rank order), FusedAdam update (see b2n_adam_step) of param_shard / exp_avg / exp_avg_sq
+ * (local, shard_n elements), fp16 result stored to half_ptrs[r][i] for every r.  grad_ptrs / grad16_ptrs / half_ptrs:
+ * HOST arrays of `world` device pointers to each rank's full fp32 gradient / fp16 gradient copy / fp16 parameter
+ * vector.  Elements with index in [half_lo, half_hi) are read from the fp16 copies made by b2n_grad_pack_half (half
+ * the NVLink bytes; grad16_ptrs == NULL or an empty range: everything fp32).  fp32 gradients are left untouched:
+ * their holder clears them after the closing barrier. */
 B2N_API int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_avg_sq, void *const *grad_ptrs,
-                               void *const *half_ptrs, int world, int64_t shard_first, int64_t shard_n, float lr,
-                               float beta1, float beta2, float eps, float inv_scale, int step,
-                               const void *hyper_dev, void *stream);
+                               void *const *grad16_ptrs, int64_t half_lo, int64_t half_hi, void *const *half_ptrs,
+                               int world, int64_t shard_first, int64_t shard_n, float lr, float beta1, float beta2,
+                               float eps, float inv_scale, int step, const void *hyper_dev, void *stream);
+/* For i in [lo, hi): grad16[i] = saturate_fp16(grad[i]); grad[i] = 0 -- the wire copy of this rank's table gradient. */
+B2N_API int b2n_grad_pack_half(float *grad, b2n_half *grad16, int64_t lo, int64_t hi, void *stream);
 
 /* Performance hint (process-wide, per current device): keep [base, base + bytes) -- the gradient vector and the
  * fp16 parameter copy -- resident in L2 across the training step.  Sets the persisting-L2 carve-out and makes

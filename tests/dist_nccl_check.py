@@ -34,32 +34,48 @@ def main():
         torch.manual_seed(0)
         m = NGP(0.5, log2_T=15).to(dev)
         m.density_bitfield.copy_(s["bitfield"])
-        tr = NGPTrainer(m, n_rays=512, use_graph=True, samples_per_ray=200, grid_update_interval=8, warmup_steps=10 ** 9,
+        # no occupancy update inside the compared trajectory (its per-cell jitter is drawn per rank, so the learned
+        # bitfields of the two runs agree only statistically); it is exercised on its own below
+        tr = NGPTrainer(m, n_rays=512, use_graph=True, samples_per_ray=200, grid_update_interval=10 ** 9, warmup_steps=10 ** 9,
                         seed=3, data_parallel=dp, comm=os.environ.get("B2N_COMM", "p2p"),
                         comm_in_graph=os.environ.get("B2N_COMM_IN_GRAPH", "0") == "1")
+        tr.step_count = 1                                    # (step 0 would start with an update)
         tr.fixed_noise = s["noise"].to(dev)
         losses = [float(tr.step(ro, rd, tgt).item()) for _ in range(24)]
         tr.sync_model()
         if tr.peer is not None:
             tr.peer.check()
-        out[dp] = (losses, m.xyz_encoder.params.detach().clone(), m.rgb_net.params.detach().clone(),
-                   m.density_bitfield.clone())
-    l1, p1, r1, b1 = out[False]; l2, p2, r2, b2 = out[True]
+        params = (m.xyz_encoder.params.detach().clone(), m.rgb_net.params.detach().clone())
+        tr.update_density_grid(warmup=True)                  # world > 1: cells shared out over the ranks + max-reduce
+        tr.update_density_grid(warmup=False)
+        torch.cuda.synchronize()
+        out[dp] = (losses, *params, m.density_bitfield.clone(), m.density_grid.clone())
+        wire16 = tr.grad_fp16
+    l1, p1, r1, b1, g1 = out[False]; l2, p2, r2, b2, g2 = out[True]
     assert l2[-1] < 0.7 * l2[0], l2
     torch.testing.assert_close(torch.tensor(l2), torch.tensor(l1), rtol=5e-2, atol=1e-5)
     # same batch on every rank => averaged gradient == local gradient, so the trajectories coincide up to
     # floating-point summation order (atomics, ring reduction)
-    assert (r2 - r1).abs().max().item() < 5e-3 * r1.abs().max().item()
+    # (fp16 wire format for the table gradients: their rounding feeds back into the MLP through the features)
+    tol = 5e-2 if wire16 else 5e-3
+    assert (r2 - r1).abs().max().item() < tol * r1.abs().max().item(), (r2 - r1).abs().max().item() / r1.abs().max().item()
     # Adam turns near-zero (rounding-noise) table gradients into +-lr steps, so single entries may differ; compare the
     # density-MLP weights entry-wise and the hash table in the L2 sense
     assert (p2[:3072] - p1[:3072]).abs().max().item() < 5e-2 * p1[:3072].abs().max().item()
     assert ((p2 - p1).norm() / p1.norm()).item() < 0.25, ((p2 - p1).norm() / p1.norm()).item()
     # every rank holds the same gathered master parameters and the same bitfield
-    for t in (p2, r2, b2.float()):
+    for t in (p2, r2, b2.float(), g2):
         ref = t.clone(); dist.broadcast(ref, src=0)
         assert torch.equal(ref, t), "ranks disagree"
+    # the shared-out occupancy update sees the same field as the single-GPU one: the density grids agree up to the
+    # random jitter inside a cell and the 0.95 decay of cells that only one of the two runs re-sampled (this barely
+    # trained field sits right at its own mean, so the thresholded bits themselves are a coin flip)
+    seen = (g1 >= 0) & (g2 >= 0)
+    agree = ((g1 - g2).abs()[seen].mean() / g1[seen].abs().mean()).item()          # mean deviation / mean density
+    assert agree < 0.25 and (g2 > 0).any() and b2.any(), (agree, (g1 - g2).abs()[seen].max().item(), g1[seen].max().item())
     if rank == 0:
-        print("dist_nccl_check ok (comm %s): world" % os.environ.get("B2N_COMM", "p2p"), dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1])
+        print("dist_nccl_check ok (comm %s): world" % os.environ.get("B2N_COMM", "p2p"), dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
+              "mean density-grid deviation %.4f" % agree)
     dist.barrier(); dist.destroy_process_group()
 
 
