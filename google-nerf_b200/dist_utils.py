@@ -51,43 +51,59 @@ def broadcast_model_(model, src=0, group=None):
     return model
 
 
+_PARTITIONS = {}
+
+
+def _partition(n, world, rank, tile, device):
+    """Index bookkeeping of a sharded render, cached per shape: which rays this rank renders, how many every rank
+    renders, and the permutation that puts the gathered (rank-major, padded) rows back in ray order."""
+    key = (n, world, rank, tile, str(device))
+    part = _PARTITIONS.get(key)
+    if part is None:
+        idx = torch.arange(n, device=device)
+        if tile is None:
+            bounds = [shard_bounds(n, world, r) for r in range(world)]
+            owners = torch.empty(n, dtype=torch.int64, device=device)
+            for r, (a, b) in enumerate(bounds):
+                owners[a:b] = r
+        else:
+            owners = (idx // int(tile)) % world
+        sels = [(owners == r).nonzero(as_tuple=True)[0] for r in range(world)]
+        counts = [int(x.numel()) for x in sels]
+        longest = max(counts)
+        # row j of rank r's padded part lands at ray sels[r][j]; padding rows are dropped
+        src = torch.cat([r * longest + torch.arange(c, device=device) for r, c in enumerate(counts)])
+        dst = torch.cat(sels)
+        part = dict(sel=sels[rank], counts=counts, longest=longest, src=src, dst=dst)
+        if len(_PARTITIONS) > 16:
+            _PARTITIONS.clear()
+        _PARTITIONS[key] = part
+    return part
+
+
 def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
-    """Tile-sharded test-time render; the (rgb, depth, opacity) parts are all-gathered and put back in ray order.
-    `render_fn(rays_o, rays_d, **kwargs)` -> dict with those three keys (+ total_samples).
+    """Tile-sharded test-time render; the (rgb, depth, opacity) parts are gathered with ONE collective and put back in
+    ray order.  `render_fn(rays_o, rays_d, **kwargs)` -> dict with those three keys (+ total_samples).
 
     tile=None: rank r renders the contiguous band [start_r, end_r).  tile=T: rays are cut into tiles of T consecutive
     rays dealt round-robin to the ranks (tile t -> rank t % world) -- empty-space rays are cheap, so contiguous bands of
-    an image are badly balanced; T = one image row keeps each rank's rays coherent."""
+    an image are badly balanced; T = one image row keeps each rank's rays coherent.  The index bookkeeping
+    is cached per (n_rays, world, tile), so repeated frames cost no host synchronisation here."""
     rank, world = world_info(group)
     n = rays_o.shape[0]
-    if tile is None:
-        owners = None
-        s, e = shard_bounds(n, world, rank)
-        sel = slice(s, e)
-        counts = [b - a for a, b in (shard_bounds(n, world, r) for r in range(world))]
-    else:
-        owners = (torch.arange(n, device=rays_o.device) // int(tile)) % world
-        sel = (owners == rank).nonzero(as_tuple=True)[0]
-        counts = [int(c) for c in torch.bincount(owners, minlength=world).tolist()]
-    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **kwargs)
     if world == 1:
-        return res
-    out = {}
-    longest = max(counts)
-    for k in ("rgb", "depth", "opacity"):
-        v = res[k].contiguous()
-        if v.shape[0] < longest:                              # all_gather needs equal shapes: pad the short parts
-            v = torch.cat([v, v.new_zeros((longest - v.shape[0],) + tuple(v.shape[1:]))], 0)
-        parts = [torch.empty_like(v) for _ in counts]
-        dist.all_gather(parts, v, group=group)
-        if owners is None:
-            out[k] = torch.cat([p[:c] for p, c in zip(parts, counts)], 0)
-        else:
-            full = v.new_empty((n,) + tuple(v.shape[1:]))
-            for r, (p, c) in enumerate(zip(parts, counts)):
-                full[owners == r] = p[:c]
-            out[k] = full
-    ts = torch.as_tensor(res["total_samples"], device=out["rgb"].device, dtype=torch.int64).reshape(1).clone()
+        return render_fn(rays_o, rays_d, **kwargs)
+    part = _partition(n, world, rank, tile, rays_o.device)
+    sel = part["sel"]
+    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **kwargs)
+    # one (longest, 5) fp32 block per rank: rgb | depth | opacity
+    mine = torch.zeros(part["longest"], 5, dtype=torch.float32, device=rays_o.device)
+    c = sel.numel()
+    mine[:c, 0:3] = res["rgb"]; mine[:c, 3] = res["depth"]; mine[:c, 4] = res["opacity"]
+    gathered = torch.empty(world * part["longest"], 5, dtype=torch.float32, device=rays_o.device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    full = torch.empty(n, 5, dtype=torch.float32, device=rays_o.device)
+    full[part["dst"]] = gathered[part["src"]]
+    ts = torch.as_tensor(res["total_samples"], device=rays_o.device, dtype=torch.int64).reshape(1).clone()
     dist.all_reduce(ts, group=group)
-    out["total_samples"] = int(ts.item())
-    return out
+    return {"rgb": full[:, 0:3], "depth": full[:, 3], "opacity": full[:, 4], "total_samples": int(ts.item())}

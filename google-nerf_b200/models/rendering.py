@@ -16,8 +16,12 @@ def render(model, rays_o, rays_d, **kwargs):
     test-time rendering (rendering.py:26-39)."""
     rays_o = rays_o.contiguous(); rays_d = rays_d.contiguous()
     _, hits_t, _ = RayAABBIntersector.apply(rays_o, rays_d, model.center, model.half_size, 1)
-    near = hits_t[:, 0, 0]
-    hits_t[(near >= 0) & (near < NEAR_DISTANCE), 0, 0] = NEAR_DISTANCE
+    if hits_t.is_cuda:       # hits_t[(t1 >= 0) & (t1 < NEAR), 0, 0] = NEAR (rendering.py:29) without the boolean-mask sync
+        from .. import _lib as L
+        L.call("b2n_clamp_near", L.ptr(hits_t), hits_t.shape[0], NEAR_DISTANCE)
+    else:
+        near = hits_t[:, 0, 0]
+        hits_t[(near >= 0) & (near < NEAR_DISTANCE), 0, 0] = NEAR_DISTANCE
 
     fn = _render_rays_test if kwargs.get("test_time", False) else _render_rays_train
     results = fn(model, rays_o, rays_d, hits_t, **kwargs)
@@ -89,7 +93,7 @@ class _DeviceLoop:
     graph and replayed; the host looks at the live-ray count once per ROUNDS_PER_SYNC rounds instead of twice per
     round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
     per-ray arithmetic as the host loop, so the images are identical."""
-    ROUNDS_PER_SYNC = 6
+    ROUNDS_PER_SYNC = 8
 
     @classmethod
     def get(cls, model, n_rays, esf, T_threshold):
