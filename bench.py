@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--comm", default=None, choices=["p2p", "nccl"],
                     help="N > 1: gradient/parameter exchange (default p2p = fused kernel over NVLink peer memory)")
-    ap.add_argument("--cpu-rays", type=int, default=4096, help="rays per step of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-rays", type=int, default=2048, help="rays per step of the bounded CPU-baseline sample")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--profile", action="store_true", help="print the per-kernel event timing table to stderr")
     return ap.parse_args()
@@ -72,10 +72,11 @@ def cpu_baseline(n_rays, steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    # exactly K timed steps after W warm-up steps; each step is a bounded sample of the workload (a CPU step over 1024
-    # rays takes ~0.6 s on 16 cores), shrunk further when K + W is large so that the arm ends within a few minutes
+    # exactly K timed steps after W warm-up steps; each step is a bounded sample of the workload (a CPU step over 2048
+    # rays takes ~0.65 s on 16 cores -- the same sample size as the main arm's cpu_baseline), shrunk further when K + W
+    # is large so that the arm ends within a few minutes
     steps, warmup = max(1, args.steps), max(0, args.warmup)
-    n_rays = 1024 if steps + warmup <= 300 else max(128, int(1024 * 300 / (steps + warmup)) // 128 * 128)
+    n_rays = args.cpu_rays if steps + warmup <= 300 else max(128, int(args.cpu_rays * 300 / (steps + warmup)) // 128 * 128)
     cb, sec = cpu_baseline(n_rays, steps, warmup)
     line = dict(impl="reference", metric="train_rays_per_s", value=cb["value"], unit="rays/s", n_gpus=args.gpus,
                 steps=steps, warmup=warmup, ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak",
@@ -419,7 +420,7 @@ def main():
                         "not the tensor pipe (ncu sm__pipe_tensor_cycles_active in profiles/)")
         cb = None
         if not args.skip_cpu:
-            cb, _ = cpu_baseline(args.cpu_rays, 4, 1)          # ~10 s of CPU work on 16 host cores
+            cb, _ = cpu_baseline(args.cpu_rays, 12, 1)         # ~10 s of CPU work on 16 host cores
         rays = N_RAYS * world * args.steps
         n_updates = sum(1 for s in range(args.steps) if s % tr.S == 0)
         line = dict(metric="train_rays_per_s", value=rays / (ms * 1e-3), unit="rays/s", n_gpus=world, steps=args.steps,
