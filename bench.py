@@ -381,10 +381,26 @@ def main():
             a.record(); LL.call("b2n_membench_read", LL.ptr(buf), nbytes, iters, LL.ptr(sink)); b.record(); torch.cuda.synchronize()
             return nbytes * iters / (a.elapsed_time(b) * 1e-3) / 1e9
         l2_gbs, hbm_read_gbs = membench(32 << 20, 200), membench(2 << 30, 4)
+
+        def gatherbench(nbytes, iters):
+            import ctypes
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=dev); sink = torch.zeros(4, dtype=torch.int32, device=dev)
+            nl = ctypes.c_int64(0)
+            LL.call("b2n_membench_gather", LL.ptr(buf), nbytes, 4, LL.ptr(sink), ctypes.byref(nl))
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); LL.call("b2n_membench_gather", LL.ptr(buf), nbytes, iters, LL.ptr(sink), ctypes.byref(nl)); b.record()
+            torch.cuda.synchronize()
+            return nl.value / (a.elapsed_time(b) * 1e-3)                       # sector requests per second
+        l2_gather_rate = gatherbench(16 << 20, 64)           # 16 MiB: about the fp16 table (21.8 MiB), L2-resident
         t_fw, t_bw = table.get("b2n_hashgrid_fw", 0) * 1e-3, table.get("b2n_hashgrid_bw", 0) * 1e-3
         hash_encode = dict(fw_gbs=588 * samples / t_fw / 1e9 if t_fw else None, bw_gbs=1100 * samples / t_bw / 1e9 if t_bw else None,
                            l2_read_gbs_measured=l2_gbs, hbm_read_gbs_measured=hbm_read_gbs,
                            fw_frac_of_l2=(588 * samples / t_fw / 1e9) / l2_gbs if t_fw else None,
+                           # what actually bounds the gather: 32-byte sector REQUESTS to L2.  58.2 per sample = 128
+                           # gathers x (1 - 0.545 L1 hit rate) from the committed ncu capture (profiles/r01d_ncu_summary.md)
+                           l2_gather_gsectors_per_s_measured=l2_gather_rate / 1e9,
+                           fw_gsectors_per_s=58.2 * samples / t_fw / 1e9 if t_fw else None,
+                           fw_frac_of_l2_gather=(58.2 * samples / t_fw) / l2_gather_rate if t_fw else None,
                            note="algorithmic bytes: 588 B/sample fw, 1100 B/sample bw (SURVEY 8d); table 21.8 MiB fp16, L2-resident")
         t_m = (table.get("b2n_raymarching_train_count", 0) + table.get("b2n_raymarching_train_write", 0)) * 1e-3
         marcher = dict(samples_per_s=samples / t_m if t_m else None, rays_per_s=N_RAYS / t_m if t_m else None,

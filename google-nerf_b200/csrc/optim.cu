@@ -245,6 +245,37 @@ __global__ void __launch_bounds__(256) membench_read_kernel(const uint4 *__restr
     if (acc == 0x9e3779b9u) sink[0] = acc;   // keeps the loads alive
 }
 
+// Random-gather probe: every thread issues independent 4-byte loads at pseudo-random word offsets of a buffer (an LCG
+// per thread; addresses do not depend on loaded data, 8 loads in flight).  With a buffer that fits L2 but not L1 every
+// load is one 32-byte sector request to L2: this measures the L2 REQUEST rate, which is what bounds the hash-grid
+// gather (4 useful bytes per sector), rather than the byte bandwidth of streaming loads.
+__global__ void __launch_bounds__(256) membench_gather_kernel(const uint32_t *__restrict__ buf, uint32_t word_mask, int iters,
+                                                              uint32_t *__restrict__ sink) {
+    uint32_t s = ((uint32_t)blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        uint32_t v[8];
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            s = s * 1664525u + 1013904223u;
+            v[k] = __ldg(buf + ((s >> 7) & word_mask));
+        }
+        #pragma unroll
+        for (int k = 0; k < 8; ++k) acc ^= v[k];
+    }
+    if (acc == 0x9e3779b9u) sink[0] = acc;   // keeps the loads alive
+}
+
+extern "C" int b2n_membench_gather(const void *buf, int64_t bytes, int iters, void *sink, int64_t *n_loads, void *stream) {
+    B2N_CHECK_ARG(bytes >= 4096 && (bytes & (bytes - 1)) == 0 && iters >= 1, "bytes must be a power of two >= 4096");
+    const unsigned grid = B2N_SMS * 8;
+    membench_gather_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint32_t *)buf, (uint32_t)(bytes / 4 - 1), iters,
+                                                                   (uint32_t *)sink);
+    B2N_LAUNCH_CHECK();
+    if (n_loads != nullptr) *n_loads = (int64_t)grid * 256 * 8 * iters;
+    return 0;
+}
+
 extern "C" int b2n_membench_read(const void *buf, int64_t bytes, int iters, void *sink, void *stream) {
     B2N_CHECK_ARG(bytes >= 16 && iters >= 1 && ((uintptr_t)buf & 15) == 0, "bad membench arguments");
     membench_read_kernel<<<B2N_SMS * 8, 256, 0, (cudaStream_t)stream>>>((const uint4 *)buf, bytes / 16, iters,

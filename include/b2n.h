@@ -290,6 +290,9 @@ B2N_API int b2n_grid_ema(float *density_grid, const float *tmp, int64_t n_cells,
 B2N_API int b2n_grid_threshold(const float *density_grid, int64_t n_cells, float density_threshold,
                        double *workspace, float *stats_dev, void *stream);
 
+/* Random 4-byte gathers over a power-of-two buffer (L2 request-rate probe for bench.py: the roofline of the hash-grid
+ * gather).  *n_loads (host, may be NULL) receives the number of loads the launch issues. */
+B2N_API int b2n_membench_gather(const void *buf, int64_t bytes, int iters, void *sink, int64_t *n_loads, void *stream);
 /* Read-bandwidth probe (bench.py): streams `bytes` of buf `iters` times with ld.global.cg; a buffer that fits the
  * L2 measures L2 bandwidth, a larger one HBM bandwidth.  sink: 4 bytes, never written in practice. */
 B2N_API int b2n_membench_read(const void *buf, int64_t bytes, int iters, void *sink, void *stream);
