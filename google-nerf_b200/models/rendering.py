@@ -89,9 +89,8 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 class _DeviceLoop:
     """The loop of rendering.py:64-102 driven from the device.  One round = schedule -> march -> hash-grid gather ->
     fused field MLP -> composite (+ compaction of the alive list); ray counts, samples per ray and the alive list
-    stay on the GPU, every launch has a fixed grid, so two rounds (the alive list ping-pongs) are captured as ONE CUDA
-    graph and replayed; the host looks at the live-ray count once per ROUNDS_PER_SYNC rounds instead of twice per
-    round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
+    stay on the GPU, every launch has a fixed grid, so ROUNDS_PER_SYNC rounds (the alive list ping-pongs) are captured
+    as ONE CUDA graph and replayed; the host looks at the live-ray count once per replay instead of twice per round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
     per-ray arithmetic as the host loop, so the images are identical."""
     ROUNDS_PER_SYNC = 8
 
@@ -142,8 +141,9 @@ class _DeviceLoop:
         call("b2n_composite_test_fw_dev", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.alive[cur]),
              P(self.alive[1 - cur]), self.T, P(self.n_eff), n, P(self.ctl), P(self.opacity), P(self.depth), P(self.rgb))
 
-    def _two_rounds(self):
-        self._round(0); self._round(1)
+    def _rounds(self):
+        for k in range(self.ROUNDS_PER_SYNC):
+            self._round(k & 1)
 
     def run(self, rays_o, rays_d, hits):
         self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d); self.hits.copy_(hits)
@@ -152,16 +152,15 @@ class _DeviceLoop:
             side = torch.cuda.Stream(device=rays_o.device)   # eager warm-up, then capture
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                self._two_rounds()
+                self._rounds()
             torch.cuda.current_stream().wait_stream(side)
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._two_rounds()
+                self._rounds()
             self.hits.copy_(hits)                            # the warm-up rounds advanced the rays
         self._reset()
         while True:
-            for _ in range(self.ROUNDS_PER_SYNC // 2):
-                self.graph.replay()
+            self.graph.replay()
             self.ctl_host.copy_(self.ctl, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             c = self.ctl_host

@@ -63,6 +63,9 @@ def full():
         seen = set()
         for r in rows[2:]:
             name = short(r[kn])
+            if "march_test" in name or "composite_test" in name:       # render rounds differ a lot: keep every capture
+                gi = hdr.index("launch__grid_size") if "launch__grid_size" in hdr else None
+                name = f"{name} #{sum(1 for x in seen if x.startswith(name))}"
             if name in seen:
                 continue
             seen.add(name)
@@ -82,6 +85,7 @@ def full():
 
 
 if __name__ == "__main__":
-    launch_list()
+    if os.path.exists(os.path.join(OUT, f"{R}_launches.csv")):      # the render capture has no launch list
+        launch_list()
     full()
     print("written", R)
