@@ -92,7 +92,8 @@ class _DeviceLoop:
     stay on the GPU, every launch has a fixed grid, so ROUNDS_PER_SYNC rounds (the alive list ping-pongs) are captured
     as ONE CUDA graph and replayed; the host looks at the live-ray count once per replay instead of twice per round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
     per-ray arithmetic as the host loop, so the images are identical."""
-    ROUNDS_PER_SYNC = 8
+    ROUNDS_PER_SYNC = 8                                  # host looks at the live-ray count this often
+    ROUNDS_PER_GRAPH = int(__import__('os').environ.get('B2N_RENDER_RPG', 8))   # rounds captured per graph (even)
 
     @classmethod
     def get(cls, model, n_rays, esf, T_threshold):
@@ -142,7 +143,7 @@ class _DeviceLoop:
              P(self.alive[1 - cur]), self.T, P(self.n_eff), n, P(self.ctl), P(self.opacity), P(self.depth), P(self.rgb))
 
     def _rounds(self):
-        for k in range(self.ROUNDS_PER_SYNC):
+        for k in range(self.ROUNDS_PER_GRAPH):
             self._round(k & 1)
 
     def run(self, rays_o, rays_d, hits):
@@ -160,7 +161,8 @@ class _DeviceLoop:
             self.hits.copy_(hits)                            # the warm-up rounds advanced the rays
         self._reset()
         while True:
-            self.graph.replay()
+            for _ in range(self.ROUNDS_PER_SYNC // self.ROUNDS_PER_GRAPH):
+                self.graph.replay()
             self.ctl_host.copy_(self.ctl, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             c = self.ctl_host

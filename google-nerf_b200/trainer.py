@@ -1,21 +1,23 @@
 """NGPTrainer: one training step of ngp_pl/train.py:144-170 (render -> NeRFLoss -> backward -> FusedAdam,
 density-grid update every 16 steps) run directly on the libb2n kernels, without autograd, on pre-allocated
-buffers and with every count kept on the device, so the whole step is replayed as one CUDA graph.
+buffers and with every count kept on the device, so the whole step is replayed as CUDA graphs.
 
 Pipelining: ray generation + AABB + marching of batch k+1 depend only on the occupancy bitfield, not on the
-weights, and the marcher is instruction-issue bound while the field backward is latency bound.  When the caller
-hands over the next batch (the reference's DataLoader always has it, train.py:126-131) the graph of step k has two
-branches: [field forward .. Adam on batch k] and [march batch k+1 into the other sample set].  Steps that are
-followed by a density-grid update are not pre-marched, so every batch is marched against exactly the bitfield
-the sequential reference loop would use.
+weights, and the marcher is instruction-issue bound while the field kernels are latency / bandwidth bound.  When the
+caller hands over the next batch (the reference's DataLoader always has it, train.py:126-131) its copies and its march
+graph run on a side stream underneath the training graph of batch k [field forward .. Adam]; the main stream joins at
+the end of the step.  Steps that are followed by a density-grid update are not pre-marched, so every batch is marched
+against exactly the bitfield the sequential reference loop would use.
 
 Data-parallel: one process per GPU, each with its own ray batch (like PL DDP at
-train.py:262-263); gradients of the two flat parameters are summed with NCCL all-reduce and averaged, and the
-occupancy grid is max-reduced after every update so that all ranks march the same bitfield.
+train.py:262-263).  The flat parameter vector is sharded over the ranks (fp32 master + Adam moments); gradients are
+summed, Adam runs on the owner's shard and the fp16 working copy is re-distributed -- by ONE kernel over NVLink peer
+memory bracketed by flag barriers (comm="p2p", peer.py / csrc/peer.cu) or by NCCL reduce-scatter / all-gather
+(comm="nccl").  The sampled cells of the occupancy update are shared out over the ranks and max-reduced, so all ranks
+march the same bitfield.
 """
-import struct
-
 import os
+import struct
 
 import torch
 import torch.distributed as dist
@@ -85,9 +87,9 @@ class NGPTrainer:
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
         n_xyz, n_rgb = xe.params.numel(), rn.params.numel()
         # All trainable parameters live in ONE flat vector [xyz_encoder (MLP + hash table) | rgb_net | pad]: one Adam
-        # launch, and for world > 1 one collective each way.  Sharded optimiser (world > 1): the vector is padded to
-        # world * shard; every rank reduce-scatters the gradient, runs Adam on ITS shard of the fp32 master / moments
-        # only, and the fp16 working copy is all-gathered.  Less traffic than an all-reduce (fp32 RS + fp16 AG) and
+        # launch, and for world > 1 one exchange.  Sharded optimiser (world > 1): the vector is padded to world * shard;
+        # the gradients are summed shard-wise, every rank runs Adam on ITS shard of the fp32 master / moments only, and
+        # the fp16 working copy goes back to all ranks.  Less traffic than an all-reduce (fp32 one way, fp16 back) and
         # Adam's HBM sweep shrinks by the world size.  The model's Parameters are views of the master buffer.
         assert n_xyz % 8 == 0
         n_all = n_xyz + n_rgb
@@ -137,7 +139,7 @@ class NGPTrainer:
         self.m, self.v = z(self.p_shard), z(self.p_shard)
         self.h_xyz, self.h_rgb = self.h_all[:n_xyz], self.h_all[n_xyz:n_all]
         self.h_shard = self.h_all[lo:lo + self.shard]
-        # True captures the NCCL collectives into the training graph (world > 1).  Measured: 22 us/step faster at 2
+        # comm == "nccl" only: True captures the collectives into the training graph.  Measured: 22 us/step faster at 2
         # GPUs, but communicator teardown after captured collectives hung on this stack, so the default keeps them
         # eager between two graphs.
         self.comm_in_graph = comm_in_graph

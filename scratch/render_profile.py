@@ -28,8 +28,13 @@ with torch.no_grad():
     st = model._device_loop
     print("rounds", int(st.ctl_host[5]), "samples", res["total_samples"], "alive left", int(st.ctl_host[4]))
     import time
-    t0 = time.perf_counter(); res = render(model, ro, rd, test_time=True, T_threshold=1e-2); torch.cuda.synchronize()
-    print("frame ms", (time.perf_counter() - t0) * 1e3)
+    ts = []
+    for _ in range(6):
+        t0 = time.perf_counter(); res = render(model, ro, rd, test_time=True, T_threshold=1e-2); torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t0) * 1e3)
+    print("frame ms", [round(t, 3) for t in ts])
+    if os.environ.get("NOPROF"):
+        sys.exit(0)
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         res = render(model, ro, rd, test_time=True, T_threshold=1e-2)
         torch.cuda.synchronize()
