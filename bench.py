@@ -329,6 +329,20 @@ def main():
                        note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 as in "
                             "test.ipynb; N > 1: row tiles dealt round-robin to the ranks, max over ranks, all-gather of "
                             "rgb/depth/opacity included")
+    # ---- image quality of what was just trained (sanity of the whole path, not a timed number): PSNR of a training view
+    # and of a held-out view against the analytic ground truth (T_threshold 1e-4 like validation, train.py:178-183)
+    quality = None
+    if rank == 0:
+        from google_nerf_b200.metrics import psnr
+        with torch.no_grad():
+            novel = syn.hemisphere_poses(4, seed=12345).to(dev)
+            vals = []
+            for pose in (pp[0], novel[0], novel[1]):
+                ro, rd = syn.get_rays(dd, pose)
+                img = render(model, ro, rd, test_time=True)["rgb"]
+                vals.append(float(psnr(img, syn.shade(ro, rd, SCALE))))
+        quality = dict(psnr_train_view=vals[0], psnr_heldout_views=vals[1:], train_steps=tr.step_count,
+                       note="800x800 frames against the analytic scene's closed-form shading")
     if rank == 0:
         # ---- per-kernel table + roofline of the dominant kernel (eager replays of the same step)
         tr.use_graph = False
@@ -451,7 +465,7 @@ def main():
                     e2e=dict(value=rays / (ms_e2e * 1e-3), unit="rays/s", h2d_bytes_per_step=N_RAYS * (8 + 8 + 12),
                              d2h_bytes_per_step=4, ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
                     gpu_launches=launches_per_step * args.steps + 12 * n_updates,
-                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, compositing=compositing, mlp=mlp, render=render_info, grid_update_ms=grid_update_ms,
+                    roofline=roofline, cpu_baseline=cb, hash_encode=hash_encode, marcher=marcher, compositing=compositing, mlp=mlp, render=render_info, quality=quality, grid_update_ms=grid_update_ms,
                     kernels_us={k: round(v * 1e3, 1) for k, v in table.items()})
         print(json.dumps(line), flush=True)
     if world > 1:
