@@ -25,12 +25,17 @@ extern "C" int b2n_peer_alloc(int64_t bytes, void **ptr, void *handle64) {
     B2N_CHECK_ARG(bytes > 0 && ptr != nullptr && handle64 != nullptr, "bad arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
-    if (e != cudaSuccess) { b2n_set_error("b2n_peer_alloc: cudaMalloc: %s", cudaGetErrorString(e)); return 2; }
+    if (e != cudaSuccess) {
+        b2n_set_error("b2n_peer_alloc: cudaMalloc: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return 2;
+    }
     e = cudaMemset(*ptr, 0, (size_t)bytes);
     if (e == cudaSuccess) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, *ptr);
     if (e != cudaSuccess) {
         b2n_set_error("b2n_peer_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
         cudaFree(*ptr); *ptr = nullptr;
+        (void)cudaGetLastError();
         return 2;
     }
     return 0;
@@ -41,21 +46,25 @@ extern "C" int b2n_peer_open(const void *handle64, void **ptr) {
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, sizeof(h));
     const cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) { b2n_set_error("b2n_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e)); return 2; }
+    if (e != cudaSuccess) {
+        b2n_set_error("b2n_peer_open: cudaIpcOpenMemHandle: %s", cudaGetErrorString(e));
+        (void)cudaGetLastError();                           // reported through the status; do not leave it pending
+        return 2;
+    }
     return 0;
 }
 
 extern "C" int b2n_peer_close(void *ptr) {
     if (ptr == nullptr) return 0;
     const cudaError_t e = cudaIpcCloseMemHandle(ptr);
-    if (e != cudaSuccess) { b2n_set_error("b2n_peer_close: %s", cudaGetErrorString(e)); return 2; }
+    if (e != cudaSuccess) { b2n_set_error("b2n_peer_close: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return 2; }
     return 0;
 }
 
 extern "C" int b2n_peer_free(void *ptr) {
     if (ptr == nullptr) return 0;
     const cudaError_t e = cudaFree(ptr);
-    if (e != cudaSuccess) { b2n_set_error("b2n_peer_free: %s", cudaGetErrorString(e)); return 2; }
+    if (e != cudaSuccess) { b2n_set_error("b2n_peer_free: %s", cudaGetErrorString(e)); (void)cudaGetLastError(); return 2; }
     return 0;
 }
 
