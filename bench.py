@@ -144,20 +144,21 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- kernel table
 # algorithmic bytes / flops per unit (DESIGN.md "Cost model")
-def kernel_costs(n_rays, n_samples, n_params_xyz, n_params_rgb):
-    s, r = n_samples, n_rays
+def kernel_costs(n_rays, n_samples, n_alive, n_params_xyz, n_params_rgb):
+    # the two backward kernels run over the alive samples only (those composited before their ray's early stop)
+    s, r, a = n_samples, n_rays, n_alive
     return {
         "b2n_ray_aabb_intersect": ("hbm", 32 * r),
         "b2n_raymarching_train_count": ("hbm", 36 * r + 24 * r),
         "b2n_raymarching_train_write": ("hbm", 60 * r + 32 * s),
         "b2n_hashgrid_fw": ("hbm", 588 * s),
-        "b2n_hashgrid_bw": ("hbm", 1100 * s),
+        "b2n_hashgrid_bw": ("hbm", 1100 * a),
         "b2n_mlp_fw": ("tensor", None),
         "b2n_mlp_bw": ("tensor", None),
         # fused tcgen05 field MLPs: 20.5 / 41 kFLOP per sample are ~1% of the tensor roofline; what bounds them is
         # the activation traffic (enc 64 + dirs 12 + sigma 4 + rgb 12 + saved hid_s 128, h 32, hid_r 256 B/sample)
         "b2n_field_mlp_fw": ("hbm", 508 * s),
-        "b2n_field_mlp_bw": ("hbm", 584 * s),
+        "b2n_field_mlp_bw": ("hbm", 584 * a),
         "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_sh4_fw": ("hbm", 44 * s),
         "b2n_composite_loss_fwbw": ("hbm", 40 * s + 76 * r),
@@ -352,7 +353,9 @@ def main():
             os.path.join(ROOT, "MEASURED_PEAKS.json")) else None
         hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
         tf_peak = peaks["bf16_tflops_sustained"] if peaks else 1400.0
-        costs = kernel_costs(N_RAYS, samples, tr.p_xyz.numel(), tr.p_rgb.numel())
+        samples = int(tr.sets[tr.cur].counter[0].item())      # sample / alive-sample counts of the profiled batch
+        alive = int(tr.alive_cnt.item())
+        costs = kernel_costs(N_RAYS, samples, alive, tr.p_xyz.numel(), tr.p_rgb.numel())
         # the dominant kernel of the step's critical path (ray generation / AABB / marching of the NEXT batch run on
         # the side stream underneath it and are reported separately in `marcher`)
         side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near", "b2n_rays_from_indices")
@@ -377,7 +380,8 @@ def main():
         ncu_traffic_per_sample = {"b2n_field_mlp_bw": 629.0, "b2n_field_mlp_fw": 441.0, "b2n_hashgrid_fw": 55.0,
                                   "b2n_hashgrid_bw": 156.0, "b2n_composite_loss_fwbw": 27.0}
         traffic = ncu_traffic_per_sample.get(base)
-        traffic = traffic * samples if traffic else (29.07 * tr.shard if base == "b2n_adam_step" else None)
+        traffic = traffic * (alive if base in ("b2n_field_mlp_bw", "b2n_hashgrid_bw") else samples) if traffic else (
+            29.07 * tr.shard if base == "b2n_adam_step" else None)
         roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
                         traffic=traffic,
                         peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
@@ -407,7 +411,7 @@ def main():
             return nl.value / (a.elapsed_time(b) * 1e-3)                       # sector requests per second
         l2_gather_rate = gatherbench(16 << 20, 64)           # 16 MiB: about the fp16 table (21.8 MiB), L2-resident
         t_fw, t_bw = table.get("b2n_hashgrid_fw", 0) * 1e-3, table.get("b2n_hashgrid_bw", 0) * 1e-3
-        hash_encode = dict(fw_gbs=588 * samples / t_fw / 1e9 if t_fw else None, bw_gbs=1100 * samples / t_bw / 1e9 if t_bw else None,
+        hash_encode = dict(fw_gbs=588 * samples / t_fw / 1e9 if t_fw else None, bw_gbs=1100 * alive / t_bw / 1e9 if t_bw else None,
                            l2_read_gbs_measured=l2_gbs, hbm_read_gbs_measured=hbm_read_gbs,
                            fw_frac_of_l2=(588 * samples / t_fw / 1e9) / l2_gbs if t_fw else None,
                            # what actually bounds the gather: 32-byte sector REQUESTS to L2.  58.2 per sample = 128
@@ -444,7 +448,7 @@ def main():
                            note="fused fw + loss + bw launch; algorithmic 40 B/sample + 76 B/ray; latency-bound at 8192 rays")
         t_f, t_b = table.get("b2n_field_mlp_fw", 0) * 1e-3, table.get("b2n_field_mlp_bw", 0) * 1e-3
         mlp = dict(fw_tflops=20480 * samples / t_f / 1e12 if t_f else None,
-                   bw_tflops=40960 * samples / t_b / 1e12 if t_b else None, tensor_peak_tflops=tf_peak,
+                   bw_tflops=40960 * alive / t_b / 1e12 if t_b else None, tensor_peak_tflops=tf_peak,
                    fw_frac_of_tensor_peak=20480 * samples / t_f / 1e12 / tf_peak if t_f else None,
                    note="tcgen05 kind::f16; the MLPs are 64 wide: activation traffic and dependency latency bound them, "
                         "not the tensor pipe (ncu sm__pipe_tensor_cycles_active in profiles/)")
@@ -457,7 +461,7 @@ def main():
                     warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f16", data="synthetic (analytic 3-sphere+box scene, random-init weights "
                     f"trained {args.pretrain} untimed steps to steady-state occupancy)",
-                    config=dict(workload=WORKLOAD, rays_per_gpu=N_RAYS, samples_per_step=samples,
+                    config=dict(workload=WORKLOAD, rays_per_gpu=N_RAYS, samples_per_step=samples, alive_samples_per_step=alive,
                                 samples_per_ray=samples / N_RAYS, cuda_graph=not args.no_graph,
                                 l2="per-step working set (206 MB optimiser state + sample buffers) exceeds the 126 MB "
                                    "L2; no explicit flush", parallelism=f"dp{world}", comm=tr.comm),
