@@ -41,28 +41,64 @@ class PeerBlock:
             self.layout[name] = (off, dtype, numel)
             off += -(-nbytes // _ALIGN) * _ALIGN
         self.nbytes = off
+        # Every step that can fail locally (allocation, IPC export, mapping a peer) is followed by a collective vote, so
+        # that either all ranks end up with a working block or all of them raise -- never a rank left waiting.
+        self.local, self.base, err = None, [], None
         with torch.cuda.device(device):
             ptr, handle = C.c_void_p(), C.create_string_buffer(64)
-            L.call_nostream("b2n_peer_alloc", self.nbytes, C.byref(ptr), handle)
-            self.local = ptr.value
+            try:
+                L.call_nostream("b2n_peer_alloc", self.nbytes, C.byref(ptr), handle)
+                self.local = ptr.value
+            except RuntimeError as e:
+                err = e
             handles = [None] * self.world
-            dist.all_gather_object(handles, (handle.raw, self.nbytes), group=group)
-            self.base = []
+            dist.all_gather_object(handles, (handle.raw, self.nbytes) if err is None else None, group=group)
+            if any(h is None for h in handles):
+                self._abort(None)
+                raise RuntimeError(f"peer memory unavailable: allocation / IPC export failed on a rank ({err})")
             for r, (h, nb) in enumerate(handles):
+                if err is not None:
+                    break
                 if nb != self.nbytes:
-                    raise RuntimeError("peer blocks differ in size across ranks")
-                if r == self.rank:
+                    err = RuntimeError("peer blocks differ in size across ranks")
+                elif r == self.rank:
                     self.base.append(self.local)
                 else:
                     q = C.c_void_p()
-                    L.call_nostream("b2n_peer_open", C.create_string_buffer(h, 64), C.byref(q))
-                    self.base.append(q.value)
+                    try:
+                        L.call_nostream("b2n_peer_open", C.create_string_buffer(h, 64), C.byref(q))
+                        self.base.append(q.value)
+                    except RuntimeError as e:
+                        err = e
+            ok = torch.tensor([0 if err is not None else 1], dtype=torch.int32, device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if int(ok.item()) == 0:
+                self._abort(group)
+                raise RuntimeError(f"peer memory unavailable: mapping a peer's block failed on a rank ({err})")
         self._raw = torch.as_tensor(_Raw(self.local, self.nbytes), device=device)      # uint8 view of the local block
         self.state = torch.zeros(2, dtype=torch.int32, device=device)                  # {epoch, sticky error}
         self._flags = (C.c_void_p * self.world)(*self.base)
         self._tables = {}
         self.closed = False
         dist.barrier(group=group)                                                      # every mapping exists
+
+    def _abort(self, group):
+        """Undo a partly built block (all ranks call it together when `group` is given)."""
+        with torch.cuda.device(self.device):
+            for r, b in enumerate(self.base):
+                if r != self.rank:
+                    try:
+                        L.call_nostream("b2n_peer_close", b)
+                    except RuntimeError:
+                        pass
+            if group is not None:
+                dist.barrier(group=group)                     # nobody frees a block a peer still has mapped
+            if self.local is not None:
+                try:
+                    L.call_nostream("b2n_peer_free", self.local)
+                except RuntimeError:
+                    pass
+        self.base, self.local = [], None
 
     def tensor(self, name):
         """The local region as a torch tensor."""

@@ -116,7 +116,15 @@ class NGPTrainer:
             regions = {"g": (_f32, self.n_pad), "h": (_f16, self.n_pad)}
             if self.grad_fp16:
                 regions["g16"] = (_f16, self.n_pad)
-            self.peer = PeerBlock(regions, self.dev, process_group)
+            try:
+                self.peer = PeerBlock(regions, self.dev, process_group)      # raises on ALL ranks or on none
+            except RuntimeError as e:
+                if comm == "p2p":                            # asked for explicitly
+                    raise
+                import warnings
+                warnings.warn(f"NVLink peer memory is not available ({e}); exchanging through NCCL instead")
+                self.comm, self.grad_fp16 = "nccl", False
+        if self.comm == "p2p":
             self.g_all, self.h_all = self.peer.tensor("g"), self.peer.tensor("h")
             self.h_all.copy_(tc.cast_half(p_pad))
             torch.cuda.synchronize(self.dev)

@@ -26,6 +26,16 @@ def main():
     from google_nerf_b200 import synthetic as syn
     from google_nerf_b200.models.networks import NGP
     from google_nerf_b200.trainer import NGPTrainer
+    if os.environ.get("B2N_TEST_PEER_FAIL") == "1":
+        # a rank that cannot map its peers: every rank must fall back to NCCL together (nobody left in a collective)
+        from google_nerf_b200 import _lib as L
+        orig = L.call_nostream
+
+        def failing(name, *a):
+            if name == "b2n_peer_open" and rank == dist.get_world_size() - 1:
+                raise RuntimeError("b2n_peer_open failed (injected)")
+            return orig(name, *a)
+        L.call_nostream = failing
     s = make_scene(0.5, 512, seed=11)
     ro, rd = s["rays_o"].to(dev), s["rays_d"].to(dev)
     tgt = syn.shade(ro, rd, 0.5)
@@ -37,8 +47,10 @@ def main():
         # no occupancy update inside the compared trajectory (its per-cell jitter is drawn per rank, so the learned
         # bitfields of the two runs agree only statistically); it is exercised on its own below
         tr = NGPTrainer(m, n_rays=512, use_graph=True, samples_per_ray=200, grid_update_interval=10 ** 9, warmup_steps=10 ** 9,
-                        seed=3, data_parallel=dp, comm=os.environ.get("B2N_COMM", "p2p"),
+                        seed=3, data_parallel=dp, comm=os.environ.get("B2N_COMM") or None,
                         comm_in_graph=os.environ.get("B2N_COMM_IN_GRAPH", "0") == "1")
+        if dp and os.environ.get("B2N_TEST_PEER_FAIL") == "1":
+            assert tr.comm == "nccl" and tr.peer is None, tr.comm
         tr.step_count = 1                                    # (step 0 would start with an update)
         tr.fixed_noise = s["noise"].to(dev)
         losses = [float(tr.step(ro, rd, tgt).item()) for _ in range(24)]
@@ -74,7 +86,7 @@ def main():
     agree = ((g1 - g2).abs()[seen].mean() / g1[seen].abs().mean()).item()          # mean deviation / mean density
     assert agree < 0.25 and (g2 > 0).any() and b2.any(), (agree, (g1 - g2).abs()[seen].max().item(), g1[seen].max().item())
     if rank == 0:
-        print("dist_nccl_check ok (comm %s): world" % os.environ.get("B2N_COMM", "p2p"), dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
+        print("dist_nccl_check ok (comm %s): world" % tr.comm, dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
               "mean density-grid deviation %.4f" % agree)
     dist.barrier(); dist.destroy_process_group()
 
