@@ -93,7 +93,7 @@ class _DeviceLoop:
     as ONE CUDA graph and replayed; the host looks at the live-ray count once per replay instead of twice per round.  Same schedule (N_samples = max(min(N_rays // N_alive, 64), min_samples)), same kernels and the same
     per-ray arithmetic as the host loop, so the images are identical."""
     ROUNDS_PER_SYNC = 8                                  # host looks at the live-ray count this often
-    ROUNDS_PER_GRAPH = int(__import__('os').environ.get('B2N_RENDER_RPG', 8))   # rounds captured per graph (even)
+    ROUNDS_PER_GRAPH = 8                                 # rounds captured per graph (even; 2 measured the same)
 
     @classmethod
     def get(cls, model, n_rays, esf, T_threshold):
