@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2n.so")
+LIB_PATH = os.environ.get("B2N_LIB") or os.path.join(_HERE, "lib", "libb2n.so")     # B2N_LIB: a variant build (experiments)
 
 MAX_LEVELS = 32
 

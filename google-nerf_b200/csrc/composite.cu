@@ -38,7 +38,9 @@ struct RayTotals { float O, D, D2, R, G, B; };
 // product / sum scans are independent instruction streams, so a long ray (the kernel's critical path: half of the
 // rays of a batch are empty, the rest carry 100-1000 samples) costs one memory latency and one scan latency per
 // 32*CU samples.  The arithmetic per chunk -- and so every result bit -- is that of the one-chunk-at-a-time form.
+#ifndef CU
 #define CU 4
+#endif
 
 __device__ __forceinline__ void warp_scan_mul_cu(float (&v)[CU], int lane) {
     #pragma unroll
