@@ -76,6 +76,17 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
 // warp-level gather touches half as many L1 wavefronts as a one-lane-per-sample mapping (the kernel is L1
 // wavefront bound on the fine levels: 10 hashed levels x 8 corners x 32 distinct lines per warp instruction).
 // The two half-results are combined with one xor-shuffle.
+#define B2N_PRAGMA_(x) _Pragma(#x)
+#define B2N_PRAGMA(x) B2N_PRAGMA_(x)
+#ifndef HG_FW_UNROLL
+#define HG_FW_UNROLL 4       // levels in flight per lane (16 independent gathers)
+#endif
+#ifndef HG_FW_CTAS
+#define HG_FW_CTAS 16
+#endif
+#ifndef HG_BW_CTAS
+#define HG_BW_CTAS 16
+#endif
 struct Corner4 {
     uint32_t idx[4];
     float w[4];
@@ -119,7 +130,7 @@ __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restric
         const float px = (__ldg(x + 3 * ii) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * ii + 1) - g.x_offset) * g.x_scale,
                     pz = (__ldg(x + 3 * ii + 2) - g.x_offset) * g.x_scale;
         __half2 *row = reinterpret_cast<__half2 *>(out + ii * out_stride);
-        #pragma unroll 4
+        B2N_PRAGMA(unroll HG_FW_UNROLL)
         for (int l = 0; l < g.n_levels; ++l) {
             Corner4 c;
             level_corners4(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], cx, c);
@@ -243,7 +254,7 @@ extern "C" int b2n_hashgrid_fw(const float *x, const b2n_half *table, const b2n_
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(out_stride >= 2 * g.n_levels && out_stride % 2 == 0, "out_stride too small / odd");
     if (n <= 0) return 0;
-    b2n_launch(hashgrid_fw_kernel, b2n_grid(b2n_blocks(2 * n, 128), 16), 128, (cudaStream_t)stream,
+    b2n_launch(hashgrid_fw_kernel, b2n_grid(b2n_blocks(2 * n, 128), HG_FW_CTAS), 128, (cudaStream_t)stream,
                x, (const __half2 *)table, g, n, n_dev, (__half *)out, out_stride);
     B2N_LAUNCH_CHECK();
     return 0;
@@ -256,7 +267,7 @@ extern "C" int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_s
     if (to_levels(layout, g)) return 1;
     B2N_CHECK_ARG(dy_stride >= 2 * g.n_levels && dy_stride % 2 == 0, "dy_stride too small / odd");
     if (n <= 0) return 0;
-    b2n_launch(hashgrid_bw_kernel, b2n_grid(b2n_blocks(n, 128), 16), 128, (cudaStream_t)stream,
+    b2n_launch(hashgrid_bw_kernel, b2n_grid(b2n_blocks(n, 128), HG_BW_CTAS), 128, (cudaStream_t)stream,
                x, (const __half *)dL_dout, dy_stride, g, n, n_dev, grad_scale, (float2 *)grad_table, sample_idx);
     B2N_LAUNCH_CHECK();
     return 0;

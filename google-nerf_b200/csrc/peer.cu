@@ -213,7 +213,7 @@ extern "C" int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp
         g16.p[r] = (r < world && grad16_ptrs != nullptr) ? grad16_ptrs[r] : nullptr;
         h.p[r] = r < world ? half_ptrs[r] : nullptr;
     }
-    const unsigned grid = b2n_grid(b2n_blocks(shard_n / 4, 256), 8);
+    const unsigned grid = b2n_grid(b2n_blocks(shard_n / 4, 256), 32);     // like adam_kernel: ~4 waves beat a persistent grid
     if (grad16_ptrs != nullptr && half_hi > half_lo)
         adam_peer_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, g16, half_lo / 4, half_hi / 4, h, world,
