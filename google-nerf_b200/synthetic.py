@@ -135,3 +135,35 @@ def shade(rays_o, rays_d, scale, bg=1.0):
     lam = (n * light).sum(-1).clamp(min=0) * 0.7 + 0.3
     colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
     return colour
+
+
+def write_nsvf_dataset(root, n_train=24, n_test=4, res=100, scale=0.5, seed=0):
+    """Write the analytic scene as an NSVF-format "Synthetic" dataset that ngp_pl/datasets/nsvf.py reads unchanged:
+    ``bbox.txt`` (xyz_min xyz_max), ``intrinsics.txt`` (fx of the 800-pixel image on the first line), ``pose/*.txt``
+    (4x4 camera-to-world, [right down front]) and ``rgb/*.png`` with the split prefixes 0_ (train) / 2_ (test)
+    (nsvf.py:17-35,66-75).  `root` must contain 'Synthetic' (that is how the loader picks this layout).  Images are
+    res x res; load them with ``downsample = res / 800``.  The loader maps positions with (p - shift) / (2 * 1.05 *
+    bbox_half), so raw positions are the model-space ones times 2.1 for the unit bbox written here."""
+    import os
+    from PIL import Image
+    if "Synthetic" not in root:
+        raise ValueError("the NSVF loader recognises this layout by 'Synthetic' in the path")
+    os.makedirs(os.path.join(root, "rgb"), exist_ok=True); os.makedirs(os.path.join(root, "pose"), exist_ok=True)
+    np.savetxt(os.path.join(root, "bbox.txt"), np.array([[-1.0, -1.0, -1.0, 1.0, 1.0, 1.0, 0.1]]), fmt="%.6f")
+    with open(os.path.join(root, "intrinsics.txt"), "w") as f:
+        f.write("1111.1 400.0 400.0 0.\n0. 0. 0.\n0.\n1.\n800 800\n")
+    K = intrinsics(res, res)
+    dirs = directions(res, res, K)
+    poses = hemisphere_poses(n_train + n_test, seed=seed)
+    for i in range(n_train + n_test):
+        prefix = "0_" if i < n_train else "2_"
+        c2w = poses[i]
+        rays_o, rays_d = get_rays(dirs, c2w)
+        img = shade(rays_o, rays_d, scale).reshape(res, res, 3)
+        Image.fromarray((img.clamp(0, 1) * 255 + 0.5).to(torch.uint8).numpy()).save(
+            os.path.join(root, "rgb", f"{prefix}{i:04d}.png"))
+        raw = torch.eye(4)
+        raw[:3, :3] = c2w[:, :3]
+        raw[:3, 3] = c2w[:, 3] * 2.1
+        np.savetxt(os.path.join(root, "pose", f"{prefix}{i:04d}.txt"), raw.numpy(), fmt="%.8f")
+    return poses[:n_train], poses[n_train:]
