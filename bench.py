@@ -327,9 +327,9 @@ def main():
             frames.append(float(dt.item())); render_samples = int(res["total_samples"])
     render_info = dict(mrays_per_s=W_IMG * H_IMG / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
                        rays=W_IMG * H_IMG, samples_per_ray=render_samples / (W_IMG * H_IMG), n_gpus=world,
-                       note="reference-style host loop (rendering.py:42-114) over the b2n kernels, T_threshold 1e-2 as in "
-                            "test.ipynb; N > 1: row tiles dealt round-robin to the ranks, max over ranks, all-gather of "
-                            "rgb/depth/opacity included")
+                       note="render(test_time=True): the loop of rendering.py:42-114 driven from the device (8 rounds per "
+                            "CUDA-graph replay), T_threshold 1e-2 as in test.ipynb; N > 1: row tiles dealt round-robin to "
+                            "the ranks, max over ranks, all-gather of rgb/depth/opacity included")
     # ---- image quality of what was just trained (sanity of the whole path, not a timed number): PSNR of a training view
     # and of a held-out view against the analytic ground truth (T_threshold 1e-4 like validation, train.py:178-183)
     quality = None
