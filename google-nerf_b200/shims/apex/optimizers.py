@@ -6,6 +6,15 @@ import torch
 from google_nerf_b200 import _lib as L
 
 
+def _bump_version(t):
+    try:
+        torch._C._increment_version([t])
+    except TypeError:
+        torch._C._increment_version(t)
+    except AttributeError:                                   # very old torch: an in-place no-op does the same
+        t.add_(0)
+
+
 class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-8, adam_w_mode=True,
                  weight_decay=0.0, amsgrad=False, set_grad_none=True):
@@ -36,6 +45,8 @@ class FusedAdam(torch.optim.Optimizer):
                     g = g.to(torch.float32).contiguous().clone()      # the kernel zeroes the gradient buffer it is given
                     L.call("b2n_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), None,
                            p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]), 1.0, st["step"], None)
+                    _bump_version(p)      # the kernel wrote through the raw pointer: consumers that cache derived data
+                                          # by (pointer, version) -- the tinycudann modules' fp16 copy -- must see a change
                 else:
                     m, v = st["exp_avg"], st["exp_avg_sq"]
                     m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)

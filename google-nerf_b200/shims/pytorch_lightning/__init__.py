@@ -134,7 +134,8 @@ class Trainer:
             self.current_epoch = int(state.get("epoch", -1)) + 1 if "epoch" in state else 0
             self.global_step = int(state.get("global_step", 0))
         amp = self.precision == 16 and device.type == "cuda"
-        scaler = torch.cuda.amp.GradScaler(enabled=amp)
+        scaler = torch.amp.GradScaler("cuda", enabled=amp) if hasattr(torch.amp, "GradScaler") else \
+            torch.cuda.amp.GradScaler(enabled=amp)
         train_loader, val_loader = model.train_dataloader(), model.val_dataloader()
         for cb in self.callbacks:
             cb.on_fit_start(self, model)
