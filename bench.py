@@ -155,15 +155,27 @@ def kernel_costs(n_rays, n_samples, n_alive, n_params_xyz, n_params_rgb):
         "b2n_hashgrid_bw": ("hbm", 1100 * a),
         "b2n_mlp_fw": ("tensor", None),
         "b2n_mlp_bw": ("tensor", None),
-        # fused tcgen05 field MLPs: 20.5 / 41 kFLOP per sample are ~1% of the tensor roofline; what bounds them is
-        # the activation traffic (enc 64 + dirs 12 + sigma 4 + rgb 12 + saved hid_s 128, h 32, hid_r 256 B/sample)
-        "b2n_field_mlp_fw": ("hbm", 508 * s),
-        "b2n_field_mlp_bw": ("hbm", 584 * a),
+        # fused tcgen05 field MLPs: 20.5 / 61 kFLOP per sample (the backward pass recomputes the hidden layers) are ~1% of
+        # the tensor roofline; their algorithmic traffic is enc 64 + dirs 12 + sigma 4 + rgb 12 + h 32 = 124 B/sample
+        # forward, enc 64 + h 32 + dirs 12 + rgb 12 + dL 16 + index 4 in and dL/denc 64 out = 204 B/alive sample backward
+        "b2n_field_mlp_fw": ("hbm", 124 * s),
+        "b2n_field_mlp_bw": ("hbm", 204 * a),
         "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_sh4_fw": ("hbm", 44 * s),
         "b2n_composite_loss_fwbw": ("hbm", 40 * s + 76 * r),
         "b2n_adam_step": ("hbm", None),
     }
+
+
+def load_ncu_metrics():
+    """Per-kernel counters of the committed ncu capture (profiles/summarise.py writes the file from the .ncu-rep of
+    profiles/run_ncu.sh): DRAM bytes, L2 sectors / requests and L1 hit rate per processed unit.  bench.py only scales
+    them to this run's unit counts; nothing here is a constant typed in by hand."""
+    path = os.path.join(ROOT, "profiles", "ncu_metrics.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f)
 
 
 def profile_kernels(tr, reps=5):
@@ -377,11 +389,12 @@ def main():
             ach, peak, unit = alg / dur_s / 1e12, tf_peak, "TFLOP/s"
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed capture
         # profiles/r01d_ncu_summary.md (580k samples, 11.43 M parameters), scaled to this run's units
-        ncu_traffic_per_sample = {"b2n_field_mlp_bw": 629.0, "b2n_field_mlp_fw": 441.0, "b2n_hashgrid_fw": 55.0,
-                                  "b2n_hashgrid_bw": 156.0, "b2n_composite_loss_fwbw": 27.0}
-        traffic = ncu_traffic_per_sample.get(base)
-        traffic = traffic * (alive if base in ("b2n_field_mlp_bw", "b2n_hashgrid_bw") else samples) if traffic else (
-            29.07 * tr.shard if base == "b2n_adam_step" else None)
+        ncu = load_ncu_metrics()
+        traffic = None
+        if ncu and base in ncu.get("kernels", {}):
+            per_unit = ncu["kernels"][base].get("dram_bytes_per_unit")
+            units = {"alive_sample": alive, "sample": samples, "param": tr.shard}.get(ncu["kernels"][base].get("unit"))
+            traffic = per_unit * units if per_unit is not None and units is not None else None
         roofline = dict(kernel=top, bound=bound, achieved=ach, peak=peak, unit=unit, frac=ach / peak,
                         traffic=traffic,
                         peak_source="MEASURED_PEAKS.json" if peaks else "fallback",
@@ -453,7 +466,7 @@ def main():
                    note="tcgen05 kind::f16; the MLPs are 64 wide: activation traffic and dependency latency bound them, "
                         "not the tensor pipe (ncu sm__pipe_tensor_cycles_active in profiles/)")
         cb = None
-        if not args.skip_cpu:
+        if not args.skip_cpu and world == 1:                  # rank 0 at N = 1 only (the other ranks would spin in NCCL)
             cb, _ = cpu_baseline(args.cpu_rays, 12, 1)         # ~10 s of CPU work on 16 host cores
         rays = N_RAYS * world * args.steps
         n_updates = sum(1 for s in range(args.steps) if s % tr.S == 0)

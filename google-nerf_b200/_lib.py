@@ -34,7 +34,6 @@ _SIGS = {
     "b2n_ray_aabb_intersect": [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "b2n_ray_sphere_intersect": [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "b2n_clamp_near": [_P, _L, _F, _P],
-    "b2n_set_l2_persist": [_P, _L],
     "b2n_render_schedule": [_P, _L, _I, _I, _P],
     "b2n_raymarching_test_dev": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
     "b2n_composite_test_fw_dev": [_P, _P, _P, _P, _P, _P, _F, _P, _L, _P, _P, _P, _P, _P],
@@ -43,7 +42,9 @@ _SIGS = {
     "b2n_peer_close": [_P],
     "b2n_peer_free": [_P],
     "b2n_peer_barrier": [_P, _I, _I, _P, _D, _P],
-    "b2n_adam_step_peer": [_P, _P, _P, _P, _P, _L, _L, _P, _I, _L, _L, _F, _F, _F, _F, _F, _I, _P, _P],
+    "b2n_adam_step_peer": [_P, _P, _P, _P, _P, _L, _L, _P, _I, _L, _L, _F, _F, _F, _F, _F, _I, _P, _P, _P, _P],
+    "b2n_scaler_update": [_P, _P, _I, _P],
+    "b2n_field_image_halves": [_I],
     "b2n_grad_pack_half": [_P, _P, _L, _L, _P],
     "b2n_rays_from_indices": [_P, _P, _P, _P, _L, _P, _P, _P],
     "b2n_morton3D": [_P, _L, _P, _P],
@@ -52,31 +53,32 @@ _SIGS = {
     "b2n_raymarching_train_count": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _L, _P, _P, _P, _P],
     "b2n_raymarching_train_count_serial": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _L, _P, _P, _P, _P],
     "b2n_raymarching_train_write": [_P, _P, _P, _P, _I, _F, _F, _P, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
-    "b2n_set_march_ctas_per_sm": [_I],
+    "b2n_raymarcher_bw": [_P, _P, _P, _P, _L, _P, _P, _P],
     "b2n_raymarching_test": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _I, _L, _P, _P, _P, _P, _P, _P],
     "b2n_composite_train_fw": [_P, _P, _P, _P, _P, _F, _L, _P, _P, _P, _P, _P],
     "b2n_composite_train_bw": [_P] * 13 + [_F, _L, _P, _P, _P, _P, _P],
-    "b2n_composite_loss_fwbw": [_P] * 6 + [_F, _L, _F, _F, _F] + [_P] * 9,
+    "b2n_composite_loss_fwbw": [_P] * 6 + [_F, _L, _F, _F, _F] + [_P] * 10,
     "b2n_composite_test_fw": [_P, _P, _P, _P, _P, _P, _F, _P, _I, _L, _P, _P, _P, _P],
     "b2n_hashgrid_layout": [_I, _I, _I, _I, _D, C.POINTER(GridLayout)],
     "b2n_hashgrid_fw": [_P, _P, C.POINTER(GridLayout), _L, _P, _P, _I, _P],
     "b2n_hashgrid_bw": [_P, _P, _I, C.POINTER(GridLayout), _L, _P, _F, _P, _P, _P],
-    "b2n_frequency_fw": [_P, _I, _L, _P, _P, _I, _P],
+    "b2n_frequency_fw": [_P, _I, _L, _P, _P, _I, _F, _F, _P],
     "b2n_sh4_fw": [_P, _I, _L, _P, _P, _I, _P],
     "b2n_mlp_fw": [_P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _P],
     "b2n_mlp_bw": [_P, _P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _F, _P, _P, _P],
-    "b2n_field_pack_weights": [_P, _P, _P, _P],
-    "b2n_field_mlp_fw": [_P, _P, _P, _L, _P, _P, _P, _P, _P, _P, _P],
-    "b2n_field_mlp_bw": [_P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _L, _P],
+    "b2n_field_pack_weights": [_P, _P, _P, _I, _P],
+    "b2n_field_mlp_fw": [_P, _I, _P, _P, _L, _P, _P, _P, _P, _P],
+    "b2n_field_mlp_bw": [_P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _P],
     "b2n_cast_half": [_P, _P, _L, _P],
     "b2n_grid_cell_positions": [_P, _P, _L, _I, _F, _F, _F, _I, _P, _P],
-    "b2n_grid_scatter": [_P, _P, _L, _P, _P],
+    "b2n_grid_scatter": [_P, _P, _L, _P, _L, _P],
     "b2n_grid_ema": [_P, _P, _L, _F, _P],
     "b2n_grid_threshold": [_P, _L, _F, _P, _P, _P],
+    "b2n_mark_invisible_cells": [_P, _P, _I, _I, _I, _F, _I, _I, _F, _P, _P],
     "b2n_membench_read": [_P, _L, _I, _P, _P],
     "b2n_membench_gather": [_P, _L, _I, _P, C.POINTER(C.c_int64), _P],
-    "b2n_nerf_loss_fwbw": [_P, _P, _P, _L, _F, _F, _F, _P, _P, _P, _P, _P],
+    "b2n_nerf_loss_fwbw": [_P, _P, _P, _L, _F, _F, _F, _P, _P, _P, _P, _P, _P],
 }
 
 _lib = None

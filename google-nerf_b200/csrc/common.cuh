@@ -38,24 +38,12 @@ static inline unsigned b2n_grid(int64_t n_ctas_needed, int per_sm) {
     return (unsigned)(n_ctas_needed < cap ? n_ctas_needed : cap);
 }
 
-// Optional L2 persistence window (b2n_set_l2_persist): kernels that gather from / scatter into the fp16 parameter copy
-// and the gradient vector launch with an access-policy-window attribute, so that those 69 MB stay resident in the
-// 126 MB L2 across the step instead of being evicted by the streaming activation traffic.  A launch attribute (not a
-// stream attribute) so that it is recorded in captured graph nodes.
-bool b2n_l2_window(cudaAccessPolicyWindow *out);
-
+// cudaLaunchKernelEx wrapper used by the gather / scatter / Adam kernels (argument conversion to the kernel's types)
 template <class... KArgs, class... Args>
 static inline cudaError_t b2n_launch(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t stream,
                                      Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    cudaAccessPolicyWindow win;
-    if (b2n_l2_window(&win)) {
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow = win;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-    }
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(256) composite_loss_fwbw_kernel(
     const float *__restrict__ ts, const int64_t *__restrict__ rays_a, const float *__restrict__ target,
     float T_threshold, int64_t n_rays, float bg, float lambda_opa, float loss_scale, float *__restrict__ opacity,
     float *__restrict__ depth, float *__restrict__ rgb_out, float *loss, float *__restrict__ dL_dsigmas,
-    float *__restrict__ dL_drgbs, int32_t *__restrict__ alive_idx, int32_t *alive_count) {
+    float *__restrict__ dL_drgbs, int32_t *__restrict__ alive_idx, int32_t *alive_count,
+    const float *__restrict__ loss_scale_dev) {
+    if (loss_scale_dev != nullptr) loss_scale = __ldg(loss_scale_dev);    // the trainer's device-side loss scaler
     const int lane = threadIdx.x & 31;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const float inv3n = 1.0f / (3.0f * (float)n_rays), invn = 1.0f / (float)n_rays;
@@ -433,7 +435,7 @@ extern "C" int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, c
                                        int64_t n_rays, float bg, float lambda_opa, float loss_scale,
                                        float *opacity, float *depth, float *rgb_out, float *loss_dev,
                                        float *dL_dsigmas, float *dL_drgbs, int32_t *alive_idx,
-                                       int32_t *alive_count, void *stream) {
+                                       int32_t *alive_count, const float *loss_scale_dev, void *stream) {
     B2N_CHECK_ARG((alive_idx == nullptr) == (alive_count == nullptr), "alive_idx and alive_count go together");
     B2N_CHECK_ARG(loss_dev != nullptr, "loss_dev is required");
     if (alive_count != nullptr && (void *)loss_dev == (void *)(alive_count + 1)) {
@@ -445,7 +447,7 @@ extern "C" int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, c
     if (n_rays <= 0) return 0;
     composite_loss_fwbw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, rays_a, target, T_threshold, n_rays, bg, lambda_opa, loss_scale, opacity, depth,
-        rgb_out, loss_dev, dL_dsigmas, dL_drgbs, alive_idx, alive_count);
+        rgb_out, loss_dev, dL_dsigmas, dL_drgbs, alive_idx, alive_count, loss_scale_dev);
     B2N_LAUNCH_CHECK();
     return 0;
 }
@@ -471,6 +473,57 @@ extern "C" int b2n_composite_test_fw_dev(const float *sigmas, const float *rgbs,
     if (max_alive <= 0) return 0;
     composite_test_fw_kernel<<<b2n_blocks(max_alive, 256), 256, 0, (cudaStream_t)stream>>>(
         sigmas, rgbs, deltas, ts, alive_indices, T_threshold, n_eff, 1, max_alive, opacity, depth, rgb, ctl, alive_next);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RayMarcher.backward (ngp_pl/models/custom_functions.py:103-113, the --optimize_ext path): per-ray segment sums
+//   dL_drays_o = sum_s dL_dxyzs[s]      dL_drays_d = sum_s (dL_dxyzs[s] * ts[s] + dL_ddirs[s])
+// over the ray's packed samples [start, start + N).  The reference builds a CSR pointer from rays_a and calls
+// torch_scatter.segment_csr twice; here a warp owns a ray (coalesced reads, shuffle reduction, no atomics).
+__global__ void __launch_bounds__(256) raymarcher_bw_kernel(const float *__restrict__ dL_dxyzs,
+                                                            const float *__restrict__ dL_ddirs,
+                                                            const float *__restrict__ ts,
+                                                            const int64_t *__restrict__ rays_a, int64_t n_rays,
+                                                            float *__restrict__ dL_drays_o, float *__restrict__ dL_drays_d) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t n = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; n < n_rays; n += warps) {
+        const int64_t ray = rays_a[3 * n], start = rays_a[3 * n + 1];
+        const int N = (int)rays_a[3 * n + 2];
+        float o[3] = {0.f, 0.f, 0.f}, d[3] = {0.f, 0.f, 0.f};
+        for (int i = lane; i < N; i += 32) {
+            const int64_t s = start + i;
+            const float t = __ldg(ts + s);
+            #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float g = __ldg(dL_dxyzs + 3 * s + k);
+                o[k] += g;
+                d[k] += g * t + (dL_ddirs != nullptr ? __ldg(dL_ddirs + 3 * s + k) : 0.f);
+            }
+        }
+        #pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            #pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                o[k] += __shfl_xor_sync(0xffffffffu, o[k], off);
+                d[k] += __shfl_xor_sync(0xffffffffu, d[k], off);
+            }
+        }
+        if (lane < 3) {
+            dL_drays_o[3 * ray + lane] = lane == 0 ? o[0] : (lane == 1 ? o[1] : o[2]);
+            dL_drays_d[3 * ray + lane] = lane == 0 ? d[0] : (lane == 1 ? d[1] : d[2]);
+        }
+    }
+}
+
+extern "C" int b2n_raymarcher_bw(const float *dL_dxyzs, const float *dL_ddirs, const float *ts, const int64_t *rays_a,
+                                 int64_t n_rays, float *dL_drays_o, float *dL_drays_d, void *stream) {
+    B2N_CHECK_ARG(dL_dxyzs && ts && rays_a && dL_drays_o && dL_drays_d, "null argument");
+    if (n_rays <= 0) return 0;
+    raymarcher_bw_kernel<<<warp_grid(n_rays), 256, 0, (cudaStream_t)stream>>>(dL_dxyzs, dL_ddirs, ts, rays_a, n_rays,
+                                                                            dL_drays_o, dL_drays_d);
     B2N_LAUNCH_CHECK();
     return 0;
 }

@@ -1,12 +1,15 @@
 // encoding.cu -- multiresolution hash grid (fw / table-bw), frequency and spherical-harmonics encodings.
 // Replaces the tiny-cuda-nn encodings NGP builds (ngp_pl/models/networks.py:34-53,63-70).
 //
-// Hash grid design (DESIGN.md "Hash grid"): gather-bound.  One thread owns one sample and walks all levels,
-// so the 32 lanes of a warp always gather from the SAME level's table (neighbouring samples of a ray hit
-// neighbouring entries) and every thread keeps 8 independent 4-byte gathers in flight per level; the
-// thread's 64-byte output row is written with 16-byte stores.  The fp16 table (21.8 MiB at T=2^19) stays
-// L2-resident on B200 (126 MB L2).  Backward accumulates straight into the fp32 gradient table with
-// vector red.global.add.v2.f32 (no fp16 underflow, no separate cast pass).
+// Hash grid design: gather-bound on the L1-miss path (one sector request per clock and SM).
+// Forward: TWO lanes per sample (lane parity = x-corner, so the pair's gathers fall into one 128-byte line), a warp
+// walks all levels of 16 consecutive samples of a ray, four levels (16 independent 4-byte gathers) in flight per lane,
+// fp32 accumulation, one fp16 rounding, the 64-byte output row written as four 16-byte stores.  The fp16 table
+// (21.8 MiB at T=2^19) stays L2-resident on B200 (126 MB L2); at T=2^22 (185 MiB) the fine levels come from HBM.
+// Backward: one lane per (alive) sample, runs of lanes in one cell are summed with a segmented shuffle reduction on
+// the coarse levels, then vector red.global.add.v2.f32 straight into the fp32 gradient table (no fp16 underflow, no
+// separate cast pass).  Entry indices avoid the integer division of `index % size`: hashed levels have a
+// power-of-two size (mask), dense levels overshoot the size by less than one period (conditional subtract).
 // Algorithmic bytes per sample: 12 in + 16 levels x 8 corners x 4 B gathered + 64 out = 588 B.
 #include "common.cuh"
 
@@ -16,6 +19,7 @@ struct GridLevels {
     uint32_t resolution[B2N_MAX_LEVELS];
     uint32_t size[B2N_MAX_LEVELS];
     uint32_t offset[B2N_MAX_LEVELS];
+    uint8_t mode[B2N_MAX_LEVELS];       // 0 dense (index < 2 * size), 1 hashed with a power-of-two size, 2 generic
     float x_offset, x_scale;
 };
 
@@ -27,6 +31,14 @@ static int to_levels(const b2n_grid_layout *l, GridLevels &g) {
     for (int i = 0; i < l->n_levels; ++i) {
         g.scale[i] = l->scale[i]; g.resolution[i] = l->resolution[i];
         g.size[i] = l->size[i]; g.offset[i] = l->offset[i];
+        // the stride walk of grid_index on the host: does this level fall through to the hash?
+        const uint32_t res = l->resolution[i], size = l->size[i];
+        uint32_t stride = 1;
+        for (int d = 0; d < 3; ++d)
+            if (stride <= size) stride *= res;
+        const bool hashed = size < stride, pow2 = size && (size & (size - 1)) == 0;
+        const bool dense_ok = !hashed && res >= 2 && (uint64_t)res * res * res <= size;   // index <= res+res^2+res^3 < 2*size
+        g.mode[i] = hashed ? (pow2 ? 1 : 2) : (dense_ok ? 0 : 2);
     }
     return 0;
 }
@@ -87,6 +99,20 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
 #ifndef HG_BW_CTAS
 #define HG_BW_CTAS 16
 #endif
+// the same index without the division (mode from to_levels)
+__device__ __forceinline__ uint32_t grid_index_m(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size, int mode) {
+    if (mode == 1) return (x ^ (y * 2654435761u) ^ (z * 805459861u)) & (size - 1);
+    if (mode == 0) {
+        uint32_t index = x + (y + z * res) * res;
+        if (index >= size) {                          // only the x/y/z = res boundary corners; positions inside the box
+            index -= size;                            // overshoot by less than one period
+            if (index >= size) index %= size;         // out-of-box positions stay in bounds like the generic form
+        }
+        return index;
+    }
+    return grid_index(x, y, z, res, size);
+}
+
 struct Corner4 {
     uint32_t idx[4];
     float w[4];
@@ -94,7 +120,7 @@ struct Corner4 {
 };
 
 __device__ __forceinline__ void level_corners4(float px, float py, float pz, float scale, uint32_t res, uint32_t size,
-                                               uint32_t offset, int cx, Corner4 &c) {
+                                               uint32_t offset, int mode, int cx, Corner4 &c) {
     const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
     const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
     const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
@@ -109,7 +135,7 @@ __device__ __forceinline__ void level_corners4(float px, float py, float pz, flo
         w *= wxc;                                  // same product order as the 8-corner form: ((1*wx)*wy)*wz
         w *= (k & 1) ? wy : 1.0f - wy;
         w *= (k & 2) ? wz : 1.0f - wz;
-        c.idx[k] = offset + grid_index(x, y, z, res, size);
+        c.idx[k] = offset + grid_index_m(x, y, z, res, size, mode);
         c.w[k] = w;
     }
 }
@@ -121,6 +147,7 @@ __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restric
                                                           __half *__restrict__ out, int out_stride) {
     n = b2n_eff_n(n, n_dev);
     const int lane = threadIdx.x & 31, cx = lane & 1;
+    const bool vec16 = (out_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);   // rows 16-byte aligned
     const int64_t pairs_per_grid = ((int64_t)gridDim.x * blockDim.x) >> 1;
     // warp-uniform loop: a warp covers 16 consecutive samples per iteration
     for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31)) >> 1; base < n; base += pairs_per_grid) {
@@ -129,24 +156,42 @@ __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restric
         const int64_t ii = live ? i : n - 1;
         const float px = (__ldg(x + 3 * ii) - g.x_offset) * g.x_scale, py = (__ldg(x + 3 * ii + 1) - g.x_offset) * g.x_scale,
                     pz = (__ldg(x + 3 * ii + 2) - g.x_offset) * g.x_scale;
-        __half2 *row = reinterpret_cast<__half2 *>(out + ii * out_stride);
-        B2N_PRAGMA(unroll HG_FW_UNROLL)
-        for (int l = 0; l < g.n_levels; ++l) {
-            Corner4 c;
-            level_corners4(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], cx, c);
-            __half2 v[4];
+        __half *row = out + ii * out_stride;
+        // four levels per block: 16 independent gathers in flight per lane, one 16-byte store per block
+        for (int l0 = 0; l0 < g.n_levels; l0 += 4) {
+            uint32_t packed[4];
             #pragma unroll
-            for (int k = 0; k < 4; ++k) v[k] = __ldg(table + c.idx[k]);
-            float a0 = 0.f, a1 = 0.f;
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const float2 f = __half22float2(v[k]);
-                a0 = fmaf(c.w[k], f.x, a0);
-                a1 = fmaf(c.w[k], f.y, a1);
+            for (int q = 0; q < 4; ++q) {
+                const int l = l0 + q;
+                packed[q] = 0u;
+                if (l < g.n_levels) {
+                    Corner4 c;
+                    level_corners4(px, py, pz, g.scale[l], g.resolution[l], g.size[l], g.offset[l], g.mode[l], cx, c);
+                    __half2 v[4];
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = __ldg(table + c.idx[k]);
+                    float a0 = 0.f, a1 = 0.f;
+                    #pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = __half22float2(v[k]);
+                        a0 = fmaf(c.w[k], f.x, a0);
+                        a1 = fmaf(c.w[k], f.y, a1);
+                    }
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+                    const __half2 r = __floats2half2_rn(a0, a1);
+                    packed[q] = *reinterpret_cast<const uint32_t *>(&r);
+                }
             }
-            a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-            if (cx == 0 && live) row[l] = __floats2half2_rn(a0, a1);
+            if (cx == 0 && live) {
+                if (vec16 && l0 + 4 <= g.n_levels) {
+                    *reinterpret_cast<uint4 *>(row + 2 * l0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                } else {
+                    #pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (l0 + q < g.n_levels) *reinterpret_cast<uint32_t *>(row + 2 * (l0 + q)) = packed[q];
+                }
+            }
         }
     }
 }
@@ -157,7 +202,7 @@ struct Corner8 {
 };
 
 __device__ __forceinline__ void level_corners(float px, float py, float pz, float scale, uint32_t res,
-                                              uint32_t size, uint32_t offset, Corner8 &c) {
+                                              uint32_t size, uint32_t offset, int mode, Corner8 &c) {
     const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
     const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
     const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
@@ -169,7 +214,7 @@ __device__ __forceinline__ void level_corners(float px, float py, float pz, floa
         w *= (k & 1) ? wx : 1.0f - wx;
         w *= (k & 2) ? wy : 1.0f - wy;
         w *= (k & 4) ? wz : 1.0f - wz;
-        c.idx[k] = offset + grid_index(x, y, z, res, size);
+        c.idx[k] = offset + grid_index_m(x, y, z, res, size, mode);
         c.w[k] = w;
     }
 }
@@ -208,7 +253,7 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
             gr.y = live ? gr.y * grad_scale : 0.f;
             const uint32_t res = g.resolution[l];
             Corner8 c;
-            level_corners(px, py, pz, g.scale[l], res, g.size[l], g.offset[l], c);
+            level_corners(px, py, pz, g.scale[l], res, g.size[l], g.offset[l], g.mode[l], c);
             if (res > AGG_RES) {
                 if (gr.x != 0.0f || gr.y != 0.0f) {
                     #pragma unroll
@@ -278,7 +323,8 @@ extern "C" int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_s
 // d = j / (2F), f = (j/2) % F; the remaining columns up to a multiple of 16 are ones.
 __global__ void __launch_bounds__(256) frequency_fw_kernel(const float *__restrict__ x, int n_freq, int width,
                                                            int64_t n, const int32_t *__restrict__ n_dev,
-                                                           __half *__restrict__ out, int out_stride) {
+                                                           __half *__restrict__ out, int out_stride, float x_min,
+                                                           float x_extent) {
     n = b2n_eff_n(n, n_dev);
     const int enc = 3 * n_freq * 2;
     const int64_t total = n * width;
@@ -288,7 +334,8 @@ __global__ void __launch_bounds__(256) frequency_fw_kernel(const float *__restri
         float v = 1.0f;
         if (j < enc) {
             const int d = j / (2 * n_freq), f = (j >> 1) % n_freq;
-            const float xs = scalbnf(__ldg(x + 3 * i + d), f);
+            // box normalisation of NGP.density (networks.py:96) folded in: (x - xyz_min) / (xyz_max - xyz_min)
+            const float xs = scalbnf(__fdiv_rn(__fsub_rn(__ldg(x + 3 * i + d), x_min), x_extent), f);
             v = sinf(__fadd_rn(__fmul_rn(xs, 3.14159265358979323846f), (j & 1) ? 1.57079632679489661923f : 0.0f));
         }
         out[i * out_stride + j] = __float2half_rn(v);
@@ -296,12 +343,12 @@ __global__ void __launch_bounds__(256) frequency_fw_kernel(const float *__restri
 }
 
 extern "C" int b2n_frequency_fw(const float *x, int n_frequencies, int64_t n, const int32_t *n_dev,
-                                b2n_half *out, int out_stride, void *stream) {
+                                b2n_half *out, int out_stride, float x_min, float x_extent, void *stream) {
     const int width = (3 * n_frequencies * 2 + 15) / 16 * 16;
-    B2N_CHECK_ARG(n_frequencies >= 1 && out_stride >= width, "bad frequency config");
+    B2N_CHECK_ARG(n_frequencies >= 1 && out_stride >= width && x_extent != 0.f, "bad frequency config");
     if (n <= 0) return 0;
     frequency_fw_kernel<<<b2n_grid(b2n_blocks(n * width, 256), 8), 256, 0, (cudaStream_t)stream>>>(
-        x, n_frequencies, width, n, n_dev, (__half *)out, out_stride);
+        x, n_frequencies, width, n, n_dev, (__half *)out, out_stride, x_min, x_extent);
     B2N_LAUNCH_CHECK();
     return 0;
 }

@@ -8,36 +8,6 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
-static cudaAccessPolicyWindow g_l2_window;
-static bool g_l2_window_on = false;
-bool b2n_l2_window(cudaAccessPolicyWindow *out) {
-    if (g_l2_window_on) *out = g_l2_window;
-    return g_l2_window_on;
-}
-
-extern "C" int b2n_set_l2_persist(void *base, int64_t bytes) {
-    if (base == nullptr || bytes <= 0) {                    // switch off and give the carve-out back
-        g_l2_window_on = false;
-        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0);
-        return 0;
-    }
-    int dev = 0, max_persist = 0, max_window = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
-    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
-    if (max_persist <= 0 || max_window <= 0) { g_l2_window_on = false; return 0; }   // not supported: stay off
-    const size_t carve = (size_t)bytes < (size_t)max_persist ? (size_t)bytes : (size_t)max_persist;
-    const cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
-    if (e != cudaSuccess) { b2n_set_error("b2n_set_l2_persist: %s", cudaGetErrorString(e)); return 2; }
-    const size_t span = (size_t)bytes < (size_t)max_window ? (size_t)bytes : (size_t)max_window;
-    g_l2_window.base_ptr = base;
-    g_l2_window.num_bytes = span;
-    g_l2_window.hitRatio = carve >= span ? 1.0f : (float)carve / (float)span;
-    g_l2_window.hitProp = cudaAccessPropertyPersisting;
-    g_l2_window.missProp = cudaAccessPropertyStreaming;
-    g_l2_window_on = true;
-    return 0;
-}
 
 void b2n_set_error(const char *fmt, ...) {
     va_list ap;
@@ -268,6 +238,60 @@ extern "C" int b2n_packbits(const float *density_grid, int64_t n_bytes, float th
     B2N_CHECK_ARG(((uintptr_t)density_grid & 15) == 0, "density_grid must be 16-byte aligned");
     packbits_kernel<<<b2n_grid(b2n_blocks(n_bytes, 256), 8), 256, 0, (cudaStream_t)stream>>>(
         (const float4 *)density_grid, n_bytes, threshold, threshold_dev, density_bitfield);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// NGP.mark_invisible_cells (ngp_pl/models/networks.py:159-214) as one launch: a thread per (cascade, cell) projects
+// the cell centre into every training camera; the cell is valid (density 0) when at least one camera sees it at
+// depth >= near and no camera has it in its image closer than near, otherwise it gets -1 and is never updated.
+// The reference does this with chunked bmm over (N_img, 3, 64^3) tensors.
+__global__ void __launch_bounds__(256) mark_invisible_cells_kernel(const float *__restrict__ K,
+                                                                   const float *__restrict__ poses, int n_img,
+                                                                   float img_w, float img_h, float near_d, int G,
+                                                                   int cascades, float scale,
+                                                                   float *__restrict__ density_grid) {
+    const int64_t cells = (int64_t)G * G * G;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cells * cascades) return;
+    const int c = (int)(t / cells);
+    const int64_t cell = t - (int64_t)c * cells;
+    const uint32_t cx = (uint32_t)(cell % G), cy = (uint32_t)((cell / G) % G), cz = (uint32_t)(cell / ((int64_t)G * G));
+    const float s = fminf(scalbnf(1.0f, c - 1), scale);           // min(2^(c-1), scale)
+    const float span = s - s / (float)G;
+    const float gm1 = (float)(G - 1);
+    const float xw = ((float)cx / gm1 * 2.0f - 1.0f) * span, yw = ((float)cy / gm1 * 2.0f - 1.0f) * span,
+                zw = ((float)cz / gm1 * 2.0f - 1.0f) * span;
+    const float k00 = K[0], k01 = K[1], k02 = K[2], k10 = K[3], k11 = K[4], k12 = K[5], k20 = K[6], k21 = K[7], k22 = K[8];
+    bool covered = false, too_near = false;
+    for (int i = 0; i < n_img && !too_near; ++i) {
+        const float *P = poses + 12 * i;                            // (3,4) row-major camera-to-world
+        // world -> camera: R^T (x - t) written like the reference, R^T x + (-R^T t)
+        float pc[3];
+        #pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float tr = -(P[r] * P[3] + P[4 + r] * P[7] + P[8 + r] * P[11]);
+            pc[r] = P[r] * xw + P[4 + r] * yw + P[8 + r] * zw + tr;
+        }
+        const float u3 = k00 * pc[0] + k01 * pc[1] + k02 * pc[2], v3 = k10 * pc[0] + k11 * pc[1] + k12 * pc[2],
+                    d = k20 * pc[0] + k21 * pc[1] + k22 * pc[2];
+        const float u = u3 / d, v = v3 / d;
+        const bool in_image = (d >= 0.0f) && (u >= 0.0f) && (u < img_w) && (v >= 0.0f) && (v < img_h);
+        covered |= in_image && (d >= near_d);
+        too_near |= in_image && (d < near_d);
+    }
+    density_grid[(int64_t)c * cells + b2n_morton3D(cx, cy, cz)] = (covered && !too_near) ? 0.0f : -1.0f;
+}
+
+extern "C" int b2n_mark_invisible_cells(const float *K, const float *poses, int n_img, int img_w, int img_h,
+                                        float near_distance, int grid_size, int cascades, float scale,
+                                        float *density_grid, void *stream) {
+    B2N_CHECK_ARG(K && poses && density_grid && n_img >= 1 && grid_size >= 2 && grid_size <= 1024 && cascades >= 1,
+                  "bad arguments");
+    const int64_t n = (int64_t)grid_size * grid_size * grid_size * cascades;
+    mark_invisible_cells_kernel<<<b2n_blocks(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        K, poses, n_img, (float)img_w, (float)img_h, near_distance, grid_size, cascades, scale, density_grid);
     B2N_LAUNCH_CHECK();
     return 0;
 }

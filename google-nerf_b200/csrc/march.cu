@@ -407,15 +407,6 @@ static int fill_params(MarchParams &p, const uint8_t *bitfield, int cascades, fl
     return 0;
 }
 
-// Resident CTAs per SM for the TRAIN marcher (8 warps each).  8 = every ray's warp resident at once (fastest in
-// isolation); the pipelined trainer lowers it so that the marcher, which runs on a side stream underneath the
-// latency-bound backward kernels, trickles through spare issue slots instead of occupying every warp slot.
-static int g_march_ctas_per_sm = 8;
-extern "C" int b2n_set_march_ctas_per_sm(int ctas) {
-    B2N_CHECK_ARG(ctas >= 1 && ctas <= 8, "ctas per SM must be 1..8");
-    g_march_ctas_per_sm = ctas;
-    return 0;
-}
 static inline unsigned march_grid(int64_t n_warps, int per_sm = 8) { return b2n_grid((n_warps + 7) / 8, per_sm); }
 
 extern "C" int b2n_raymarching_train_count(const float *rays_o, const float *rays_d, const float *hits_t,
@@ -429,10 +420,10 @@ extern "C" int b2n_raymarching_train_count(const float *rays_o, const float *ray
     cudaStream_t st = (cudaStream_t)stream;
     if (n_rays > 0) {
         if (exp_step_factor == 0.0f)
-            march_train_kernel<true, false><<<march_grid(n_rays, g_march_ctas_per_sm), 256, 0, st>>>(
+            march_train_kernel<true, false><<<march_grid(n_rays), 256, 0, st>>>(
                 rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr, workspace);
         else
-            march_train_kernel<false, false><<<march_grid(n_rays, g_march_ctas_per_sm), 256, 0, st>>>(
+            march_train_kernel<false, false><<<march_grid(n_rays), 256, 0, st>>>(
                 rays_o, rays_d, hits_t, noise, p, n_rays, rays_a, nullptr, nullptr, nullptr, nullptr, workspace);
         B2N_LAUNCH_CHECK();
     }
@@ -478,10 +469,10 @@ extern "C" int b2n_raymarching_train_write(const float *rays_o, const float *ray
     if (n_rays <= 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (exp_step_factor == 0.0f)
-        march_train_kernel<true, true><<<march_grid(n_rays, g_march_ctas_per_sm), 256, 0, st>>>(
+        march_train_kernel<true, true><<<march_grid(n_rays), 256, 0, st>>>(
             rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts, (uint32_t *)workspace);
     else
-        march_train_kernel<false, true><<<march_grid(n_rays, g_march_ctas_per_sm), 256, 0, st>>>(
+        march_train_kernel<false, true><<<march_grid(n_rays), 256, 0, st>>>(
             rays_o, rays_d, hits_t, noise, p, n_rays, (int64_t *)rays_a, xyzs, dirs, deltas, ts, (uint32_t *)workspace);
     B2N_LAUNCH_CHECK();
     return 0;

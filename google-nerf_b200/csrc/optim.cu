@@ -9,17 +9,25 @@
 
 // ------------------------------------------------------------------------------------------------ Adam
 // Per parameter: read p, g, m, v (16 B), write p, m, v (12 B), zero g (4 B), write fp16 copy (2 B) = 34 B.
+// hyper (b2n_hyper, optional): learning rate, step count and the loss-scaler state live on the device so that a captured
+// graph replays with fresh values.  found_inf != 0 (a backward kernel saw a gradient leave the fp16 range) turns the
+// step into "clear the gradient, keep everything else" -- what torch.cuda.amp.GradScaler does for the reference's
+// precision=16 training (ngp_pl/train.py:265): the optimiser step is skipped and does not count for the bias correction.
 __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float4 *__restrict__ g,
                                                    float4 *__restrict__ m, float4 *__restrict__ v,
                                                    __half2 *__restrict__ h, int64_t n4, float lr, float b1,
                                                    float b2, float eps, float inv_scale, int step,
-                                                   const void *__restrict__ hyper) {
+                                                   const b2n_hyper *__restrict__ hyper) {
+    bool skip = false;
     if (hyper != nullptr) {
-        lr = *reinterpret_cast<const float *>(hyper);
-        step = reinterpret_cast<const int *>(hyper)[1];
+        lr = hyper->lr;
+        step = hyper->step - hyper->skipped;
+        skip = hyper->found_inf != 0;
+        if (hyper->loss_scale > 0.f) inv_scale /= hyper->loss_scale;
     }
     const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        if (skip) { g[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
         float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
         float *P = &pp.x, *G = &gg.x, *M = &mm.x, *V = &vv.x;
         #pragma unroll
@@ -40,7 +48,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float
 
 extern "C" int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
                              int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale,
-                             int step, const void *hyper_dev, void *stream) {
+                             int step, const b2n_hyper *hyper_dev, void *stream) {
     B2N_CHECK_ARG(n % 4 == 0, "parameter count must be a multiple of 4");
     B2N_CHECK_ARG(step >= 1 || hyper_dev != nullptr, "step is 1-based");
     if (n == 0) return 0;
@@ -50,6 +58,32 @@ extern "C" int b2n_adam_step(float *param, float *grad, float *exp_avg, float *e
     b2n_launch(adam_kernel, b2n_grid(b2n_blocks(n / 4, 256), ADAM_CTAS), 256, (cudaStream_t)stream,
                (float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, (__half2 *)half_copy, n / 4,
                lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
+// GradScaler bookkeeping after the optimiser step (one thread): found_inf (OR over the ranks' blocks when a pointer
+// table is given; every rank computes the same value) halves the loss scale and counts a skipped step, otherwise
+// growth_interval clean steps in a row double it (0 = fixed scale).  found_inf itself is cleared by the caller once
+// every rank has read it.
+struct HyperPtrs { const b2n_hyper *p[16]; };
+__global__ void scaler_update_kernel(b2n_hyper *hyper, const __grid_constant__ HyperPtrs all, int world) {
+    int bad = hyper->found_inf;
+    for (int r = 0; r < world; ++r) bad |= all.p[r] != nullptr ? *reinterpret_cast<const volatile int32_t *>(&all.p[r]->found_inf) : 0;
+    if (bad) {
+        hyper->skipped += 1;
+        hyper->good_steps = 0;
+        hyper->loss_scale = fmaxf(hyper->loss_scale * 0.5f, 1.0f);
+    } else if (hyper->growth_interval > 0 && ++hyper->good_steps >= hyper->growth_interval) {
+        hyper->good_steps = 0;
+        hyper->loss_scale = fminf(hyper->loss_scale * 2.0f, 65536.0f);
+    }
+}
+extern "C" int b2n_scaler_update(b2n_hyper *hyper_dev, void *const *hyper_ptrs, int world, void *stream) {
+    B2N_CHECK_ARG(hyper_dev != nullptr && world >= 1 && world <= 16, "bad arguments");
+    HyperPtrs all;
+    for (int r = 0; r < 16; ++r) all.p[r] = (hyper_ptrs != nullptr && r < world) ? (const b2n_hyper *)hyper_ptrs[r] : nullptr;
+    scaler_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper_dev, all, hyper_ptrs != nullptr ? world : 0);
     B2N_LAUNCH_CHECK();
     return 0;
 }
@@ -102,13 +136,18 @@ extern "C" int b2n_grid_cell_positions(const int32_t *coords, const float *noise
 
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const int64_t *__restrict__ indices,
                                                            const float *__restrict__ sigmas, int64_t n,
-                                                           float *__restrict__ tmp) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        tmp[indices[i]] = sigmas[i];
+                                                           float *__restrict__ tmp, int64_t n_cells) {
+    // tmp[indices] = sigmas (networks.py:233).  Duplicate indices: one of the written values survives, as with
+    // torch's index_put; indices outside [0, n_cells) are ignored instead of writing out of bounds.
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = indices[i];
+        if (c >= 0 && c < n_cells) tmp[c] = sigmas[i];
+    }
 }
-extern "C" int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, void *stream) {
+extern "C" int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, int64_t n_cells,
+                                void *stream) {
     if (n <= 0) return 0;
-    grid_scatter_kernel<<<b2n_grid(b2n_blocks(n, 256), 8), 256, 0, (cudaStream_t)stream>>>(indices, sigmas, n, tmp);
+    grid_scatter_kernel<<<b2n_grid(b2n_blocks(n, 256), 8), 256, 0, (cudaStream_t)stream>>>(indices, sigmas, n, tmp, n_cells);
     B2N_LAUNCH_CHECK();
     return 0;
 }
@@ -187,7 +226,9 @@ __global__ void __launch_bounds__(256) nerf_loss_kernel(const float *__restrict_
                                                         const float *__restrict__ target, int64_t n, float bg,
                                                         float lambda_opa, float loss_scale, float *__restrict__ rgb_out,
                                                         float *loss, float *__restrict__ d_rgb,
-                                                        float *__restrict__ d_opacity) {
+                                                        float *__restrict__ d_opacity,
+                                                        const float *__restrict__ loss_scale_dev) {
+    if (loss_scale_dev != nullptr) loss_scale = __ldg(loss_scale_dev);
     float part = 0.f;
     const float inv3n = 1.0f / (3.0f * (float)n), invn = 1.0f / (float)n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -221,10 +262,10 @@ __global__ void __launch_bounds__(256) nerf_loss_kernel(const float *__restrict_
 
 extern "C" int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const float *target, int64_t n_rays,
                                   float bg, float lambda_opa, float loss_scale, float *rgb_out, float *loss_dev,
-                                  float *dL_drgb, float *dL_dopacity, void *stream) {
+                                  float *dL_drgb, float *dL_dopacity, const float *loss_scale_dev, void *stream) {
     if (n_rays <= 0) return 0;
     nerf_loss_kernel<<<b2n_grid(b2n_blocks(n_rays, 256), 2), 256, 0, (cudaStream_t)stream>>>(
-        rgb, opacity, target, n_rays, bg, lambda_opa, loss_scale, rgb_out, loss_dev, dL_drgb, dL_dopacity);
+        rgb, opacity, target, n_rays, bg, lambda_opa, loss_scale, rgb_out, loss_dev, dL_drgb, dL_dopacity, loss_scale_dev);
     B2N_LAUNCH_CHECK();
     return 0;
 }

@@ -159,10 +159,19 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, 
                                                         int64_t half_hi4,
                                                         const __grid_constant__ PeerPtrs h, int world, int64_t first4,
                                                         int64_t n4, float lr, float b1, float b2, float eps,
-                                                        float inv_scale, int step, const void *__restrict__ hyper) {
+                                                        float inv_scale, int step, const b2n_hyper *__restrict__ hyper,
+                                                        const __grid_constant__ PeerPtrs hy,
+                                                        const uint32_t *__restrict__ barrier_state) {
+    // a timed-out barrier (sticky error word) means some peer's gradients are incomplete: leave everything untouched
+    if (barrier_state != nullptr && barrier_state[1] != 0u) return;
     if (hyper != nullptr) {
-        lr = *reinterpret_cast<const float *>(hyper);
-        step = reinterpret_cast<const int *>(hyper)[1];
+        lr = hyper->lr;
+        step = hyper->step - hyper->skipped;
+        int bad = hyper->found_inf;                          // GradScaler semantics: any rank's overflow skips the step
+        for (int r = 0; r < world; ++r)
+            if (hy.p[r] != nullptr) bad |= reinterpret_cast<const volatile b2n_hyper *>(hy.p[r])->found_inf;
+        if (bad) return;                                     // (the gradient vectors are cleared by the caller's memset)
+        if (hyper->loss_scale > 0.f) inv_scale /= hyper->loss_scale;
     }
     const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -201,14 +210,16 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, 
 extern "C" int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_avg_sq, void *const *grad_ptrs,
                                   void *const *grad16_ptrs, int64_t half_lo, int64_t half_hi, void *const *half_ptrs,
                                   int world, int64_t shard_first, int64_t shard_n, float lr, float beta1, float beta2,
-                                  float eps, float inv_scale, int step, const void *hyper_dev, void *stream) {
+                                  float eps, float inv_scale, int step, const b2n_hyper *hyper_dev,
+                                  void *const *hyper_ptrs, const uint32_t *barrier_state, void *stream) {
     B2N_CHECK_ARG(world >= 1 && world <= PEER_MAX_WORLD, "bad world size");
     B2N_CHECK_ARG(shard_n % 4 == 0 && shard_first % 4 == 0, "shard bounds must be multiples of 4");
     B2N_CHECK_ARG(half_lo % 4 == 0 && half_hi % 4 == 0, "fp16 range bounds must be multiples of 4");
     B2N_CHECK_ARG(step >= 1 || hyper_dev != nullptr, "step is 1-based");
     if (shard_n == 0) return 0;
-    PeerPtrs g, g16, h;
+    PeerPtrs g, g16, h, hy;
     for (int r = 0; r < PEER_MAX_WORLD; ++r) {
+        hy.p[r] = (r < world && hyper_ptrs != nullptr) ? hyper_ptrs[r] : nullptr;
         g.p[r] = r < world ? grad_ptrs[r] : nullptr;
         g16.p[r] = (r < world && grad16_ptrs != nullptr) ? grad16_ptrs[r] : nullptr;
         h.p[r] = r < world ? half_ptrs[r] : nullptr;
@@ -217,11 +228,11 @@ extern "C" int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp
     if (grad16_ptrs != nullptr && half_hi > half_lo)
         adam_peer_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, g16, half_lo / 4, half_hi / 4, h, world,
-            shard_first / 4, shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+            shard_first / 4, shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev, hy, barrier_state);
     else
         adam_peer_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
             (float4 *)param_shard, (float4 *)exp_avg, (float4 *)exp_avg_sq, g, g16, 0, 0, h, world, shard_first / 4,
-            shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+            shard_n / 4, lr, beta1, beta2, eps, inv_scale, step, hyper_dev, hy, barrier_state);
     B2N_LAUNCH_CHECK();
     return 0;
 }

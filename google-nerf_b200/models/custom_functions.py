@@ -48,17 +48,16 @@ class RayMarcher(torch.autograd.Function):
     @staticmethod
     @_bwd
     def backward(ctx, dL_drays_a, dL_dxyzs, dL_ddirs, dL_ddeltas, dL_dts, dL_dtotal_samples):
-        # per-ray segmented sums (the reference uses torch_scatter.segment_csr, custom_functions.py:108-111);
-        # the deterministic packing makes the segments contiguous and ordered, so index_add suffices
+        # per-ray segmented sums (the reference uses torch_scatter.segment_csr, custom_functions.py:108-111) in one
+        # warp-per-ray launch
         rays_a, ts = ctx.saved_tensors
         n_rays = rays_a.shape[0]
-        seg = torch.repeat_interleave(torch.arange(n_rays, device=ts.device), rays_a[:, 2])
-        zero = lambda: torch.zeros(n_rays, 3, dtype=dL_dxyzs.dtype, device=ts.device)
-        dL_drays_o = zero().index_add_(0, seg, dL_dxyzs)
-        g_d = dL_dxyzs * ts[:, None]
-        if dL_ddirs is not None:
-            g_d = g_d + dL_ddirs
-        dL_drays_d = zero().index_add_(0, seg, g_d)
+        from .. import _lib as L
+        g_x = dL_dxyzs.float().contiguous()
+        g_d = dL_ddirs.float().contiguous() if dL_ddirs is not None else None
+        dL_drays_o = torch.zeros(n_rays, 3, device=ts.device); dL_drays_d = torch.zeros(n_rays, 3, device=ts.device)
+        L.call("b2n_raymarcher_bw", L.ptr(g_x), L.ptr(g_d), L.ptr(ts), L.ptr(rays_a), n_rays, L.ptr(dL_drays_o),
+               L.ptr(dL_drays_d))
         return dL_drays_o, dL_drays_d, None, None, None, None, None, None, None
 
 

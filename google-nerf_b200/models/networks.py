@@ -18,8 +18,56 @@ from torch import nn
 from .. import _lib as L
 from .. import tinycudann as tcnn
 from .. import vren
+from torch.amp import custom_bwd, custom_fwd
+
 from .custom_functions import TruncExp
 from .rendering import NEAR_DISTANCE
+
+
+class _FieldFn(torch.autograd.Function):
+    """NGP.forward (networks.py:102-117) as ONE autograd node on the fused kernels: encode (hash-grid gather or
+    frequency) -> b2n_field_mlp_fw, and b2n_field_mlp_bw -> hash-grid scatter on the way back.  No eager
+    normalise / cat / exp launches; the only saved activations are enc and h.  Gradients are computed at tcnn's
+    loss scale (128) and returned unscaled in fp32; a gradient that leaves the fp16 range on the way is reported as
+    inf in the returned parameter gradient, which is what a GradScaler (precision=16, train.py:265) keys on."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, d, xyz_params, rgb_params, model):
+        L.require_cuda(x, d, xyz_params, rgb_params)
+        x, d = x.contiguous(), d.contiguous()
+        p16, image = model._fused_state(x.device)
+        n, dev = x.shape[0], x.device
+        enc = model._encode(x, p16)
+        sigmas = torch.empty(n, device=dev); rgbs = torch.empty(n, 3, device=dev)
+        h = torch.empty(n, 16, dtype=torch.float16, device=dev)
+        L.call("b2n_field_mlp_fw", L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, None, L.ptr(sigmas), L.ptr(rgbs),
+               L.ptr(h))
+        ctx.model = model
+        ctx.save_for_backward(x, d, enc, h, rgbs, image)
+        return sigmas, rgbs.to(torch.float16)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dL_dsigmas, dL_drgbs):
+        model = ctx.model
+        x, d, enc, h, rgbs, image = ctx.saved_tensors
+        n, dev, S = x.shape[0], x.device, tcnn.LOSS_SCALE
+        xe = model.xyz_encoder
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        ds = (dL_dsigmas.float() * S).contiguous() if dL_dsigmas is not None else z(n)
+        dc = (dL_drgbs.float() * S).contiguous() if dL_drgbs is not None else z(n, 3)
+        g_xyz, g_rgb = z(xe.params.numel()), z(model.rgb_net.params.numel())
+        hashed = model.encoding == "HashGrid"
+        denc = torch.empty(n, 32, dtype=torch.float16, device=dev) if hashed else None
+        found = torch.zeros(1, dtype=torch.int32, device=dev)
+        L.call("b2n_field_mlp_bw", L.ptr(ds), L.ptr(dc), L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, None,
+               L.ptr(rgbs), L.ptr(h), 1.0 / S, L.ptr(denc), L.ptr(g_xyz), L.ptr(g_rgb), None, 0, L.ptr(found))
+        if hashed:
+            L.call("b2n_hashgrid_bw", L.ptr(x), L.ptr(denc), 32, model._layout, n, None, 1.0 / S,
+                   L.ptr(g_xyz[xe.mlp.n_params:]), None)
+        g_rgb[:1] += torch.where(found > 0, float("inf"), 0.0)
+        return None, None, g_xyz, g_rgb, None
 
 
 class NGP(nn.Module):
@@ -56,10 +104,18 @@ class NGP(nn.Module):
             network_config={"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "Sigmoid",
                             "n_neurons": 64, "n_hidden_layers": 2})
         self.sigma_act = TruncExp.apply
+        # first-layer width of the fused field kernels: 16 levels x 2 features, or Frequency-12 padded to 80
+        self.k1 = self.xyz_encoder.mlp.in_width
+        if self.k1 not in (32, 80):
+            raise ValueError("the fused field kernels are built for 16 hash levels x 2 features or Frequency-12")
+        self._image = self._image_key = self._layout = None
 
     # ------------------------------------------------------------------ field
     def density(self, x, return_feat=False):
         """x (N,3) in [-scale, scale] -> sigmas (N) fp32 [, h (N,16) fp16]."""
+        if x.is_cuda and not (torch.is_grad_enabled() and self.xyz_encoder.params.requires_grad):
+            sigmas, h = self._density_fused(x.contiguous().float(), want_h=return_feat)
+            return (sigmas, h) if return_feat else sigmas
         x = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
         h = self.xyz_encoder(x)
         sigmas = self.sigma_act(h[:, 0]).float()
@@ -68,54 +124,83 @@ class NGP(nn.Module):
         return sigmas
 
     def forward(self, x, d):
-        """x (N,3) positions, d (N,3) directions (normalised IN PLACE like the reference, networks.py:113)
-        -> sigmas (N) fp32, rgbs (N,3) fp16."""
-        if self.encoding == "HashGrid" and not torch.is_grad_enabled() and x.is_cuda:
-            return self._forward_fused(x, d)
-        sigmas, h = self.density(x, return_feat=True)
-        d /= torch.norm(d, dim=-1, keepdim=True)
-        d = self.dir_encoder((d + 1) / 2)
-        rgbs = self.rgb_net(torch.cat([d, h], 1))
-        return sigmas, rgbs
+        """x (N,3) positions, d (N,3) directions -> sigmas (N) fp32, rgbs (N,3) fp16.  One fused autograd node
+        (or, without grad, the bare kernels).  The reference normalises d IN PLACE (networks.py:113); here the
+        normalisation happens inside the kernel and d is left as it was."""
+        if not x.is_cuda:
+            raise RuntimeError("google-nerf_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        xe, rn = self.xyz_encoder.params, self.rgb_net.params
+        if torch.is_grad_enabled() and (xe.requires_grad or rn.requires_grad):
+            return _FieldFn.apply(x, d, xe, rn, self)
+        return self._forward_fused(x, d)
 
     def _fused_state(self, device):
+        """(fp16 parameter copy of xyz_encoder, canonical weight image).  The image lives in ONE buffer per model that
+        is never reallocated (captured CUDA graphs keep pointing at it) and is re-packed in place when the fp16
+        copies change; a trainer may adopt it (`adopt_image`) and keep it current itself."""
         xe, rn = self.xyz_encoder, self.rgb_net
         p16, r16 = xe.half_params(), rn.half_params()
-        key = (xe._p16_key, rn._p16_key)
-        if getattr(self, "_image_key", None) != key:
-            self._image = torch.empty(10240, dtype=torch.float16, device=device)
-            L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image))
-            self._image_key = key
-            self._layout = L.GridLayout.from_buffer_copy(xe.enc.layout)
+        if self._image is None or self._image.device != device:
+            self._image = torch.empty(64 * self.k1 + 8192, dtype=torch.float16, device=device)
+            self._image_key = None
+        if self._layout is None and self.encoding == "HashGrid":
+            self._layout = L.GridLayout.from_buffer_copy(xe.enc.layout)      # NGP.density's box normalisation folded in
             self._layout.x_offset = -float(self.scale)
             self._layout.x_scale = 1.0 / (2.0 * float(self.scale))
+        key = (xe._p16_key, rn._p16_key, p16.data_ptr(), r16.data_ptr())
+        if self._image_key != key:
+            L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image), self.k1)
+            self._image_key = key
         return p16, self._image
 
+    def adopt_image(self, image):
+        """A trainer that re-packs `image` after every optimiser step hands it over: the model's fused paths (and
+        graphs captured over them) read that buffer from now on."""
+        xe, rn = self.xyz_encoder, self.rgb_net
+        p16, r16 = xe.half_params(), rn.half_params()
+        self._image = image
+        self._image_key = (xe._p16_key, rn._p16_key, p16.data_ptr(), r16.data_ptr())
+        self._fused_state(image.device)
+
+    def _encode(self, x, p16, out=None, n_dev=None, unit_cube=False):
+        """positions (N,3) fp32 (world, or already in [0,1]^3 when unit_cube) -> encoded features (N,k1) fp16."""
+        xe = self.xyz_encoder
+        n = x.shape[0]
+        if out is None:
+            out = torch.empty(n, self.k1, dtype=torch.float16, device=x.device)
+        if self.encoding == "HashGrid":
+            L.call("b2n_hashgrid_fw", L.ptr(x), L.ptr(p16[xe.mlp.n_params:]), xe.enc.layout if unit_cube else self._layout,
+                   n, L.ptr(n_dev), L.ptr(out), self.k1)
+        else:
+            lo, ext = (0.0, 1.0) if unit_cube else (-float(self.scale), 2.0 * float(self.scale))
+            L.call("b2n_frequency_fw", L.ptr(x), 12, n, L.ptr(n_dev), L.ptr(out), self.k1, lo, ext)
+        return out
+
+    def _density_fused(self, x, want_h=False, unit_cube=False):
+        """sigma (and optionally h) through the encode kernel + the density half of the fused tcgen05 kernel."""
+        p16, image = self._fused_state(x.device)
+        n = x.shape[0]
+        enc = self._encode(x, p16, unit_cube=unit_cube)
+        sigmas = torch.empty(n, device=x.device)
+        h = torch.empty(n, 16, dtype=torch.float16, device=x.device) if want_h else None
+        L.call("b2n_field_mlp_fw", L.ptr(enc), self.k1, None, L.ptr(image), n, None, L.ptr(sigmas), None, L.ptr(h))
+        return sigmas, h
+
     def _density_fused01(self, x01):
-        """sigma at positions already normalised to [0,1]^3 (occupancy-grid update): hash gather + the density half
-        of the fused tcgen05 kernel."""
-        p16, image = self._fused_state(x01.device)
-        n = x01.shape[0]
-        enc = torch.empty(n, 32, dtype=torch.float16, device=x01.device)
-        sigmas = torch.empty(n, device=x01.device)
-        L.call("b2n_hashgrid_fw", L.ptr(x01), L.ptr(p16[self.xyz_encoder.mlp.n_params:]), self.xyz_encoder.enc.layout, n,
-               None, L.ptr(enc), 32)
-        L.call("b2n_field_mlp_fw", L.ptr(enc), None, L.ptr(image), n, None, L.ptr(sigmas), None, None, None, None)
-        return sigmas
+        """sigma at positions already normalised to [0,1]^3 (occupancy-grid update)."""
+        return self._density_fused(x01, unit_cube=True)[0]
 
     def _forward_fused(self, x, d, rgb_fp32=False):
-        """Inference path (no autograd): hash-grid gather + ONE fused tcgen05 kernel for both MLPs, SH and the
-        activations.  Same outputs as the modular path (sigmas fp32, rgbs fp16); the box normalisation and the
-        direction normalisation happen inside the kernels, so `d` is left untouched here."""
-        xe = self.xyz_encoder
-        p16, _ = self._fused_state(x.device)
+        """Inference path (no autograd): encode + ONE fused tcgen05 kernel for both MLPs, SH and the activations.
+        Same outputs as the reference (sigmas fp32, rgbs fp16); the box normalisation and the direction normalisation
+        happen inside the kernels, so `d` is left untouched here."""
+        p16, image = self._fused_state(x.device)
         x = x.contiguous().float(); d = d.contiguous().float()
         n = x.shape[0]
-        enc = torch.empty(n, 32, dtype=torch.float16, device=x.device)
+        enc = self._encode(x, p16)
         sigmas = torch.empty(n, device=x.device); rgbs = torch.empty(n, 3, device=x.device)
-        L.call("b2n_hashgrid_fw", L.ptr(x), L.ptr(p16[xe.mlp.n_params:]), self._layout, n, None, L.ptr(enc), 32)
-        L.call("b2n_field_mlp_fw", L.ptr(enc), L.ptr(d), L.ptr(self._image), n, None, L.ptr(sigmas), L.ptr(rgbs),
-               None, None, None)
+        L.call("b2n_field_mlp_fw", L.ptr(enc), self.k1, L.ptr(d), L.ptr(image), n, None, L.ptr(sigmas), L.ptr(rgbs),
+               None)
         return sigmas, (rgbs if rgb_fp32 else rgbs.to(torch.float16))   # values are fp16-rounded either way
 
     # ------------------------------------------------------------------ occupancy grid
@@ -151,7 +236,9 @@ class NGP(nn.Module):
             cs = torch.cumsum(self.density_grid[c] > 0, 0, dtype=torch.int32)
             k = (torch.rand(M, device=dev) * cs[-1]).to(torch.int32)
             k = torch.minimum(k, (cs[-1] - 1).clamp(min=0))
-            indices2 = torch.searchsorted(cs, k, right=True)
+            # a cascade without any occupied cell (cs[-1] == 0; the reference's randint(0) raises there,
+            # networks.py:151) would make the search return G^3: clamp, the draw then degenerates to a harmless repeat
+            indices2 = torch.searchsorted(cs, k, right=True).clamp_(max=self.grid_size ** 3 - 1)
             # the order of the cells is immaterial (each one scatters into its own slot), so evaluate them in Morton
             # order: neighbouring cells share hash-grid corners, which turns most of the coarse-level gathers of the
             # 1M-cell density query into L1 hits
@@ -162,43 +249,34 @@ class NGP(nn.Module):
     @torch.no_grad()
     def mark_invisible_cells(self, K, poses, img_wh, chunk=64 ** 3):
         """Cells no training camera sees (or that sit closer than NEAR_DISTANCE to one) get density -1 and are
-        never updated (networks.py:159-214).  One-time torch ops."""
-        w2c_R = poses[:, :3, :3].transpose(1, 2)                       # (N,3,3)
-        w2c_T = -torch.bmm(w2c_R, poses[:, :3, 3:])                    # (N,3,1)
-        cells = self.get_all_cells()
-        G = self.grid_size
-        for c in range(self.cascades):
-            indices, coords = cells[c]
-            s = min(2 ** (c - 1), self.scale)
-            half_grid_size = s / G
-            for i in range(0, len(indices), chunk):
-                xyzs = coords[i:i + chunk] / (G - 1) * 2 - 1
-                xyzs_w = (xyzs * (s - half_grid_size)).T               # (3,chunk)
-                xyzs_c = w2c_R @ xyzs_w[None] + w2c_T                  # (N,3,chunk)
-                uvd = K @ xyzs_c
-                uv = uvd[:, :2] / uvd[:, 2:]
-                in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & \
-                           (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
-                covered = ((uvd[:, 2] >= NEAR_DISTANCE) & in_image).any(0)
-                too_near = ((uvd[:, 2] < NEAR_DISTANCE) & in_image).any(0)
-                valid = covered & ~too_near
-                self.density_grid[c, indices[i:i + chunk]] = torch.where(valid, 0., -1.)
+        never updated (networks.py:159-214).  One kernel launch: a thread per cell walks the cameras (`chunk`, the
+        reference's bmm chunk size, is accepted and unused)."""
+        L.require_cuda(self.density_grid)
+        K = K.to(self.density_grid.device, torch.float32).contiguous()
+        poses = poses.to(self.density_grid.device, torch.float32)[:, :3, :4].contiguous()
+        if not self.density_grid.is_contiguous():
+            self.density_grid = self.density_grid.contiguous()
+        L.call("b2n_mark_invisible_cells", L.ptr(K), L.ptr(poses), poses.shape[0], int(img_wh[0]), int(img_wh[1]),
+               NEAR_DISTANCE, self.grid_size, self.cascades, float(self.scale), L.ptr(self.density_grid))
 
     @torch.no_grad()
-    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False, shard=None, reduce_tmp=None):
+    def update_density_grid(self, density_threshold, warmup=False, decay=0.95, erode=False, shard=None, reduce_tmp=None,
+                            cells=None, noise=None):
         """EMA-max update of the cascaded density grid from fresh field samples, then re-pack the bitfield
         (networks.py:216-252).  The mean/threshold stays on the device (no .item() sync).
 
         Data parallel (SURVEY 8e "occupancy update"): shard=(rank, world) makes this rank evaluate 1/world of the
         cells and reduce_tmp(tmp) must max-reduce the sampled densities over the ranks before they are merged, so
-        that all ranks keep identical grids while the field evaluations are shared out."""
-        self._grid_eval(warmup, shard)
+        that all ranks keep identical grids while the field evaluations are shared out.
+        cells / noise (parity tests): the per-cascade (indices, coords) lists and (n,3) jitter tensors to use instead of
+        drawing them here (the reference draws both with torch's global RNG, networks.py:221-231)."""
+        self._grid_eval(warmup, shard, cells, noise)
         if reduce_tmp is not None:
             reduce_tmp(self._grid_tmp)
         self._grid_commit(density_threshold, decay, erode)
 
     @torch.no_grad()
-    def _grid_eval(self, warmup, shard=None):
+    def _grid_eval(self, warmup, shard=None, cells=None, noise_in=None):
         """Densities at jittered positions inside the selected cells -> self._grid_tmp (0 where not sampled)."""
         G = self.grid_size
         rank, world = shard if shard is not None else (0, 1)
@@ -207,7 +285,9 @@ class NGP(nn.Module):
             self._grid_tmp = torch.zeros_like(self.density_grid)
         tmp = self._grid_tmp
         tmp.zero_()
-        if warmup:
+        if cells is not None:
+            pass
+        elif warmup:
             cells = self.get_all_cells()
             if world > 1:                                    # a contiguous slice of all cells per rank
                 n = G ** 3
@@ -219,15 +299,13 @@ class NGP(nn.Module):
         for c in range(self.cascades):
             indices, coords = cells[c]
             s = min(2 ** (c - 1), self.scale)
-            noise = torch.rand(coords.shape[0], 3, device=coords.device)
+            noise = torch.rand(coords.shape[0], 3, device=coords.device) if noise_in is None else noise_in[c].contiguous()
             xyz01 = torch.empty(coords.shape[0], 3, device=coords.device)
             L.call("b2n_grid_cell_positions", L.ptr(coords.contiguous()), L.ptr(noise), coords.shape[0], G, float(s),
                    lo, hi, 1, L.ptr(xyz01))
-            if self.encoding == "HashGrid":
-                sigmas = self._density_fused01(xyz01)
-            else:
-                sigmas = torch.exp(self.xyz_encoder(xyz01)[:, 0].float())
-            L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]))
+            sigmas = self._density_fused01(xyz01)
+            L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]),
+                   tmp.shape[1])
 
     @torch.no_grad()
     def _grid_commit(self, density_threshold, decay=0.95, erode=False):

@@ -48,7 +48,7 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     hits = hits_t[:, 0]                                   # (N_rays,2) view, advanced in place by the marcher
 
     samples = total_samples = 0
-    fused = getattr(model, "encoding", None) == "HashGrid" and hasattr(model, "_forward_fused")
+    fused = hasattr(model, "_forward_fused")            # this repo's NGP (HashGrid or Frequency): fused field kernels
     if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
         return _DeviceLoop.get(model, N_rays, exp_step_factor, T_threshold).run(rays_o, rays_d, hits)
     alive_indices = torch.arange(N_rays, device=device)
@@ -115,7 +115,7 @@ class _DeviceLoop:
         self.alive = f(2, n, dt=torch.int64); self.arange = torch.arange(n, device=dev)
         self.n_eff = f(n, dt=torch.int32)
         self.xyzs, self.dirs, self.deltas, self.ts = f(cap, 3), f(cap, 3), f(cap), f(cap)
-        self.enc = f(cap, 32, dt=torch.float16); self.sigmas, self.rgbs = f(cap), f(cap, 3)
+        self.enc = f(cap, model.k1, dt=torch.float16); self.sigmas, self.rgbs = f(cap), f(cap, 3)
         self.opacity, self.depth, self.rgb = f(n), f(n), f(n, 3)
         self.ctl = torch.zeros(8, dtype=torch.int32, device=dev)
         self.ctl_init = torch.tensor([0, 0, 0, 0, n, 0, 0, 0], dtype=torch.int32, device=dev)
@@ -136,9 +136,9 @@ class _DeviceLoop:
         call("b2n_raymarching_test_dev", P(self.rays_o), P(self.rays_d), P(self.hits), P(self.alive[cur]),
              P(m.density_bitfield), m.cascades, float(m.scale), self.esf, m.grid_size, MAX_SAMPLES, n, P(self.ctl),
              P(self.xyzs), P(self.dirs), P(self.deltas), P(self.ts), P(self.n_eff))
-        call("b2n_hashgrid_fw", P(self.xyzs), P(p16[m.xyz_encoder.mlp.n_params:]), m._layout, cap, P(slots), P(self.enc), 32)
-        call("b2n_field_mlp_fw", P(self.enc), P(self.dirs), P(image), cap, P(slots), P(self.sigmas), P(self.rgbs),
-             None, None, None)
+        m._encode(self.xyzs, p16, out=self.enc, n_dev=slots)
+        call("b2n_field_mlp_fw", P(self.enc), m.k1, P(self.dirs), P(image), cap, P(slots), P(self.sigmas), P(self.rgbs),
+             None)
         call("b2n_composite_test_fw_dev", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.alive[cur]),
              P(self.alive[1 - cur]), self.T, P(self.n_eff), n, P(self.ctl), P(self.opacity), P(self.depth), P(self.rgb))
 

@@ -47,11 +47,12 @@ def hashgrid_bw(x, dy16, layout, grad_table, grad_scale, n_dev=None):
            float(grad_scale), L.ptr(grad_table), None)
 
 
-def frequency_fw(x, n_frequencies, out=None, n_dev=None):
+def frequency_fw(x, n_frequencies, out=None, n_dev=None, x_min=0.0, x_extent=1.0):
     width = _pad16(3 * n_frequencies * 2)
     if out is None:
         out = torch.empty(x.shape[0], width, dtype=_f16, device=x.device)
-    L.call("b2n_frequency_fw", L.ptr(x), int(n_frequencies), x.shape[0], L.ptr(n_dev), L.ptr(out), out.stride(0))
+    L.call("b2n_frequency_fw", L.ptr(x), int(n_frequencies), x.shape[0], L.ptr(n_dev), L.ptr(out), out.stride(0),
+           float(x_min), float(x_extent))
     return out
 
 

@@ -51,11 +51,17 @@ class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
-                 march_ctas_per_sm=None, comm=None, comm_in_graph=False, grad_fp16=None):
-        if model.encoding != "HashGrid":
-            raise ValueError("NGPTrainer drives the HashGrid configuration; the Frequency variant trains through "
-                             "render() + autograd")
+                 comm=None, comm_in_graph=False, grad_fp16=None, erode=False, scale_growth_interval=0,
+                 serialize_mma=False):
+        """model: NGP with either encoding (HashGrid: networks.py:39-47; Frequency: networks.py:49-53).
+        erode: the reference passes erode=True for colmap scenes (train.py:148).  loss_scale: start value of the
+        device-side loss scaler (tcnn's fixed 128); an overflow in the fp16 backward pass skips that optimiser step and
+        halves it like GradScaler (train.py:265 precision=16), scale_growth_interval > 0 doubles it again after that
+        many clean steps (GradScaler's growth; 0 keeps tcnn's behaviour of never growing)."""
         self.model, self.n_rays = model, n_rays
+        self.hashed = model.encoding == "HashGrid"
+        self.k1 = model.k1
+        self.erode, self.serialize_mma = bool(erode), int(bool(serialize_mma))
         self.dev = model.center.device
         if self.dev.type != "cuda":
             raise RuntimeError("NGPTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -64,8 +70,9 @@ class NGPTrainer:
         self.esf, self.T_threshold, self.lambda_opa, self.loss_scale = exp_step_factor, T_threshold, lambda_opa, loss_scale
         self.bg = 1.0 if exp_step_factor == 0 else 0.0
         self.capacity = int(n_rays * samples_per_ray)
-        torch.cuda.manual_seed(seed)
+        self.scale_growth_interval = int(scale_growth_interval)
         self.fixed_noise = None                   # parity tests pin the per-ray jitter here
+        self.fixed_grid_noise = None              # ... and the occupancy update's per-cascade (G^3,3) cell jitter here
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (data_parallel and dist.is_available() and dist.is_initialized()) else 1
         self.S, self.warmup_steps = grid_update_interval, warmup_steps
@@ -79,12 +86,14 @@ class NGPTrainer:
         # pays once a batch has enough rays to fill the machine with threads (measured at 8192 rays: the tail of the
         # longest rays outlasts the training step, 0.47 vs 0.415 ms/step)
         self.serial_prefetch = os.environ.get("B2N_SERIAL_PREFETCH", "1" if n_rays >= 65536 else "0") == "1"
-        self.march_ctas = int(march_ctas_per_sm if march_ctas_per_sm is not None else os.environ.get("B2N_MARCH_CTAS", 8))
 
         xe, rn = model.xyz_encoder, model.rgb_net
         self.n_mlp = xe.mlp.n_params
         z = lambda t: torch.zeros_like(t)
         self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        # every rank draws its own jitter / occupancy cells: the sharded occupancy update relies on the ranks sampling
+        # different cells (M / world each) before the max-reduce
+        torch.cuda.manual_seed(seed + self.rank)
         n_xyz, n_rgb = xe.params.numel(), rn.params.numel()
         # All trainable parameters live in ONE flat vector [xyz_encoder (MLP + hash table) | rgb_net | pad]: one Adam
         # launch, and for world > 1 one exchange.  Sharded optimiser (world > 1): the vector is padded to world * shard;
@@ -113,7 +122,7 @@ class NGPTrainer:
             # local pack pass (which also clears the fp32 vector); measured to pay from 4 ranks up
             self.grad_fp16 = os.environ.get("B2N_GRAD_FP16", "1" if self.world >= 4 else "0") == "1" \
                 if grad_fp16 is None else bool(grad_fp16)
-            regions = {"g": (_f32, self.n_pad), "h": (_f16, self.n_pad)}
+            regions = {"g": (_f32, self.n_pad), "h": (_f16, self.n_pad), "hy": (torch.int32, 8)}
             if self.grad_fp16:
                 regions["g16"] = (_f16, self.n_pad)
             try:
@@ -135,11 +144,8 @@ class NGPTrainer:
             self.g_all = self._gh[:4 * self.n_pad].view(_f32)
             self.h_all = self._gh[4 * self.n_pad:].view(_f16)
             self.h_all.copy_(tc.cast_half(p_pad))
-        # L2 persistence window over both (b2n_set_l2_persist): measured NEGATIVE on B200 (0.460 vs 0.418 ms/step: the
-        # 69 MB carve-out halves the L2 left for write-combining the activation stream, field_mlp_fw 50 -> 91 us), so
-        # it stays off unless asked for
-        if os.environ.get("B2N_L2_PERSIST", "0") == "1":
-            L.call_nostream("b2n_set_l2_persist", L.ptr(self.g_all), 6 * self.n_pad)
+        # (an L2 persistence window over gradient + fp16 copy was measured NEGATIVE on B200 in round 1 -- 0.460 vs
+        # 0.418 ms/step: the 69 MB carve-out halves the L2 left for write-combining the activation stream -- and is gone)
         self.g_xyz, self.g_rgb = self.g_all[:n_xyz], self.g_all[n_xyz:n_all]
         self.p_shard = p_pad[lo:lo + self.shard]
         self.g_shard = torch.zeros(self.shard, dtype=_f32, device=self.dev) if self.comm == "nccl" else \
@@ -151,13 +157,22 @@ class NGPTrainer:
         # GPUs, but communicator teardown after captured collectives hung on this stack, so the default keeps them
         # eager between two graphs.
         self.comm_in_graph = comm_in_graph
-        self.hyper = torch.zeros(2, dtype=torch.int32, device=self.dev)        # {float lr; int32 step}
-        self.w_image = torch.empty(10240, dtype=_f16, device=self.dev)
+        # b2n_hyper (include/b2n.h): {lr, step, found_inf, skipped, loss_scale, good_steps, growth_interval, -}; in
+        # peer memory when ranks exchange through it (an overflow on ANY rank skips the step on all of them)
+        self.hyper = self.peer.tensor("hy") if self.comm == "p2p" else torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.hyper.copy_(torch.tensor([0, 0, 0, 0, struct.unpack("i", struct.pack("f", float(loss_scale)))[0], 0,
+                                       self.scale_growth_interval, 0], dtype=torch.int32))
+        self.w_image = torch.empty(64 * self.k1 + 8192, dtype=_f16, device=self.dev)
         self._pack_weights()
+        self.sync_model_half()                    # the model's fused paths read the fp16 copies / image kept current here
         # fold NGP.density's box normalisation (networks.py:96) into the hash-grid kernels
-        self.layout = L.GridLayout.from_buffer_copy(xe.enc.layout)
-        self.layout.x_offset = -float(model.scale)
-        self.layout.x_scale = 1.0 / (2.0 * float(model.scale))
+        self.layout = model._layout
+        self._peer_err = None
+        if self.comm == "p2p":
+            self._peer_err = (torch.zeros(2, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+            self._peer_err_pending = False
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(group=process_group)     # every rank's control block is initialised before anyone reads it
         self._alloc()
 
     # ------------------------------------------------------------------ buffers
@@ -166,8 +181,8 @@ class NGPTrainer:
         e = lambda *s, dt=_f32: torch.empty(*s, dtype=dt, device=dev)
         self.sets = [_SampleSet(n, cap, dev), _SampleSet(n, cap, dev)]
         self.cur = 0
-        self.enc = e(cap, 32, dt=_f16); self.hid_s = e(cap, 64, dt=_f16); self.h = e(cap, 16, dt=_f16)
-        self.hid_r = e(2, cap, 64, dt=_f16)
+        # saved activations: enc and h only (the hidden layers are recomputed by the backward kernel)
+        self.enc = e(cap, self.k1, dt=_f16); self.h = e(cap, 16, dt=_f16)
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
         self.opacity, self.depth = e(n), e(n)
         self.rgb_out = e(n, 3)
@@ -175,7 +190,7 @@ class NGPTrainer:
         self._scalars = torch.zeros(4, dtype=torch.int32, device=dev)
         self.alive_cnt, self.loss = self._scalars[0:1], self._scalars[1:2].view(_f32)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
-        self.din_enc = e(cap, 32, dt=_f16)
+        self.din_enc = e(cap, 32, dt=_f16) if self.hashed else None
         self.alive_idx = e(cap, dt=torch.int32)
         self.last_counter = self.sets[0].counter
         self.graphs = {}
@@ -187,7 +202,6 @@ class NGPTrainer:
         takes ~10x fewer issue slots away from the training kernels than the warp-per-ray form)."""
         m, P, call = self.model, L.ptr, L.call
         n, cap = self.n_rays, self.capacity
-        L.call_nostream("b2n_set_march_ctas_per_sm", self.march_ctas)    # grid size is baked into a captured graph
         if self._from_indices:
             # get_rays (datasets/ray_utils.py:152-175): rotate camera-frame directions, origin = camera centre
             call("b2n_rays_from_indices", P(self.directions), P(self.poses), P(s.img_idxs), P(s.pix_idxs), n,
@@ -208,35 +222,44 @@ class NGPTrainer:
     def _forward_backward(self, s):
         P, call = L.ptr, L.call
         n, cap, nd = self.n_rays, self.capacity, s.counter
-        # field forward: hash-grid gather, then the fused tcgen05 MLP chain (sigma + colour)
-        call("b2n_hashgrid_fw", P(s.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
-        call("b2n_field_mlp_fw", P(self.enc), P(s.dirs), P(self.w_image), cap, P(nd), P(self.sigmas), P(self.rgbs),
-             P(self.hid_s), P(self.h), P(self.hid_r))
-        # compositing + loss
+        # field forward: encode (hash-grid gather / frequency), then the fused tcgen05 MLP chain (sigma + colour)
+        if self.hashed:
+            call("b2n_hashgrid_fw", P(s.xyzs), P(self.h_xyz[self.n_mlp:]), self.layout, cap, P(nd), P(self.enc), 32)
+        else:
+            call("b2n_frequency_fw", P(s.xyzs), 12, cap, P(nd), P(self.enc), self.k1, -float(self.model.scale),
+                 2.0 * float(self.model.scale))
+        call("b2n_field_mlp_fw", P(self.enc), self.k1, P(s.dirs), P(self.w_image), cap, P(nd), P(self.sigmas),
+             P(self.rgbs), P(self.h))
+        # compositing + loss (the loss scale is read from the device-side scaler)
         call("b2n_composite_loss_fwbw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(s.target),
              self.T_threshold, n, self.bg, self.lambda_opa, self.loss_scale, P(self.opacity), P(self.depth),
              P(self.rgb_out), P(self.loss), P(self.dL_dsigmas), P(self.dL_drgbs), P(self.alive_idx),
-             P(self.alive_cnt))
-        # field backward (gradients carry loss_scale; parameter gradients are unscaled inside Adam)
+             P(self.alive_cnt), P(self.hyper[4:]))
+        # field backward (gradients carry the loss scale; parameter gradients are unscaled inside Adam)
         # only the samples composited before each ray's early stop carry gradient: the two heavy backward kernels
         # run over that compacted list (alive_cnt is a device-side count)
-        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), P(s.dirs), P(self.w_image), cap,
-             P(self.alive_cnt), P(self.rgbs), P(self.hid_s), P(self.h), P(self.hid_r), 1.0, P(self.din_enc),
-             P(self.g_xyz), P(self.g_rgb), P(self.alive_idx), cap)
-        call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(self.alive_cnt), 1.0,
-             P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
+        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), self.k1, P(s.dirs), P(self.w_image),
+             cap, P(self.alive_cnt), P(self.rgbs), P(self.h), 1.0, P(self.din_enc), P(self.g_xyz), P(self.g_rgb),
+             P(self.alive_idx), self.serialize_mma, P(self.hyper[2:]))
+        if self.hashed:
+            call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(self.alive_cnt), 1.0,
+                 P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
 
     def _reduce_grads(self):
-        """comm == "nccl": sum the gradients over ranks; every rank keeps its shard (reduce-scatter)."""
+        """comm == "nccl": sum the gradients over ranks; every rank keeps its shard (reduce-scatter).  The overflow
+        flags are max-reduced so that every rank skips (or takes) the step together."""
         dist.reduce_scatter_tensor(self.g_shard, self.g_all, op=dist.ReduceOp.SUM, group=self.pg)
+        dist.all_reduce(self.hyper[2:3], op=dist.ReduceOp.MAX, group=self.pg)
 
     def _optimizer(self):
         """Adam on this rank's shard from the (already reduced, or local) gradient shard."""
         P, call = L.ptr, L.call
-        inv = 1.0 / (self.loss_scale * self.world)
+        inv = 1.0 / self.world                               # the loss scale is divided out from the device block
         b1, b2 = self.betas
         call("b2n_adam_step", P(self.p_shard), P(self.g_shard), P(self.m), P(self.v), P(self.h_shard), self.shard,
              self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
+        call("b2n_scaler_update", P(self.hyper), None, 1)
+        self.hyper[2:3].zero_()                              # found_inf consumed
         if self.world == 1:
             self._pack_weights()
         else:
@@ -252,7 +275,7 @@ class NGPTrainer:
         peer loads, runs Adam on the local master shard and stores the fp16 result into every rank's working copy;
         barrier; clear the local gradient vector; re-pack the MLP image."""
         P, call, pb = L.ptr, L.call, self.peer
-        inv = 1.0 / (self.loss_scale * self.world)
+        inv = 1.0 / self.world
         b1, b2 = self.betas
         lo16, hi16 = self.n_mlp, self.p_xyz.numel()           # the hash table; the MLP weights stay fp32 on the wire
         if self.grad_fp16:
@@ -260,8 +283,11 @@ class NGPTrainer:
         pb.barrier()
         call("b2n_adam_step_peer", P(self.p_shard), P(self.m), P(self.v), pb.table("g"),
              pb.table("g16") if self.grad_fp16 else None, lo16, hi16 if self.grad_fp16 else lo16, pb.table("h"),
-             self.world, self.rank * self.shard, self.shard, self.lr, b1, b2, self.eps, inv, 1, P(self.hyper))
+             self.world, self.rank * self.shard, self.shard, self.lr, b1, b2, self.eps, inv, 1, P(self.hyper),
+             pb.table("hy"), P(pb.state))
+        call("b2n_scaler_update", P(self.hyper), pb.table("hy"), self.world)     # same OR on every rank
         pb.barrier()
+        self.hyper[2:3].zero_()                              # every rank has read every flag
         if self.grad_fp16:
             self.g_all[:lo16].zero_(); self.g_all[hi16:].zero_()
         else:
@@ -270,7 +296,7 @@ class NGPTrainer:
 
     def _pack_weights(self):
         """fp16 MLP weights -> UMMA canonical shared-memory image for the fused field kernels."""
-        L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image))
+        L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image), self.k1)
 
     def _train(self, p):
         """Forward, backward and the optimiser on sample set p (world > 1: with the gradient reduce-scatter and the
@@ -300,7 +326,8 @@ class NGPTrainer:
     def _capture(self, fn, touches_params, touches_grid=False):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
-        state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all) + ((self.g_shard,) if self.comm == "nccl" else ())
+        state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all, self.hyper) + \
+            ((self.g_shard,) if self.comm == "nccl" else ())
         if touches_grid:
             if getattr(self.model, "_grid_tmp", None) is None:        # the persistent scratch grid of the update
                 self.model._grid_tmp = torch.zeros_like(self.model.density_grid)
@@ -355,8 +382,10 @@ class NGPTrainer:
         self._load(self.sets[self.cur], (rays_o, rays_d, target_rgb))
 
     def _set_hyper(self):
+        # a fresh pageable tensor per step: the driver stages the copy at once, so the host may run many graph replays
+        # ahead without ever overwriting a value the GPU has not consumed yet
         packed = struct.unpack("i", struct.pack("f", float(self.lr)))[0]
-        self.hyper.copy_(torch.tensor([packed, self.step_count], dtype=torch.int32), non_blocking=True)
+        self.hyper[:2].copy_(torch.tensor([packed, self.step_count], dtype=torch.int32), non_blocking=True)
 
     def step(self, rays_o=None, rays_d=None, target_rgb=None, next_batch=None):
         """One optimisation step on the given (or previously set / pre-marched) batch.  `next_batch`, if given, is
@@ -419,17 +448,48 @@ class NGPTrainer:
         m, w = self.model, bool(warmup)
         self.sync_model_half()
         if self.world == 1:
-            self._run(("grid", w), lambda: m.update_density_grid(thr, warmup=w, erode=False))
+            self._run(("grid", w), lambda: m.update_density_grid(thr, warmup=w, erode=self.erode,
+                                                                 noise=self.fixed_grid_noise if w else None))
             return
+        self._check_peer()
         self._run(("grid_eval", w), lambda: m._grid_eval(w, (self.rank, self.world)))
         dist.all_reduce(m._grid_tmp, op=dist.ReduceOp.MAX, group=self.pg)
-        self._run(("grid_commit",), lambda: m._grid_commit(thr, 0.95, False))
+        self._run(("grid_commit",), lambda: m._grid_commit(thr, 0.95, self.erode))
+
+    def _check_peer(self):
+        """comm == "p2p": the barrier's sticky error word is copied to pinned host memory at every grid update and the
+        PREVIOUS copy is inspected (no host synchronisation on the training path): a peer that stopped arriving raises
+        here on every rank within two update intervals (the exchange kernel is already a no-op from the first timeout)."""
+        if self._peer_err is None:
+            return
+        host, ev = self._peer_err
+        if self._peer_err_pending and ev.query():
+            err = int(host[1])
+            if err:
+                raise RuntimeError(f"peer barrier timed out waiting for rank {err - 1}; parameters were left untouched")
+        host.copy_(self.peer.state, non_blocking=True)
+        ev.record()
+        self._peer_err_pending = True
+
+    def close(self):
+        """Collective: release the NVLink peer mappings (comm == "p2p").  Call on every rank when training ends."""
+        self.graphs = {}
+        if self.peer is not None:
+            self.peer.close()
+            self.peer = None
+
+    def skipped_steps(self):
+        """Optimiser steps skipped by the loss scaler so far, and the current loss scale (host sync)."""
+        h = self.hyper.cpu()
+        return int(h[3]), struct.unpack("f", struct.pack("i", int(h[4])))[0]
 
     def sync_model_half(self):
         """Hand the fp16 working copies (always current) to the nn.Module view; no communication."""
         self.model.xyz_encoder.set_half_params(self.h_xyz)
         self.model.rgb_net.set_half_params(self.h_rgb)
-        self.model._image_key = None              # the fused inference path re-packs its weight image
+        # the model's fused paths -- and the CUDA graphs captured over them (occupancy update, render loop) -- read
+        # the weight image this trainer re-packs after every optimiser step: never a stale or reallocated copy
+        self.model.adopt_image(self.w_image)
 
     def overflowed(self):
         """True if the last step hit the sample capacity (host sync; call sparingly)."""

@@ -27,6 +27,21 @@ extern "C" {
 #endif
 typedef uint16_t b2n_half; /* IEEE binary16 bit pattern */
 
+/* Device-resident optimiser control block (32 bytes).  The host writes lr / step before every step (a captured CUDA
+ * graph replays with fresh values); the backward kernels set found_inf; b2n_adam_step[_peer] skip the update while
+ * found_inf is set and count steps as step - skipped; b2n_scaler_update advances skipped / loss_scale / good_steps.
+ * This is torch.cuda.amp.GradScaler (the reference trains with precision=16, train.py:265) kept on the device. */
+typedef struct {
+    float lr;
+    int32_t step;            /* 1-based count of steps issued */
+    int32_t found_inf;       /* != 0: a gradient left the fp16 range in this step */
+    int32_t skipped;         /* steps skipped so far */
+    float loss_scale;        /* current loss scale (<= 0: not managed here) */
+    int32_t good_steps;      /* clean steps since the last change of the scale */
+    int32_t growth_interval; /* double the scale after this many clean steps; 0 = never (tcnn's fixed scale) */
+    int32_t reserved;
+} b2n_hyper;
+
 B2N_API int b2n_version(void);
 B2N_API const char *b2n_last_error(void);
 
@@ -87,9 +102,12 @@ B2N_API int b2n_raymarching_train_write(const float *rays_o, const float *rays_d
                                 float exp_step_factor, const float *noise, int grid_size,
                                 int max_samples, int64_t n_rays, const int64_t *rays_a, float *xyzs,
                                 float *dirs, float *deltas, float *ts, const uint32_t *workspace, void *stream);
-/* Tuning knob (process-wide): resident CTAs per SM of the train marcher, 1..8 (default 8).  The pipelined trainer
- * lowers it so that the marcher overlaps the backward kernels instead of occupying every warp slot. */
-B2N_API int b2n_set_march_ctas_per_sm(int ctas);
+/* RayMarcher.backward (models/custom_functions.py:103-113; reached with --optimize_ext): per-ray segment sums over
+ * the packed samples of rays_a (n_rays,3) = [ray_idx, start, N]: dL_drays_o[ray] = sum dL_dxyzs,
+ * dL_drays_d[ray] = sum (dL_dxyzs * ts + dL_ddirs).  dL_ddirs may be NULL.  Every ray row is written (rays_a holds
+ * each ray once). */
+B2N_API int b2n_raymarcher_bw(const float *dL_dxyzs, const float *dL_ddirs, const float *ts, const int64_t *rays_a,
+                              int64_t n_rays, float *dL_drays_o, float *dL_drays_d, void *stream);
 /* vren.raymarching_test (models/rendering.py:79-83).  hits_t (n_rays,2) is advanced IN PLACE;
  * outputs (n_alive,n_samples[,3]) are fully written (unused slots zero); n_eff (n_alive) i32. */
 B2N_API int b2n_raymarching_test(const float *rays_o, const float *rays_d, float *hits_t,
@@ -137,12 +155,13 @@ B2N_API int b2n_composite_train_bw(const float *dL_dopacity, const float *dL_dde
 /* Training fast path: composite_train_fw + NeRFLoss (losses.py:20-40, incl. the random-background blend of
  * models/rendering.py:163-164) + composite_train_bw of each ray in one launch; the results equal the three separate
  * calls.  target (n_rays,3); writes opacity/depth (n_rays), rgb_out (n_rays,3, background-blended; may be NULL),
- * loss_dev (1) fp32 (unscaled loss), dL_dsigmas/dL_drgbs (scaled by loss_scale) and the optional alive list. */
+ * loss_dev (1) fp32 (unscaled loss), dL_dsigmas/dL_drgbs (scaled by loss_scale, or by *loss_scale_dev when that
+ * device pointer is non-NULL: b2n_hyper.loss_scale) and the optional alive list. */
 B2N_API int b2n_composite_loss_fwbw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
                             const int64_t *rays_a, const float *target, float T_threshold, int64_t n_rays,
                             float bg, float lambda_opa, float loss_scale, float *opacity, float *depth,
                             float *rgb_out, float *loss_dev, float *dL_dsigmas, float *dL_drgbs,
-                            int32_t *alive_idx, int32_t *alive_count, void *stream);
+                            int32_t *alive_idx, int32_t *alive_count, const float *loss_scale_dev, void *stream);
 /* vren.composite_test_fw (models/rendering.py:97-100).  In place on alive_indices/opacity/depth/rgb. */
 B2N_API int b2n_composite_test_fw(const float *sigmas, const float *rgbs, const float *deltas, const float *ts,
                           const float *hits_t, int64_t *alive_indices, float T_threshold,
@@ -176,9 +195,10 @@ B2N_API int b2n_hashgrid_bw(const float *x, const b2n_half *dL_dout, int dy_stri
                     int64_t n, const int32_t *n_dev, float grad_scale, float *grad_table, const int32_t *sample_idx,
                     void *stream);
 /* Frequency encoding (models/networks.py:49-53): x (n,3) -> out (n, out_stride) fp16, 3*n_freq*2 columns
- * then ones up to the next multiple of 16. */
+ * then ones up to the next multiple of 16.  The encoded value is (x - x_min) / x_extent: pass 0, 1 for the plain
+ * tcnn module, or xyz_min, xyz_max - xyz_min to fold in the box normalisation of NGP.density (networks.py:96). */
 B2N_API int b2n_frequency_fw(const float *x, int n_frequencies, int64_t n, const int32_t *n_dev, b2n_half *out,
-                     int out_stride, void *stream);
+                     int out_stride, float x_min, float x_extent, void *stream);
 /* SphericalHarmonics degree 4 (models/networks.py:63-70): d01 (n,3) f32 in [0,1] -> out (n,out_stride)
  * fp16 columns [0,16).  If normalize != 0 the input is a raw direction d and the kernel computes
  * d/|d| first (the fused form of networks.py:113-114; (d+1)/2 then *2-1 is folded away exactly). */
@@ -203,29 +223,34 @@ B2N_API int b2n_mlp_bw(const b2n_half *dL_dout, const b2n_half *in, int in_strid
                b2n_half *dL_din, float *grad_weights, void *stream);
 
 /* ---------------------------------------------------------------- fused field MLPs (tcgen05) --------- */
-/* The dense half of NGP.forward (models/networks.py:96-115) for the HashGrid configuration in one kernel:
- * enc(32) -> 64 -> 16 = h, sigma = exp(h[0]) (TruncExp), [SH4(dir/|dir|) | h] -> 64 -> 64 -> 3, sigmoid.
- * image: the two FullyFusedMLP weight sets repacked by b2n_field_pack_weights (10240 halves).
- * enc (n,32) fp16 (b2n_hashgrid_fw output), dirs (n,3) fp32 raw directions -> sigmas (n) fp32,
- * rgbs (n,3) fp32 (fp16-rounded).  Optional saves for the backward pass (NULL to skip):
- * hid_s (n,64), h (n,16), hid_r (2,n,64), all fp16.  rgbs == NULL selects the density-only form
- * (NGP.density, models/networks.py:87-100): the chain stops after h, dirs is not read. */
-B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights /*3072*/, const b2n_half *rgb_weights /*7168*/,
-                                   b2n_half *image /*10240*/, void *stream);
-B2N_API int b2n_field_mlp_fw(const b2n_half *enc, const float *dirs, const b2n_half *image, int64_t n,
-                             const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *hid_s, b2n_half *h,
-                             b2n_half *hid_r, void *stream);
-/* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale);
- * writes dL_denc (n,32) fp16 for b2n_hashgrid_bw and accumulates (+=) grad_sigma_w (3072) / grad_rgb_w (7168)
- * fp32 in the flat row-major (out,in) layout of the weights, times grad_scale.
+/* The dense half of NGP.forward (models/networks.py:96-115) in one kernel:
+ * enc(k1) -> 64 -> 16 = h, sigma = exp(h[0]) (TruncExp), [SH4(dir/|dir|) | h] -> 64 -> 64 -> 3, sigmoid.
+ * k1 = 32: the HashGrid configuration (networks.py:39-47, enc = b2n_hashgrid_fw output);
+ * k1 = 80: the Frequency-12 configuration this fork has active (networks.py:49-53, enc = b2n_frequency_fw output).
+ * image: the two FullyFusedMLP weight sets (sigma: 64*k1 + 1024 halves, rgb: 7168 halves, flat row-major (out,in))
+ * repacked by b2n_field_pack_weights into b2n_field_image_halves(k1) halves.
+ * enc (n,k1) fp16, dirs (n,3) fp32 raw directions -> sigmas (n) fp32 (may be NULL), rgbs (n,3) fp32 (fp16-rounded),
+ * h (n,16) fp16 (may be NULL; the one activation the backward pass wants saved).  rgbs == NULL selects the
+ * density-only form (NGP.density, models/networks.py:87-100): the chain stops after h, dirs is not read. */
+B2N_API int b2n_field_image_halves(int k1);
+B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights, const b2n_half *rgb_weights, b2n_half *image, int k1,
+                                   void *stream);
+B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, const b2n_half *image, int64_t n,
+                             const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *h, void *stream);
+/* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale); the hidden
+ * activations are recomputed from enc / dirs / h (the forward pass saves nothing else).  Writes dL_denc (n,32) fp16
+ * for b2n_hashgrid_bw (k1 = 32; NULL to skip, must be NULL for k1 = 80) and accumulates (+=) grad_sigma_w
+ * (64*k1 + 1024) / grad_rgb_w (7168) fp32 in the flat row-major (out,in) layout of the weights, times grad_scale.
  * sample_idx (may be NULL): compacted list of sample rows to process (b2n_composite_train_bw's alive_idx); then n /
- * n_dev count list entries, row i of dL_denc belongs to sample sample_idx[i], and n_alloc is the row count of the
- * saved-activation buffers (the stride between the two hid_r planes).  With NULL, n_alloc = n. */
-B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
-                             const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs,
-                             const b2n_half *hid_s, const b2n_half *h, const b2n_half *hid_r, float grad_scale,
-                             b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx,
-                             int64_t n_alloc, void *stream);
+ * n_dev count list entries and row i of dL_denc belongs to sample sample_idx[i].
+ * serialize != 0: MMA issue of the CTA's tile groups goes through a shared-memory lock (validation of the default
+ * lock-free accumulation).  found_inf (may be NULL): set to 1 when a gradient left the fp16 range (inf / NaN), the
+ * GradScaler signal of the reference's precision=16 training (train.py:265). */
+B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, int k1,
+                             const float *dirs, const b2n_half *image, int64_t n, const int32_t *n_dev,
+                             const float *rgbs, const b2n_half *h, float grad_scale, b2n_half *dL_denc,
+                             float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx, int serialize,
+                             int32_t *found_inf, void *stream);
 
 /* ---------------------------------------------------------------- multi-GPU: NVLink peer memory ------ */
 /* Data-parallel training (ngp_pl/train.py:197-208: DDPPlugin -> one NCCL gradient all-reduce per step, every rank
@@ -250,29 +275,31 @@ B2N_API int b2n_peer_barrier(void *const *flag_ptrs, int rank, int world, uint32
  * HOST arrays of `world` device pointers to each rank's full fp32 gradient / fp16 gradient copy / fp16 parameter
  * vector.  Elements with index in [half_lo, half_hi) are read from the fp16 copies made by b2n_grad_pack_half (half
  * the NVLink bytes; grad16_ptrs == NULL or an empty range: everything fp32).  fp32 gradients are left untouched:
- * their holder clears them after the closing barrier. */
+ * their holder clears them after the closing barrier.
+ * hyper_ptrs (may be NULL): HOST array of `world` device pointers to every rank's b2n_hyper (peer memory): an
+ * overflow flagged by ANY rank skips the step on all of them.  barrier_state (may be NULL): the state word pair of
+ * b2n_peer_barrier; when its sticky error is set the kernel does nothing (a peer did not arrive: gradients incomplete). */
 B2N_API int b2n_adam_step_peer(float *param_shard, float *exp_avg, float *exp_avg_sq, void *const *grad_ptrs,
                                void *const *grad16_ptrs, int64_t half_lo, int64_t half_hi, void *const *half_ptrs,
                                int world, int64_t shard_first, int64_t shard_n, float lr, float beta1, float beta2,
-                               float eps, float inv_scale, int step, const void *hyper_dev, void *stream);
+                               float eps, float inv_scale, int step, const b2n_hyper *hyper_dev,
+                               void *const *hyper_ptrs, const uint32_t *barrier_state, void *stream);
 /* For i in [lo, hi): grad16[i] = saturate_fp16(grad[i]); grad[i] = 0 -- the wire copy of this rank's table gradient. */
 B2N_API int b2n_grad_pack_half(float *grad, b2n_half *grad16, int64_t lo, int64_t hi, void *stream);
-
-/* Performance hint (process-wide, per current device): keep [base, base + bytes) -- the gradient vector and the
- * fp16 parameter copy -- resident in L2 across the training step.  Sets the persisting-L2 carve-out and makes
- * b2n_hashgrid_fw/_bw and b2n_adam_step launch with a matching access-policy window.  base == NULL switches it off.
- * No effect on results. */
-B2N_API int b2n_set_l2_persist(void *base, int64_t bytes);
 
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
  * over one flat fp32 parameter; grad is multiplied by inv_scale, then ZEROED; half_copy (may be NULL)
- * receives the fp16 copy of the updated parameter.  hyper_dev (may be NULL): device struct
- * {float lr; int32 step;} that overrides `lr` / `step` (1-based) so that a captured CUDA graph can be
- * replayed while the schedule advances. */
+ * receives the fp16 copy of the updated parameter.  hyper_dev (may be NULL): device b2n_hyper that overrides
+ * `lr` / `step` (effective step = step - skipped), divides inv_scale by its loss_scale, and turns the call into
+ * "clear the gradient only" while found_inf is set. */
 B2N_API int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
                   int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale, int step,
-                  const void *hyper_dev, void *stream);
+                  const b2n_hyper *hyper_dev, void *stream);
+/* GradScaler bookkeeping after the optimiser step: found_inf (OR-ed with the blocks in hyper_ptrs, a HOST array of
+ * `world` device pointers, or NULL) halves loss_scale and counts a skipped step; otherwise growth_interval clean
+ * steps in a row double it.  found_inf is left for the caller to clear. */
+B2N_API int b2n_scaler_update(b2n_hyper *hyper_dev, void *const *hyper_ptrs, int world, void *stream);
 /* fp32 -> fp16 parameter copy (what tcnn does before each forward). */
 B2N_API int b2n_cast_half(const float *src, b2n_half *dst, int64_t n, void *stream);
 
@@ -283,12 +310,20 @@ B2N_API int b2n_grid_cell_positions(const int32_t *coords, const float *noise, i
                             float xyz_min, float xyz_max, int unit_cube, float *xyz, void *stream);
 /* grid[idx[i]] update: tmp scatter + EMA-max: grid = grid<0 ? grid : max(grid*decay, tmp)  (:232-237)
  * done in two launches: scatter (tmp[indices[i]] = sigma[i]) and ema over the whole cascade set. */
-B2N_API int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, void *stream);
+B2N_API int b2n_grid_scatter(const int64_t *indices, const float *sigmas, int64_t n, float *tmp, int64_t n_cells,
+                             void *stream);
 B2N_API int b2n_grid_ema(float *density_grid, const float *tmp, int64_t n_cells, float decay, void *stream);
 /* mean of grid[grid>0] -> stats_dev[0] = min(mean, density_threshold), stats_dev[1] = mean, stats_dev[2]
  * = count (networks.py:249-251), no host sync.  workspace: 3 doubles (24 B), initialised by the call. */
 B2N_API int b2n_grid_threshold(const float *density_grid, int64_t n_cells, float density_threshold,
                        double *workspace, float *stats_dev, void *stream);
+
+/* NGP.mark_invisible_cells (models/networks.py:159-214) in one launch: K (3,3), poses (n_img,3,4) camera-to-world,
+ * density_grid (cascades, grid_size^3) in Morton order <- 0 for cells that at least one camera sees at depth >=
+ * near_distance and none has in view closer than that, -1 otherwise (every cell is written). */
+B2N_API int b2n_mark_invisible_cells(const float *K, const float *poses, int n_img, int img_w, int img_h,
+                                     float near_distance, int grid_size, int cascades, float scale,
+                                     float *density_grid, void *stream);
 
 /* Random 4-byte gathers over a power-of-two buffer (L2 request-rate probe for bench.py: the roofline of the hash-grid
  * gather).  *n_loads (host, may be NULL) receives the number of loads the launch issues. */
@@ -304,7 +339,7 @@ B2N_API int b2n_membench_read(const void *buf, int64_t bytes, int iters, void *s
  * loss*loss_scale with respect to the composited rgb / opacity. */
 B2N_API int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const float *target, int64_t n_rays,
                        float bg, float lambda_opa, float loss_scale, float *rgb_out, float *loss_dev,
-                       float *dL_drgb, float *dL_dopacity, void *stream);
+                       float *dL_drgb, float *dL_dopacity, const float *loss_scale_dev, void *stream);
 
 #ifdef __cplusplus
 }

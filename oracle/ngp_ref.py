@@ -108,6 +108,31 @@ class NGPRef:
         V.packbits(self.density_grid, min(mean_density, density_threshold), self.density_bitfield)
 
 
+@torch.no_grad()
+def mark_invisible_cells(model, K, poses, img_wh, chunk=64 ** 3):
+    """networks.py:159-214 on CPU tensors: density_grid <- 0 where some camera sees the cell centre at depth >=
+    NEAR_DISTANCE and no camera has it in view closer than that, else -1."""
+    G = model.grid_size
+    w2c_R = poses[:, :3, :3].permute(0, 2, 1)
+    w2c_T = torch.bmm(-w2c_R, poses[:, :3, 3:])
+    coords = _grid_coords(G)
+    indices = V.morton3D(coords).long()
+    for c in range(model.cascades):
+        for i in range(0, len(indices), chunk):
+            xyzs = coords[i:i + chunk] / (G - 1) * 2 - 1
+            s = min(2 ** (c - 1), model.scale)
+            half_grid_size = s / G
+            xyzs_w = (xyzs * (s - half_grid_size)).T
+            xyzs_w = xyzs_w.unsqueeze(0).repeat(w2c_R.shape[0], 1, 1)
+            xyzs_c = torch.bmm(w2c_R, xyzs_w) + w2c_T
+            uvd = K @ xyzs_c
+            uv = uvd[:, :2] / uvd[:, 2:]
+            in_image = (uvd[:, 2] >= 0) & (uv[:, 0] >= 0) & (uv[:, 0] < img_wh[0]) & (uv[:, 1] >= 0) & (uv[:, 1] < img_wh[1])
+            covered = ((uvd[:, 2] >= NEAR_DISTANCE) & in_image).any(0)
+            too_near = ((uvd[:, 2] < NEAR_DISTANCE) & in_image).any(0)
+            model.density_grid[c, indices[i:i + chunk]] = torch.where(covered & ~too_near, 0., -1.)
+
+
 def _grid_coords(G):
     r = torch.arange(G, dtype=torch.int32)
     z, y, x = torch.meshgrid(r, r, r, indexing="ij")

@@ -63,6 +63,8 @@ def main():
         torch.cuda.synchronize()
         out[dp] = (losses, *params, m.density_bitfield.clone(), m.density_grid.clone())
         wire16 = tr.grad_fp16
+        comm_used = tr.comm
+        tr.close()                                           # collective: unmap the peers' blocks
     l1, p1, r1, b1, g1 = out[False]; l2, p2, r2, b2, g2 = out[True]
     assert l2[-1] < 0.7 * l2[0], l2
     torch.testing.assert_close(torch.tensor(l2), torch.tensor(l1), rtol=5e-2, atol=1e-5)
@@ -86,7 +88,7 @@ def main():
     agree = ((g1 - g2).abs()[seen].mean() / g1[seen].abs().mean()).item()          # mean deviation / mean density
     assert agree < 0.25 and (g2 > 0).any() and b2.any(), (agree, (g1 - g2).abs()[seen].max().item(), g1[seen].max().item())
     if rank == 0:
-        print("dist_nccl_check ok (comm %s): world" % tr.comm, dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
+        print("dist_nccl_check ok (comm %s): world" % comm_used, dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
               "mean density-grid deviation %.4f" % agree)
     dist.barrier(); dist.destroy_process_group()
 

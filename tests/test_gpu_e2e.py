@@ -69,7 +69,7 @@ def test_render_train_forward_backward(pair):
     for got, want, name in ((model.rgb_net.params.grad, ref.rgb_params.grad, "rgb_net"),
                             (model.xyz_encoder.params.grad, ref.xyz_params.grad, "xyz_encoder")):
         sc = want.abs().max().item()
-        assert (got.cpu() - want).abs().max().item() <= 3e-2 * sc, name
+        assert (got.cpu() - want).abs().max().item() <= 1e-2 * sc, name
     model.zero_grad(); ref.xyz_params.grad = None; ref.rgb_params.grad = None
 
 
@@ -136,13 +136,19 @@ def test_update_density_grid_consistency(pair):
     ref_bits = np.packbits((grid.cpu().numpy().reshape(-1) > m._grid_stats[0].item()), bitorder="little")
     assert np.array_equal(m.density_bitfield.cpu().numpy(), ref_bits)
     # the device-side occupied-cell sampler only returns occupied cells, roughly uniformly over them
+    # (the returned list is sorted by Morton index, so the two halves cannot be told apart afterwards: at least the M
+    # occupied draws must land on occupied cells, plus the uniform draws' share)
     (idx_all, coords_all), = m.sample_uniform_and_occupied_cells(20000)
-    occ_idx = idx_all[20000:]
-    assert bool((grid[0, occ_idx] > 0).all())
     from google_nerf_b200 import vren
-    assert torch.equal(vren.morton3D(coords_all).long(), idx_all)
+    assert idx_all.numel() == 40000 and torch.equal(vren.morton3D(coords_all).long(), idx_all)
     n_occ = int((grid[0] > 0).sum())
-    assert occ_idx.unique().numel() > 0.9 * min(20000, n_occ) * (1 - np.exp(-20000 / n_occ)) if n_occ else True
+    assert 0 < n_occ < 128 ** 3
+    hits = int((grid[0, idx_all] > 0).sum())
+    expect = 20000 + 20000 * n_occ / 128 ** 3
+    assert abs(hits - expect) < 6 * (20000 * 0.25) ** 0.5 + 1, (hits, expect)
+    # and the occupied draws spread over the occupied cells instead of repeating a few
+    occ_hit = idx_all[grid[0, idx_all] > 0]
+    assert occ_hit.unique().numel() > 0.5 * min(hits, n_occ)
     before = grid.clone()
     m.update_density_grid(5.912, warmup=False)                           # uniform + occupied sampling path
     assert float((m.density_grid - before).abs().max()) > 0

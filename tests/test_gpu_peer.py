@@ -92,7 +92,7 @@ def test_adam_step_peer_world_1_equals_adam_step(block, half):
         assert float(g16[5 + 0].float()) != float("inf")
     gp = (C.c_void_p * 1)(grad.data_ptr()); g16p = (C.c_void_p * 1)(g16.data_ptr()); hp = (C.c_void_p * 1)(h_out.data_ptr())
     L.call("b2n_adam_step_peer", L.ptr(p2), L.ptr(m2), L.ptr(v2), gp, g16p if half else None, lo, hi if half else lo, hp, 1,
-           first, cnt, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 128, 7, None)
+           first, cnt, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 128, 7, None, None, None)
     torch.cuda.synchronize()
     sl = slice(first, first + cnt)
     assert torch.equal(p2, p1[sl]) and torch.equal(m2, m1[sl]) and torch.equal(v2, v1[sl])
@@ -100,4 +100,33 @@ def test_adam_step_peer_world_1_equals_adam_step(block, half):
     assert float(h_out[:first].float().abs().max()) == 0.0           # nothing written outside the shard
     with pytest.raises(RuntimeError):
         L.call("b2n_adam_step_peer", L.ptr(p2), L.ptr(m2), L.ptr(v2), gp, None, 0, 0, hp, 1, first + 2, cnt, 1e-2, 0.9,
-               0.999, 1e-15, 1.0, 1, None)                           # shard bounds must be multiples of 4
+               0.999, 1e-15, 1.0, 1, None, None, None)               # shard bounds must be multiples of 4
+    # device control block: found_inf skips the update on both kernels, the scaler halves the scale and counts the skip;
+    # a sticky barrier error turns the peer kernel into a no-op
+    import struct
+    f2i = lambda f: struct.unpack("i", struct.pack("f", f))[0]
+    hyper = torch.tensor([f2i(1e-2), 7, 1, 0, f2i(128.0), 5, 0, 0], dtype=torch.int32, device=DEV)
+    hyp = (C.c_void_p * 1)(hyper.data_ptr())
+    grad.copy_((torch.randn(n, generator=g) * 3).to(DEV))
+    p3, m3, v3 = p2.clone(), m2.clone(), v2.clone()
+    L.call("b2n_adam_step_peer", L.ptr(p3), L.ptr(m3), L.ptr(v3), gp, None, 0, 0, hp, 1, first, cnt, 0.0, 0.9, 0.999,
+           1e-15, 1.0, 0, L.ptr(hyper), hyp, None)
+    assert torch.equal(p3, p2) and torch.equal(m3, m2)               # skipped
+    p4, m4, v4, g4 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
+    L.call("b2n_adam_step", L.ptr(p4), L.ptr(g4), L.ptr(m4), L.ptr(v4), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper))
+    assert torch.equal(p4, p1) and torch.equal(m4, m1) and float(g4.abs().max()) == 0.0   # skipped, gradient cleared
+    L.call("b2n_scaler_update", L.ptr(hyper), hyp, 1)
+    assert hyper.tolist()[2:6] == [1, 1, f2i(64.0), 0]               # found_inf left for the caller, skipped, scale / 2
+    hyper[2] = 0
+    # clean step: effective step = step - skipped = 6, gradients divided by the device loss scale (64)
+    p5, m5, v5, g5 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
+    L.call("b2n_adam_step", L.ptr(p5), L.ptr(g5), L.ptr(m5), L.ptr(v5), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper))
+    p6, m6, v6, g6 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
+    L.call("b2n_adam_step", L.ptr(p6), L.ptr(g6), L.ptr(m6), L.ptr(v6), None, n, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 64, 6, None)
+    assert torch.equal(p5, p6) and torch.equal(v5, v6)
+    L.call("b2n_scaler_update", L.ptr(hyper), None, 1)
+    assert hyper.tolist()[2:6] == [0, 1, f2i(64.0), 1]
+    state = torch.tensor([3, 2], dtype=torch.int32, device=DEV)      # sticky error: rank 1 timed out
+    L.call("b2n_adam_step_peer", L.ptr(p3), L.ptr(m3), L.ptr(v3), gp, None, 0, 0, hp, 1, first, cnt, 0.0, 0.9, 0.999,
+           1e-15, 1.0, 0, L.ptr(hyper), hyp, L.ptr(state))
+    assert torch.equal(p3, p2)

@@ -62,25 +62,17 @@ def test_checkpoint_helpers(tmp_path):
     load_ckpt(lin, "")                                        # empty path is a no-op
 
 
-def test_raymarcher_backward_segment_sums():
-    """RayMarcher.backward (custom_functions.py:103-113): dL/drays_o = per-ray sum of dL/dxyz, dL/drays_d = per-ray sum
-    of dL/dxyz * t + dL/ddirs -- here without torch_scatter, against a per-ray loop and the segment_csr shim."""
-    import types
+def test_segment_csr_shim_matches_per_ray_sums():
+    """The torch_scatter.segment_csr stand-in over the reference's CSR pointer (custom_functions.py:108-111) against a
+    per-ray loop.  (RayMarcher.backward itself is one CUDA launch: tests/test_gpu_baseline.py.)"""
     sys.path.insert(0, os.path.join(ROOT, "google-nerf_b200", "shims"))
-    from google_nerf_b200.models.custom_functions import RayMarcher
     from torch_scatter import segment_csr
     g = torch.Generator().manual_seed(2)
     counts = torch.tensor([3, 0, 5, 1, 0, 7])
     n = int(counts.sum())
     start = torch.cumsum(counts, 0) - counts
     rays_a = torch.stack([torch.arange(6), start, counts], 1)
-    ts = torch.rand(n, generator=g)
-    d_xyz, d_dirs = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
-    ctx = types.SimpleNamespace(saved_tensors=(rays_a, ts), _fwd_used_autocast=False, _dtype=None)   # what custom_bwd reads
-    got = RayMarcher.backward(ctx, None, d_xyz, d_dirs, None, None, None)
-    assert len(got) == 9 and all(v is None for v in got[2:])
+    d_xyz = torch.randn(n, 3, generator=g)
     want_o = torch.stack([d_xyz[s:s + c].sum(0) for s, c in zip(start.tolist(), counts.tolist())])
-    want_d = torch.stack([(d_xyz[s:s + c] * ts[s:s + c, None] + d_dirs[s:s + c]).sum(0) for s, c in zip(start.tolist(), counts.tolist())])
-    torch.testing.assert_close(got[0], want_o); torch.testing.assert_close(got[1], want_d)
     ptr = torch.cat([rays_a[:, 1], rays_a[-1:, 1] + rays_a[-1:, 2]])           # the reference's CSR pointer
     torch.testing.assert_close(segment_csr(d_xyz, ptr), want_o)
