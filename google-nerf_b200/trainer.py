@@ -49,15 +49,17 @@ class _SampleSet:
 
 class NGPTrainer:
     def __init__(self, model, n_rays=8192, lr=1e-2, eps=1e-15, betas=(0.9, 0.999), exp_step_factor=0.0,
-                 T_threshold=1e-4, lambda_opa=1e-3, loss_scale=128.0, samples_per_ray=96, seed=0,
+                 T_threshold=1e-4, lambda_opa=1e-3, loss_scale=16384.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
                  comm=None, comm_in_graph=False, grad_fp16=None, erode=False, scale_growth_interval=0,
                  serialize_mma=False):
         """model: NGP with either encoding (HashGrid: networks.py:39-47; Frequency: networks.py:49-53).
         erode: the reference passes erode=True for colmap scenes (train.py:148).  loss_scale: start value of the
-        device-side loss scaler (tcnn's fixed 128); an overflow in the fp16 backward pass skips that optimiser step and
-        halves it like GradScaler (train.py:265 precision=16), scale_growth_interval > 0 doubles it again after that
-        many clean steps (GradScaler's growth; 0 keeps tcnn's behaviour of never growing)."""
+        device-side loss scaler.  The reference's fp16 backward pass runs at tcnn's internal 128 TIMES Lightning's
+        GradScaler (precision=16, train.py:265: 65536 at start, halved on overflow); at 128 alone the per-sample
+        gradients dL/denc of an 8192-ray batch (~1e-5) are fp16 subnormals and lose most of their mantissa, at 2^14
+        they sit in the normal range with > 2^20 of headroom.  An overflow skips that optimiser step and halves the
+        scale like GradScaler; scale_growth_interval > 0 doubles it again after that many clean steps (0: never)."""
         self.model, self.n_rays = model, n_rays
         self.hashed = model.encoding == "HashGrid"
         self.k1 = model.k1

@@ -11,7 +11,11 @@ PARITY UNPINNED (oracle/__init__.py).  All functions are differentiable torch co
 provides the gradient oracle; pass dtype=torch.float64 tables/weights for an fp64 "truth" variant.
 
 Numerics contract (DESIGN.md "Numerics"): tables and weights are rounded to fp16, products are
-accumulated in fp32, every layer output / encoding output is rounded to fp16.
+accumulated in fp32, every layer output / encoding output is rounded to fp16.  The roundings are
+straight-through for autograd (`_round16`): the gradient oracle is the EXACT fp32 gradient of the fp16-rounded
+forward function, independent of any loss scale.  (A plain `.to(float16)` would also round every gradient that
+flows back through it to fp16 -- and flush unscaled ones to zero -- which models neither tiny-cuda-nn's
+loss-scaled fp16 backward pass nor anything a test should compare against.)
 """
 import math
 
@@ -19,6 +23,27 @@ import numpy as np
 import torch
 
 PRIMES = (1, 2654435761, 805459861)
+
+
+class _Round16(torch.autograd.Function):
+    """fp32 -> nearest fp16 value (kept in fp32); identity gradient."""
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.float16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _round16(t):
+    return _Round16.apply(t.to(torch.float32))
+
+
+def _to_half(t):
+    """Module output: an fp16 tensor -- or, while autograd is recording, the same fp16 values kept in an fp32 tensor,
+    so that no dtype conversion (whose backward would round the gradient to fp16) sits on the gradient path."""
+    return _round16(t) if (t.requires_grad and torch.is_grad_enabled()) else t.to(torch.float16)
 
 
 # --------------------------------------------------------------------------- hash grid
@@ -88,13 +113,15 @@ def hashgrid_forward(x, table, layout, out_dtype=torch.float16):
     F = layout['n_features']
     tab = table.view(-1, F)
     if table.dtype == torch.float32:
-        tab = tab.to(torch.float16).to(torch.float32)
+        tab = _round16(tab)
     feats = []
     for idx, w in hashgrid_indices_weights(x, layout):
         v = tab[idx]                                                # (N,8,F)
         feats.append((v * w[..., None].to(tab.dtype)).sum(1))
     out = torch.cat(feats, 1)
-    return out.to(out_dtype) if table.dtype == torch.float32 else out
+    if table.dtype != torch.float32:
+        return out
+    return _to_half(out) if out_dtype == torch.float16 else out.to(out_dtype)
 
 
 # --------------------------------------------------------------------------- frequency / SH
@@ -146,7 +173,7 @@ def mlp_forward(x, params, shapes, n_out, output_activation="None", return_hidde
     """x (N, n_in) fp16/fp32; params flat master weights.  fp16 weights & activations, fp32 accumulate.
     -> (N, n_out) fp16 (fp64 if params are fp64)."""
     truth = params.dtype == torch.float64
-    cast = (lambda t: t) if truth else (lambda t: t.to(torch.float16).to(torch.float32))
+    cast = (lambda t: t) if truth else _round16
     h = cast(x.to(params.dtype))
     if h.shape[1] < shapes[0][1]:
         h = torch.cat([h, torch.zeros(h.shape[0], shapes[0][1] - h.shape[1], dtype=h.dtype)], 1)
@@ -159,7 +186,7 @@ def mlp_forward(x, params, shapes, n_out, output_activation="None", return_hidde
     if output_activation == "Sigmoid":
         h = torch.sigmoid(h)
     out = h[:, :n_out]
-    out = out if truth else out.to(torch.float16)
+    out = out if truth else _to_half(out)
     return (out, hidden) if return_hidden else out
 
 

@@ -22,8 +22,9 @@ DEV = "cuda"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _grad_report(tr_or_pair, ref, n_mlp, layout_offsets, k1=32):
-    """max |got - want| per MLP layer and per hash-grid level, each relative to that block's largest |want|."""
+def _grad_report(tr_or_pair, ref, n_mlp, layout_offsets, k1=32, unscale=1.0):
+    """Per MLP layer and per hash-grid level: (max |got - want| / max |want|, ||got - want||_2 / ||want||_2, share of
+    entries off by more than 1e-2 of the block's largest |want|)."""
     g_xyz, g_rgb = tr_or_pair
     want_x, want_r = ref.xyz_params.grad, ref.rgb_params.grad
     blocks = {"W1": (g_xyz[:64 * k1], want_x[:64 * k1]), "W2": (g_xyz[64 * k1:n_mlp], want_x[64 * k1:n_mlp]),
@@ -35,8 +36,23 @@ def _grad_report(tr_or_pair, ref, n_mlp, layout_offsets, k1=32):
     rep = {}
     for k, (got, want) in blocks.items():
         sc = want.abs().max().item()
-        rep[k] = ((got.cpu() - want).abs().max().item() / sc) if sc > 0 else 0.0
+        d = (got.cpu() * unscale - want).abs()
+        rep[k] = (d.max().item() / sc, (d.norm() / want.norm()).item(), (d > 1e-2 * sc).float().mean().item()) if sc > 0 \
+            else (0.0, 0.0, 0.0)
     return rep
+
+
+def _check_grad_report(rep):
+    """MLP weight gradients (sums over every sample) within 3e-3 of their largest entry (measured: 1e-4 at 8192 rays,
+    2e-3 at 1024); table gradients within 5e-3 in the L2 sense on every level (measured <= 3.3e-3).  A fine-level
+    entry is touched by one or two samples, so a single sample whose ReLU mask or early-stop decision differs between
+    the CUDA forward pass and the oracle's (fp32 accumulation order) shows up undiluted there: the max error of a level
+    is bounded at 6e-2 of its largest entry with at most 1e-4 of the entries beyond 1e-2 (measured <= 1e-5)."""
+    for k, (mx, l2, frac) in rep.items():
+        if k.startswith("W"):
+            assert mx <= 3e-3, (k, mx, l2)
+        else:
+            assert l2 <= 5e-3 and mx <= 6e-2 and frac <= 1e-4, (k, mx, l2, frac)
 
 
 def _one_step_vs_oracle(scale, log2_T, n_rays, esf, seed, spr, amp, W=800, H=800):
@@ -72,20 +88,17 @@ def _one_step_vs_oracle(scale, log2_T, n_rays, esf, seed, spr, amp, W=800, H=800
     torch.testing.assert_close(tr.opacity.cpu(), res["opacity"].detach(), rtol=5e-3, atol=5e-3)
     torch.testing.assert_close(tr.rgb_out.cpu(), res["rgb"].detach(), rtol=5e-3, atol=5e-3)
     assert abs(tr.loss.item() - loss.item()) < 2e-3 * abs(loss.item())
-    assert int(tr.hyper[2].item()) == 0                      # no fp16 overflow at loss scale 128
+    assert int(tr.hyper[2].item()) == 0                      # no fp16 overflow at the default loss scale
     rep = _grad_report((tr.g_xyz, tr.g_rgb), ref, ref.n_mlp, ref.layout["offsets"])
-    print(f"\n[grad parity scale={scale} T=2^{log2_T} rays={n_rays} samples={N}] " +
-          " ".join(f"{k}={v:.2e}" for k, v in rep.items()))
+    print(f"\n[grad parity scale={scale} T=2^{log2_T} rays={n_rays} samples={N}] (max, L2, share > 1e-2) " +
+          " ".join(f"{k}=({v[0]:.1e},{v[1]:.1e},{v[2]:.0e})" for k, v in rep.items()))
     return rep, tr, ref, s
 
 
 def test_c2_trainer_step_full_size(built_lib):
     """BASELINE config 2 at full size: 8192 rays, scale 0.5, T = 2^19."""
     rep, *_ = _one_step_vs_oracle(0.5, 19, 8192, 0.0, seed=21, spr=128, amp=0.5)
-    for k, v in rep.items():
-        assert v <= 1e-2, (k, v, rep)
-    # the MLP layers see every sample: their sums average the fp16 rounding out
-    assert max(rep[k] for k in ("W1", "W2", "W3", "W4", "W5")) <= 4e-3, rep
+    _check_grad_report(rep)
 
 
 def test_c5_marcher_bit_exact_scale16(built_lib):
@@ -145,8 +158,7 @@ def test_c5_trainer_step_scale16_T22(built_lib):
     """BASELINE config 5 shape: scale 16, 6 cascades, exp_step_factor 1/256, T = 2^22, black background."""
     rep, tr, ref, _ = _one_step_vs_oracle(16.0, 22, 1024, 1 / 256, seed=41, spr=512, amp=0.3, W=1920, H=1080)
     assert tr.model.cascades == 6 and tr.bg == 0.0
-    for k, v in rep.items():
-        assert v <= 1e-2, (k, v, rep)
+    _check_grad_report(rep)
 
 
 def test_update_density_grid_matches_oracle(built_lib):
@@ -414,7 +426,7 @@ def test_api_path_runs_on_fused_kernels(built_lib):
             res = render(model, s["rays_o"].to(DEV), s["rays_d"].to(DEV).clone())
             loss_d = NeRFLoss()(res, {"rgb": target.to(DEV)})
             loss = sum(lo.mean() for lo in loss_d.values())
-            opt.zero_grad(); loss.backward()
+            opt.zero_grad(); (loss * 1024.0).backward()      # what Lightning's GradScaler does around tcnn's own 128
         finally:
             L.call = orig; RayMarcher.noise = None
         assert "b2n_field_mlp_fw" in calls and "b2n_field_mlp_bw" in calls
@@ -428,10 +440,13 @@ def test_api_path_runs_on_fused_kernels(built_lib):
         for got, want, name in ((model.rgb_net.params.grad, ref.rgb_params.grad, "rgb_net"),
                                 (model.xyz_encoder.params.grad, ref.xyz_params.grad, "xyz_encoder")):
             sc = want.abs().max().item()
-            err = (got.cpu() - want).abs().max().item()
+            err = (got.cpu() / 1024.0 - want).abs().max().item()
             print(f"\n[api path {encoding}] {name}: max err / max = {err / sc:.2e}")
-            assert err <= 1e-2 * sc, (encoding, name, err / sc)
+            assert err <= 1e-3 * sc, (encoding, name, err / sc)
         p0 = model.xyz_encoder.params.detach().clone()
+        for p_ in model.parameters():
+            if p_.grad is not None:
+                p_.grad /= 1024.0                             # GradScaler.unscale_
         opt.step()
         assert not torch.equal(p0, model.xyz_encoder.params.detach())
 

@@ -69,7 +69,7 @@ def test_render_train_forward_backward(pair):
     for got, want, name in ((model.rgb_net.params.grad, ref.rgb_params.grad, "rgb_net"),
                             (model.xyz_encoder.params.grad, ref.xyz_params.grad, "xyz_encoder")):
         sc = want.abs().max().item()
-        assert (got.cpu() - want).abs().max().item() <= 1e-2 * sc, name
+        assert (got.cpu() - want).abs().max().item() <= 2e-3 * sc, name
     model.zero_grad(); ref.xyz_params.grad = None; ref.rgb_params.grad = None
 
 
@@ -254,4 +254,4 @@ def test_trainer_unbounded_config_matches_oracle_step(built_lib):
     assert abs(tr.loss.item() - loss.item()) < 3e-3 * abs(loss.item())
     for got, want, name in ((tr.g_rgb, ref.rgb_params.grad, "rgb_net"), (tr.g_xyz, ref.xyz_params.grad, "xyz_encoder")):
         sc = want.abs().max().item()
-        assert (got.cpu() - want).abs().max().item() <= 3e-2 * sc, name
+        assert (got.cpu() - want).abs().max().item() <= 1e-2 * sc, name

@@ -144,32 +144,31 @@ def test_field_tc_backward_reports_overflow(built_lib):
 
 def test_field_tc_backward_stress(built_lib):
     """>= 500 k samples, repeated 50 times with and without the issue lock: the weight gradients -- sums over all
-    samples accumulated in shared TMEM columns by the CTA's four MMA-issuing threads -- match an fp64 evaluation of
-    the same chain and do not move from run to run by more than fp32 summation-order noise.  A lost or torn
-    accumulation would show as an O(1/tiles) relative error."""
+    samples accumulated in shared TMEM columns by the CTA's four MMA-issuing threads -- match the oracle's exact
+    gradient of the same (fp16-rounded) chain and do not move from run to run by more than fp32 summation-order
+    noise.  A lost or torn accumulation would show as an O(1/tiles) relative error."""
     L = built_lib
     n = 524288 + 777
     T, s_shapes, r_shapes, ps, pr, enc, dirs, g = _setup(n, 3)
-    # fp64 truth on the fp16-rounded weights (what the kernel multiplies with)
-    ps64 = ps.half().double().requires_grad_(True); pr64 = pr.half().double().requires_grad_(True)
-    sigma, rgb, *_ = _oracle_forward(T, s_shapes, r_shapes, ps64, pr64, enc.double(), dirs.double())
+    ps_r, pr_r = ps.clone().requires_grad_(True), pr.clone().requires_grad_(True)
+    sigma, rgb, *_ = _oracle_forward(T, s_shapes, r_shapes, ps_r, pr_r, enc, dirs)
     dsig = torch.randn(n, generator=g); drgb = torch.randn(n, 3, generator=g)
-    ((sigma * dsig.double()).sum() + (rgb * drgb.double()).sum()).backward()
+    ((sigma.double() * dsig.double()).sum() + (rgb.double() * drgb.double()).sum()).backward()
     d = _Dev(L, ps, pr, enc, dirs, 32)
     d.forward()
     dsig_d, drgb_d = dsig.to(DEV), drgb.to(DEV)
-    ref_s, ref_r = ps64.grad.float().to(DEV), pr64.grad.float().to(DEV)
+    ref_s, ref_r = ps_r.grad.to(DEV), pr_r.grad.to(DEV)
     sc_s, sc_r = ref_s.abs().max().item(), ref_r.abs().max().item()
     first = None
     for rep in range(50):
         for serialize in (0, 1):
             _, gs, gr, found = d.backward(dsig_d, drgb_d, serialize=serialize, want_denc=(rep == 0))
             assert found == 0
-            # fp16 activations / gradients vs fp64: a few 1e-3 of the largest entry
-            assert (gs - ref_s).abs().max().item() <= 4e-3 * sc_s, (rep, serialize)
-            assert (gr - ref_r).abs().max().item() <= 4e-3 * sc_r, (rep, serialize)
+            es, er = (gs - ref_s).abs().max().item() / sc_s, (gr - ref_r).abs().max().item() / sc_r
             if first is None:
+                print(f"\n[wgrad stress, {n} samples] sigma-net {es:.2e}, rgb-net {er:.2e} of the largest entry")
                 first = (gs.clone(), gr.clone())
+            assert es <= 3e-3 and er <= 3e-3, (rep, serialize, es, er)
             # run-to-run / lock vs lock-free: summation order only
             assert (gs - first[0]).abs().max().item() <= 2e-5 * sc_s, (rep, serialize)
             assert (gr - first[1]).abs().max().item() <= 2e-5 * sc_r, (rep, serialize)

@@ -125,7 +125,7 @@ def test_adam_step_peer_world_1_equals_adam_step(block, half):
     L.call("b2n_adam_step", L.ptr(p6), L.ptr(g6), L.ptr(m6), L.ptr(v6), None, n, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 64, 6, None)
     assert torch.equal(p5, p6) and torch.equal(v5, v6)
     L.call("b2n_scaler_update", L.ptr(hyper), None, 1)
-    assert hyper.tolist()[2:6] == [0, 1, f2i(64.0), 1]
+    assert hyper.tolist()[2:6] == [0, 1, f2i(64.0), 0]               # growth_interval 0: the scale never grows
     state = torch.tensor([3, 2], dtype=torch.int32, device=DEV)      # sticky error: rank 1 timed out
     L.call("b2n_adam_step_peer", L.ptr(p3), L.ptr(m3), L.ptr(v3), gp, None, 0, 0, hp, 1, first, cnt, 0.0, 0.9, 0.999,
            1e-15, 1.0, 0, L.ptr(hyper), hyp, L.ptr(state))
