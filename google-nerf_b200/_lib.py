@@ -78,6 +78,7 @@ _SIGS = {
     "b2n_mark_invisible_cells": [_P, _P, _I, _I, _I, _F, _I, _I, _F, _P, _P],
     "b2n_membench_read": [_P, _L, _I, _P, _P],
     "b2n_membench_gather": [_P, _L, _I, _P, C.POINTER(C.c_int64), _P],
+    "b2n_ssi_depth_loss_fwbw": [_P, _P, _L, _F, _F, _P, _P, _P, _P, _P],
     "b2n_nerf_loss_fwbw": [_P, _P, _P, _L, _F, _F, _F, _P, _P, _P, _P, _P, _P],
 }
 

@@ -270,6 +270,140 @@ extern "C" int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const 
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ depth prior
+// Shift- and scale-invariant depth loss (ngp_pl/losses.py:5-23, the MiDaS loss the SCADE-style LeReS-prior path uses)
+// of a ray batch, forward and backward in ONE single-CTA launch, no host synchronisation:
+//   p_i = 1 / depth_i (predicted disparity), g_i = prior disparity, over the valid rays (prior > 0 and depth > 1e-6)
+//   t = median (torch.median: the LOWER middle element), s = mean |x - t|, u = (p - t_p)/s_p, v = (g - t_g)/s_g
+//   L = lambda / n * sum (u - v)^2
+// The two medians are found by an 8-bit radix select over order-preserving integer keys (4 histogram passes in shared
+// memory).  The gradient follows torch autograd through the median (it flows to the median element) and through the
+// mean absolute deviation:  with r_i = 2 lambda (u_i - v_i) / n, A = sum r, B = sum r u / s_p, S = sum sign(p - t_p):
+//   dL/dp_j = r_j / s_p - [j = m] A / s_p - B / n * (sign(p_j - t_p) - [j = m] S),   dL/ddepth_j = -dL/dp_j / depth_j^2.
+__device__ __forceinline__ uint32_t float_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// block-wide sum of a double (1024 threads)
+__device__ double block_sum(double v, double *scratch) {
+    #pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += scratch[k];
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) ssi_depth_loss_kernel(const float *__restrict__ depth,
+                                                              const float *__restrict__ prior, int n, float lambda,
+                                                              float loss_scale, const float *__restrict__ loss_scale_dev,
+                                                              float *loss, float *__restrict__ dL_ddepth,
+                                                              float *__restrict__ stats) {
+    __shared__ unsigned int hist[2][256];
+    __shared__ unsigned int sel_prefix[2], sel_k[2], med_idx;
+    __shared__ double scratch[32];
+    if (loss_scale_dev != nullptr) loss_scale = __ldg(loss_scale_dev);
+    const int tid = threadIdx.x;
+    // ---- valid rays
+    int cnt = 0;
+    for (int i = tid; i < n; i += blockDim.x) cnt += (prior[i] > 0.f && depth[i] > 1e-6f) ? 1 : 0;
+    const int nv = (int)(block_sum((double)cnt, scratch) + 0.5);
+    if (nv == 0) {
+        for (int i = tid; i < n; i += blockDim.x) dL_ddepth[i] = 0.f;
+        if (tid == 0 && stats != nullptr) { stats[0] = 0.f; stats[1] = stats[2] = stats[3] = stats[4] = 0.f; }
+        return;
+    }
+    // ---- radix select of the lower median of both lists at once
+    if (tid == 0) { sel_prefix[0] = sel_prefix[1] = 0u; sel_k[0] = sel_k[1] = (unsigned)((nv - 1) / 2); med_idx = 0xffffffffu; }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int b = tid; b < 512; b += blockDim.x) hist[b >> 8][b & 255] = 0u;
+        __syncthreads();
+        const uint32_t hi_mask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+        for (int i = tid; i < n; i += blockDim.x) {
+            const float d = depth[i], g = prior[i];
+            if (!(g > 0.f && d > 1e-6f)) continue;
+            const uint32_t kp = float_key(1.0f / d), kg = float_key(g);
+            if ((kp & hi_mask) == sel_prefix[0]) atomicAdd(&hist[0][(kp >> shift) & 255u], 1u);
+            if ((kg & hi_mask) == sel_prefix[1]) atomicAdd(&hist[1][(kg >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 2) {
+            unsigned k = sel_k[tid], acc = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (acc + hist[tid][b] > k) break;
+                acc += hist[tid][b];
+            }
+            sel_k[tid] = k - acc;
+            sel_prefix[tid] |= (uint32_t)b << shift;
+        }
+        __syncthreads();
+    }
+    const float tp = key_float(sel_prefix[0]), tg = key_float(sel_prefix[1]);
+    // ---- mean absolute deviations, sign sum, the median element (smallest index among equals)
+    double ap = 0.0, ag = 0.0, sg = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float d = depth[i], g = prior[i];
+        if (!(g > 0.f && d > 1e-6f)) continue;
+        const float p = 1.0f / d;
+        ap += fabsf(p - tp); ag += fabsf(g - tg);
+        sg += (p > tp) ? 1.0 : ((p < tp) ? -1.0 : 0.0);
+        if (p == tp) atomicMin(&med_idx, (unsigned)i);
+    }
+    const double sp = block_sum(ap, scratch) / nv, sgt = block_sum(ag, scratch) / nv, S = block_sum(sg, scratch);
+    // ---- residual sums
+    const float inv_sp = (float)(1.0 / sp), inv_sg = (float)(1.0 / sgt);
+    double lsum = 0.0, A = 0.0, B = 0.0;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float d = depth[i], g = prior[i];
+        if (!(g > 0.f && d > 1e-6f)) continue;
+        const float u = (1.0f / d - tp) * inv_sp, v = (g - tg) * inv_sg, e = u - v;
+        lsum += (double)e * e;
+        A += e; B += (double)e * u;
+    }
+    const double Ls = block_sum(lsum, scratch), As = block_sum(A, scratch), Bs = block_sum(B, scratch);
+    const double c = 2.0 * lambda / nv;                         // r_i = c * e_i
+    const float Ar = (float)(c * As), Br = (float)(c * Bs / sp);
+    const unsigned m = med_idx;
+    for (int i = tid; i < n; i += blockDim.x) {
+        const float d = depth[i], g = prior[i];
+        float grad = 0.f;
+        if (g > 0.f && d > 1e-6f) {
+            const float p = 1.0f / d;
+            const float u = (p - tp) * inv_sp, v = (g - tg) * inv_sg;
+            const float r = (float)c * (u - v);
+            const float sgn = (p > tp) ? 1.f : ((p < tp) ? -1.f : 0.f);
+            const float is_m = ((unsigned)i == m) ? 1.f : 0.f;
+            const float dp = r * inv_sp - is_m * Ar * inv_sp - Br / (float)nv * (sgn - is_m * (float)S);
+            grad = -dp * p * p * loss_scale;
+        }
+        dL_ddepth[i] = grad;
+    }
+    if (tid == 0) {
+        atomicAdd(loss, (float)(lambda * Ls / nv));
+        if (stats != nullptr) { stats[0] = (float)nv; stats[1] = tp; stats[2] = (float)sp; stats[3] = tg; stats[4] = (float)sgt; }
+    }
+}
+
+extern "C" int b2n_ssi_depth_loss_fwbw(const float *depth, const float *prior_disp, int64_t n_rays, float lambda,
+                                       float loss_scale, const float *loss_scale_dev, float *loss_dev,
+                                       float *dL_ddepth, float *stats, void *stream) {
+    B2N_CHECK_ARG(depth && prior_disp && loss_dev && dL_ddepth, "null argument");
+    B2N_CHECK_ARG(n_rays >= 0 && n_rays < (1ll << 30), "bad ray count");
+    if (n_rays == 0) return 0;
+    ssi_depth_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(depth, prior_disp, (int)n_rays, lambda, loss_scale,
+                                                                 loss_scale_dev, loss_dev, dL_ddepth, stats);
+    B2N_LAUNCH_CHECK();
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ membench
 // Read-bandwidth probe used by bench.py to obtain the L2 roofline the hash-grid gather is reported against
 // (MEASURED_PEAKS.json has no L2 figure): every thread streams 16-byte loads over a buffer `iters` times; with a

@@ -105,16 +105,16 @@ def get_rays(dirs_cam, c2w):
     return rays_o.contiguous(), rays_d.contiguous()
 
 
-def shade(rays_o, rays_d, scale, bg=1.0):
-    """Closed-form ground-truth colour of the analytic scene (nearest primitive, Lambert + ambient)."""
-    dev = rays_o.device
-    o = rays_o / scale; d = rays_d / scale                           # primitives are in units of scale
+def _shade_prims(o, d, spheres, boxes, bg, two_sided=False):
+    """Nearest-hit Lambert + ambient shading of spheres [(centre, radius, albedo)] and axis-aligned boxes [(centre, half
+    size, albedo)] -> colour (N,3), ray parameter t of the hit (inf = background)."""
+    dev = o.device
     N = o.shape[0]
     best_t = torch.full((N,), float("inf"), device=dev)
-    colour = torch.full((N, 3), bg, device=dev)
+    colour = torch.full((N, 3), float(bg), device=dev)
     light = torch.tensor([0.4, 0.3, 0.85], device=dev); light = light / light.norm()
     a = (d * d).sum(-1)
-    for c, r, alb in _SPHERES:
+    for c, r, alb in spheres:
         oc = o - torch.tensor(c, device=dev)
         hb = (oc * d).sum(-1); cc = (oc * oc).sum(-1) - r * r
         disc = hb * hb - a * cc
@@ -124,17 +124,91 @@ def shade(rays_o, rays_d, scale, bg=1.0):
         lam = (n * light).sum(-1).clamp(min=0) * 0.7 + 0.3
         colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
         best_t = torch.where(hit, t, best_t)
-    c, h, alb = _BOX
-    c = torch.tensor(c, device=dev); h = torch.tensor(h, device=dev)
-    inv = 1.0 / d
-    lo, hi = (c - h - o) * inv, (c + h - o) * inv
-    tmin, tmax = torch.minimum(lo, hi), torch.maximum(lo, hi)
-    t1, axis = tmin.max(-1); t2 = tmax.min(-1)[0]
-    hit = (t1 <= t2) & (t1 > 0) & (t1 < best_t)
-    n = torch.zeros(N, 3, device=dev); n.scatter_(1, axis[:, None], -torch.sign(d.gather(1, axis[:, None])))
-    lam = (n * light).sum(-1).clamp(min=0) * 0.7 + 0.3
-    colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
-    return colour
+    for c, h, alb in boxes:
+        c = torch.tensor(c, device=dev); h = torch.tensor(h, device=dev)
+        inv = 1.0 / d
+        lo, hi = (c - h - o) * inv, (c + h - o) * inv
+        tmin, tmax = torch.minimum(lo, hi), torch.maximum(lo, hi)
+        t1, axis = tmin.max(-1); t2 = tmax.min(-1)[0]
+        hit = (t1 <= t2) & (t1 > 0) & (t1 < best_t)
+        n = torch.zeros(N, 3, device=dev); n.scatter_(1, axis[:, None], -torch.sign(d.gather(1, axis[:, None])))
+        lam = (n * light).sum(-1)
+        lam = (lam.abs() if two_sided else lam.clamp(min=0)) * 0.7 + 0.3
+        colour = torch.where(hit[:, None], torch.tensor(alb, device=dev)[None] * lam[:, None], colour)
+        best_t = torch.where(hit, t1, best_t)
+    return colour, best_t
+
+
+def shade(rays_o, rays_d, scale, bg=1.0):
+    """Closed-form ground-truth colour of the analytic scene (nearest primitive, Lambert + ambient)."""
+    o = rays_o / scale; d = rays_d / scale                           # primitives are in units of scale
+    return _shade_prims(o, d, _SPHERES, [_BOX], bg)[0]
+
+
+# ---- two more analytic scenes in WORLD units, for the ScanNet-shaped (C4) and the unbounded (C5) workloads ------------
+_GREY, _WOOD = (0.75, 0.75, 0.72), (0.55, 0.40, 0.25)
+# a room filling the scale-0.5 box: six thin wall slabs, a table, a cabinet and two spheres; cameras stand inside
+ROOM = dict(
+    spheres=[((0.10, -0.05, -0.20), 0.09, (0.85, 0.25, 0.20)), ((-0.22, 0.18, -0.05), 0.07, (0.20, 0.45, 0.85))],
+    boxes=[((0.0, 0.0, -0.44), (0.46, 0.46, 0.02), _WOOD), ((0.0, 0.0, 0.44), (0.46, 0.46, 0.02), _GREY),
+           ((-0.44, 0.0, 0.0), (0.02, 0.46, 0.46), (0.80, 0.78, 0.70)), ((0.44, 0.0, 0.0), (0.02, 0.46, 0.46), (0.70, 0.78, 0.80)),
+           ((0.0, -0.44, 0.0), (0.46, 0.02, 0.46), (0.78, 0.70, 0.78)), ((0.0, 0.44, 0.0), (0.46, 0.02, 0.46), (0.72, 0.80, 0.72)),
+           ((0.10, -0.05, -0.33), (0.16, 0.10, 0.04), _WOOD), ((-0.30, -0.30, -0.22), (0.08, 0.08, 0.20), (0.35, 0.30, 0.28))],
+    bg=0.0)
+# an unbounded 360-degree scene for scale 16: the small object scene at the centre, a ground slab out to the box and a
+# few large far objects, so that all six occupancy cascades hold something; cameras circle the centre
+UNBOUNDED = dict(
+    spheres=[(tuple(0.5 * v for v in c), 0.5 * r, alb) for c, r, alb in _SPHERES] +
+            [((5.0, 2.0, 1.2), 1.5, (0.8, 0.6, 0.2)), ((-6.0, -4.0, 1.8), 2.0, (0.3, 0.7, 0.7)),
+             ((2.0, -9.0, 2.4), 2.5, (0.7, 0.3, 0.6)), ((-3.0, 11.0, 3.0), 3.0, (0.5, 0.5, 0.8))],
+    boxes=[(tuple(0.5 * v for v in _BOX[0]), tuple(0.5 * v for v in _BOX[1]), _BOX[2]),
+           ((0.0, 0.0, -0.40), (15.5, 15.5, 0.04), (0.45, 0.50, 0.40))],
+    bg=0.0)
+
+
+def scene_inside(xyz, sc):
+    occ = torch.zeros(xyz.shape[0], dtype=torch.bool, device=xyz.device)
+    for c, r, _ in sc["spheres"]:
+        occ |= ((xyz - torch.tensor(c, device=xyz.device)) ** 2).sum(-1) <= r * r
+    for c, h, _ in sc["boxes"]:
+        occ |= ((xyz - torch.tensor(c, device=xyz.device)).abs() <= torch.tensor(h, device=xyz.device)).all(-1)
+    return occ
+
+
+def scene_shade(rays_o, rays_d, sc):
+    """-> colour (N,3), ray parameter of the first hit (inf = nothing): the ground truth and the source of depth priors."""
+    return _shade_prims(rays_o, rays_d, sc["spheres"], sc["boxes"], sc["bg"], two_sided=True)
+
+
+def look_at_poses(positions, targets):
+    """(n,3) camera positions and look-at points -> (n,3,4) c2w in the [right down front] camera frame."""
+    fwd = targets - positions; fwd = fwd / fwd.norm(dim=-1, keepdim=True)
+    up = torch.tensor([0.0, 0.0, 1.0]).expand_as(fwd)
+    right = torch.cross(fwd, up, dim=-1); right = right / right.norm(dim=-1, keepdim=True)
+    down = torch.cross(fwd, right, dim=-1)
+    return torch.stack([right, down, fwd, positions], -1).contiguous()
+
+
+def room_poses(n, seed=0):
+    """ScanNet-shaped sparse views: cameras inside the room at standing height, looking across it."""
+    g = torch.Generator().manual_seed(seed)
+    pos = torch.stack([(torch.rand(n, generator=g) - 0.5) * 0.5, (torch.rand(n, generator=g) - 0.5) * 0.5,
+                       (torch.rand(n, generator=g) - 0.5) * 0.2 + 0.05], -1)
+    tgt = torch.stack([(torch.rand(n, generator=g) - 0.5) * 0.7, (torch.rand(n, generator=g) - 0.5) * 0.7,
+                       (torch.rand(n, generator=g) - 0.5) * 0.3 - 0.15], -1)
+    tgt = torch.where(((tgt - pos).norm(dim=-1, keepdim=True) < 0.15), -pos, tgt)
+    return look_at_poses(pos, tgt)
+
+
+def ring_poses(n, radius=1.3, seed=0):
+    """360-degree capture: cameras on a ring around the centre object, slightly above the ground, looking inwards."""
+    g = torch.Generator().manual_seed(seed)
+    phi = torch.rand(n, generator=g) * 2 * math.pi
+    r = radius * (0.85 + 0.3 * torch.rand(n, generator=g))
+    pos = torch.stack([r * torch.cos(phi), r * torch.sin(phi), 0.15 + 0.5 * torch.rand(n, generator=g)], -1)
+    tgt = torch.stack([0.2 * (torch.rand(n, generator=g) - 0.5), 0.2 * (torch.rand(n, generator=g) - 0.5),
+                       -0.1 * torch.rand(n, generator=g)], -1)
+    return look_at_poses(pos, tgt)
 
 
 def write_nsvf_dataset(root, n_train=24, n_test=4, res=100, scale=0.5, seed=0):

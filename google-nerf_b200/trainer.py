@@ -40,6 +40,7 @@ class _SampleSet:
         self.pix_idxs = torch.zeros(n, dtype=torch.int64, device=dev)
         self.hits_cnt = e(n, dt=torch.int32); self.hits_t = e(n, 1, 2); self.hits_idx = e(n, 1, dt=torch.int64)
         self.noise = e(n)
+        self.prior = torch.zeros(n, device=dev)                            # depth-prior disparity per ray (<= 0: none)
         self.march_ws = e(n, 64, dt=torch.int32)
         self.rays_a = e(n, 3, dt=torch.int64)
         self.counter = torch.zeros(4, dtype=torch.int32, device=dev)      # [0] = #samples (device-side count)
@@ -52,7 +53,7 @@ class NGPTrainer:
                  T_threshold=1e-4, lambda_opa=1e-3, loss_scale=16384.0, samples_per_ray=96, seed=0,
                  use_graph=True, process_group=None, grid_update_interval=16, warmup_steps=256, data_parallel=True,
                  comm=None, comm_in_graph=False, grad_fp16=None, erode=False, scale_growth_interval=0,
-                 serialize_mma=False):
+                 serialize_mma=False, lambda_depth=0.0):
         """model: NGP with either encoding (HashGrid: networks.py:39-47; Frequency: networks.py:49-53).
         erode: the reference passes erode=True for colmap scenes (train.py:148).  loss_scale: start value of the
         device-side loss scaler.  The reference's fp16 backward pass runs at tcnn's internal 128 TIMES Lightning's
@@ -64,6 +65,7 @@ class NGPTrainer:
         self.hashed = model.encoding == "HashGrid"
         self.k1 = model.k1
         self.erode, self.serialize_mma = bool(erode), int(bool(serialize_mma))
+        self.lambda_depth = float(lambda_depth)
         self.dev = model.center.device
         if self.dev.type != "cuda":
             raise RuntimeError("NGPTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -188,6 +190,10 @@ class NGPTrainer:
         self.sigmas, self.rgbs = e(cap), e(cap, 3)
         self.opacity, self.depth = e(n), e(n)
         self.rgb_out = e(n, 3)
+        if self.lambda_depth > 0:
+            self.depth_sq, self.rgb_lin = e(n), e(n, 3)
+            self.dL_drgb, self.dL_dopacity, self.dL_ddepth = e(n, 3), e(n), e(n)
+            self.zeros_n, self.depth_stats = torch.zeros(n, device=dev), torch.zeros(8, device=dev)
         # [alive count, loss] side by side, so that the compositing launch clears both with one memset
         self._scalars = torch.zeros(4, dtype=torch.int32, device=dev)
         self.alive_cnt, self.loss = self._scalars[0:1], self._scalars[1:2].view(_f32)
@@ -233,10 +239,26 @@ class NGPTrainer:
         call("b2n_field_mlp_fw", P(self.enc), self.k1, P(s.dirs), P(self.w_image), cap, P(nd), P(self.sigmas),
              P(self.rgbs), P(self.h))
         # compositing + loss (the loss scale is read from the device-side scaler)
-        call("b2n_composite_loss_fwbw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(s.target),
-             self.T_threshold, n, self.bg, self.lambda_opa, self.loss_scale, P(self.opacity), P(self.depth),
-             P(self.rgb_out), P(self.loss), P(self.dL_dsigmas), P(self.dL_drgbs), P(self.alive_idx),
-             P(self.alive_cnt), P(self.hyper[4:]))
+        if self.lambda_depth > 0:
+            # depth prior: its medians need every ray's depth before any gradient exists, so compositing forward, the
+            # two loss kernels and compositing backward (with dL/ddepth) are separate launches here
+            ls_dev = P(self.hyper[4:])
+            self._scalars.zero_()
+            call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a),
+                 self.T_threshold, n, P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb_lin))
+            call("b2n_nerf_loss_fwbw", P(self.rgb_lin), P(self.opacity), P(s.target), n, self.bg, self.lambda_opa,
+                 self.loss_scale, P(self.rgb_out), P(self.loss), P(self.dL_drgb), P(self.dL_dopacity), ls_dev)
+            call("b2n_ssi_depth_loss_fwbw", P(self.depth), P(s.prior), n, self.lambda_depth, self.loss_scale, ls_dev,
+                 P(self.loss), P(self.dL_ddepth), P(self.depth_stats))
+            call("b2n_composite_train_bw", P(self.dL_dopacity), P(self.dL_ddepth), P(self.zeros_n), P(self.dL_drgb),
+                 P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(self.opacity), P(self.depth),
+                 P(self.depth_sq), P(self.rgb_lin), self.T_threshold, n, P(self.dL_dsigmas), P(self.dL_drgbs),
+                 P(self.alive_idx), P(self.alive_cnt))
+        else:
+            call("b2n_composite_loss_fwbw", P(self.sigmas), P(self.rgbs), P(s.deltas), P(s.ts), P(s.rays_a), P(s.target),
+                 self.T_threshold, n, self.bg, self.lambda_opa, self.loss_scale, P(self.opacity), P(self.depth),
+                 P(self.rgb_out), P(self.loss), P(self.dL_dsigmas), P(self.dL_drgbs), P(self.alive_idx),
+                 P(self.alive_cnt), P(self.hyper[4:]))
         # field backward (gradients carry the loss scale; parameter gradients are unscaled inside Adam)
         # only the samples composited before each ray's early stop carry gradient: the two heavy backward kernels
         # run over that compacted list (alive_cnt is a device-side count)
@@ -374,14 +396,18 @@ class NGPTrainer:
             s.img_idxs.copy_(batch["img_idxs"], non_blocking=non_blocking)
             s.pix_idxs.copy_(batch["pix_idxs"], non_blocking=non_blocking)
             s.target.copy_(batch["rgb"], non_blocking=non_blocking)
+            if self.lambda_depth > 0:
+                s.prior.copy_(batch["disp"], non_blocking=non_blocking)
         else:
             s.rays_o.copy_(batch[0], non_blocking=non_blocking)
             s.rays_d.copy_(batch[1], non_blocking=non_blocking)
             s.target.copy_(batch[2], non_blocking=non_blocking)
+            if self.lambda_depth > 0:
+                s.prior.copy_(batch[3], non_blocking=non_blocking)
         s.marched = False
 
-    def set_batch(self, rays_o, rays_d, target_rgb):
-        self._load(self.sets[self.cur], (rays_o, rays_d, target_rgb))
+    def set_batch(self, rays_o, rays_d, target_rgb, prior_disp=None):
+        self._load(self.sets[self.cur], (rays_o, rays_d, target_rgb) + ((prior_disp,) if prior_disp is not None else ()))
 
     def _set_hyper(self):
         # a fresh pageable tensor per step: the driver stages the copy at once, so the host may run many graph replays
@@ -389,13 +415,13 @@ class NGPTrainer:
         packed = struct.unpack("i", struct.pack("f", float(self.lr)))[0]
         self.hyper[:2].copy_(torch.tensor([packed, self.step_count], dtype=torch.int32), non_blocking=True)
 
-    def step(self, rays_o=None, rays_d=None, target_rgb=None, next_batch=None):
+    def step(self, rays_o=None, rays_d=None, target_rgb=None, next_batch=None, prior_disp=None):
         """One optimisation step on the given (or previously set / pre-marched) batch.  `next_batch`, if given, is
         marched concurrently for the following step.  Returns the device loss tensor; no host synchronisation."""
         p = self.cur
         s = self.sets[p]
         if rays_o is not None:
-            self._load(s, (rays_o, rays_d, target_rgb))
+            self._load(s, (rays_o, rays_d, target_rgb) + ((prior_disp,) if prior_disp is not None else ()))
         if self.step_count % self.S == 0:
             self.update_density_grid(warmup=self.step_count < self.warmup_steps)
             s.marched = False                                # (never pre-marched across an update anyway)

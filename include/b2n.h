@@ -341,6 +341,16 @@ B2N_API int b2n_nerf_loss_fwbw(const float *rgb, const float *opacity, const flo
                        float bg, float lambda_opa, float loss_scale, float *rgb_out, float *loss_dev,
                        float *dL_drgb, float *dL_dopacity, const float *loss_scale_dev, void *stream);
 
+/* shiftscale_inv_depthloss (losses.py:5-23) of a ray batch, forward + backward in one launch without host
+ * synchronisation: p = 1/depth (rendered depth, n_rays), g = prior_disp (image-based disparity prior, e.g. LeReS);
+ * rays with prior_disp <= 0 or depth <= 1e-6 are left out.  t = torch.median (lower middle), s = mean |x - t|,
+ * loss += lambda * mean(((p - t_p)/s_p - (g - t_g)/s_g)^2) is ADDED to *loss_dev, dL_ddepth (n_rays) receives the
+ * gradient (autograd-exact through the median and the deviation), times loss_scale (or *loss_scale_dev when
+ * non-NULL).  stats (may be NULL): 5 floats {n_valid, t_p, s_p, t_g, s_g}. */
+B2N_API int b2n_ssi_depth_loss_fwbw(const float *depth, const float *prior_disp, int64_t n_rays, float lambda,
+                                    float loss_scale, const float *loss_scale_dev, float *loss_dev,
+                                    float *dL_ddepth, float *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

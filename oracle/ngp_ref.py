@@ -227,6 +227,24 @@ def nerf_loss(results, target_rgb, lambda_opa=1e-3):
     return d_rgb.mean() + d_opa.mean()
 
 
+def shiftscale_inv_depthloss(disp_pred, disp_gt):
+    """losses.py:5-23 verbatim."""
+    t_pred = torch.median(disp_pred)
+    s_pred = torch.mean(torch.abs(disp_pred - t_pred))
+    t_gt = torch.median(disp_gt)
+    s_gt = torch.mean(torch.abs(disp_gt - t_gt))
+    disp_pred_n = (disp_pred - t_pred) / s_pred
+    disp_gt_n = (disp_gt - t_gt) / s_gt
+    return (disp_pred_n - disp_gt_n) ** 2
+
+
+def depth_prior_loss(results, prior_disp, lambda_depth):
+    """The SCADE-style depth-prior term on top of NeRFLoss: lambda * mean(shiftscale_inv_depthloss(1/depth, prior))
+    over the rays that have a prior (> 0) and a rendered depth (> 1e-6)."""
+    valid = (prior_disp > 0) & (results["depth"].detach() > 1e-6)
+    return lambda_depth * shiftscale_inv_depthloss(1.0 / results["depth"][valid], prior_disp[valid]).mean()
+
+
 class AdamRef:
     """apex FusedAdam(lr, eps=1e-15) semantics (train.py:112): betas (0.9,0.999), bias correction, no decay."""
 

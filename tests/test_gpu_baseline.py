@@ -463,3 +463,87 @@ def test_data_parallel_equals_single_gpu(built_lib, comm):
                         os.path.join(ROOT, "tests", "dist_nccl_check.py")], env=env, capture_output=True, text=True,
                        timeout=600)
     assert p.returncode == 0 and "dist_nccl_check ok" in p.stdout, p.stdout[-2000:] + p.stderr[-4000:]
+
+
+def test_ssi_depth_loss_kernel_matches_reference_formula(built_lib):
+    """b2n_ssi_depth_loss_fwbw vs autograd through the reference's shiftscale_inv_depthloss (losses.py:5-23): loss,
+    medians, deviations and dL/ddepth, with invalid rays (no prior / empty ray) left out; even and odd counts."""
+    from oracle import ngp_ref as O
+    L = built_lib
+    g = torch.Generator().manual_seed(3)
+    for n in (8192, 4097, 300):
+        depth = (torch.rand(n, generator=g) * 3 + 0.2)
+        prior = 1.0 / (depth * (0.5 + torch.rand(1, generator=g)) + 0.3 + 0.1 * torch.randn(n, generator=g).abs())
+        prior[::17] = 0.0                                   # rays without a prior
+        depth[5::31] = 0.0                                  # empty rays
+        d_r = depth.clone().requires_grad_(True)
+        loss_ref = O.depth_prior_loss({"depth": d_r}, prior, 0.25)
+        loss_ref.backward()
+        dd, pp = depth.to(DEV), prior.to(DEV)
+        loss = torch.tensor([1.5], device=DEV); grad = torch.full((n,), 7.0, device=DEV); stats = torch.zeros(8, device=DEV)
+        L.call("b2n_ssi_depth_loss_fwbw", L.ptr(dd), L.ptr(pp), n, 0.25, 4.0, None, L.ptr(loss), L.ptr(grad), L.ptr(stats))
+        valid = (prior > 0) & (depth > 1e-6)
+        assert int(stats[0].item()) == int(valid.sum())
+        assert float(stats[1].item()) == float(torch.median(1.0 / depth[valid]))          # torch's lower median, exactly
+        assert float(stats[3].item()) == float(torch.median(prior[valid]))
+        assert abs(loss.item() - 1.5 - loss_ref.item()) <= 1e-5 * abs(loss_ref.item()) + 1e-6   # ADDED to the loss word
+        sc = d_r.grad.abs().max().item()
+        assert (grad.cpu() / 4.0 - d_r.grad).abs().max().item() <= 2e-5 * sc
+        assert float(grad[~valid.to(DEV)].abs().max()) == 0.0
+    # no valid ray at all: zero gradient, loss untouched
+    z = torch.zeros(64, device=DEV); loss = torch.tensor([2.0], device=DEV); grad = torch.ones(64, device=DEV)
+    L.call("b2n_ssi_depth_loss_fwbw", L.ptr(z), L.ptr(z), 64, 1.0, 1.0, None, L.ptr(loss), L.ptr(grad), None)
+    assert loss.item() == 2.0 and float(grad.abs().max()) == 0.0
+
+
+def test_c4_depth_prior_training_step_matches_oracle(built_lib):
+    """BASELINE config 4 shape: ScanNet-shaped 624x468 cameras (K of datasets/scannet.py:32-35 scaled), scale 0.5, one
+    training step with the LeReS-style depth-prior term against the oracle's render + NeRFLoss + depth-prior loss."""
+    from google_nerf_b200 import synthetic as syn
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.trainer import NGPTrainer
+    from oracle import ngp_ref as O
+    n, scale, lam = 2048, 0.5, 0.1
+    W, H = 624, 468
+    K = syn.intrinsics(W, H, fx=577.87 * 624 / 640)
+    dirs = syn.directions(W, H, K); poses = syn.hemisphere_poses(18, radius=3.0, seed=8)
+    g = torch.Generator().manual_seed(12)
+    ii = torch.randint(18, (n,), generator=g); pi = torch.randint(W * H, (n,), generator=g)
+    rays_o, rays_d = syn.get_rays(dirs[pi], poses[ii])
+    noise = torch.rand(n, generator=g); target = torch.rand(n, 3, generator=g)
+    ref = O.NGPRef(scale, log2_T=15, seed=3)
+    with torch.no_grad():
+        ref.xyz_params[ref.n_mlp:] = (torch.rand(ref.layout["n_params"], generator=g) * 2 - 1) * 0.5
+    ref.density_bitfield = syn.bitfield_from_grid(syn.density_grid(scale, 1))
+    res = O.render(ref, rays_o, rays_d.clone(), noise=noise)
+    # prior = the oracle's own depth under a random affine map of the disparity + noise (SURVEY 8d), missing on some rays
+    with torch.no_grad():
+        disp = 1.0 / res["depth"].clamp(min=1e-3)
+        prior = (0.7 * disp + 0.2 + 0.02 * torch.randn(n, generator=g)).clamp(min=1e-3)
+        prior[res["depth"] <= 1e-6] = 0.0
+        prior[::13] = 0.0
+    loss_ref = O.nerf_loss(res, target) + O.depth_prior_loss(res, prior, lam)
+    loss_ref.backward()
+    model = NGP(scale, log2_T=15).to(DEV)
+    model.xyz_encoder.params.data.copy_(ref.xyz_params.detach()); model.rgb_net.params.data.copy_(ref.rgb_params.detach())
+    model.density_bitfield.copy_(ref.density_bitfield)
+    tr = NGPTrainer(model, n_rays=n, use_graph=False, samples_per_ray=200, grid_update_interval=10 ** 9, lambda_depth=lam)
+    tr.step_count = 1
+    tr.fixed_noise = noise.to(DEV)
+    tr.set_batch(rays_o.to(DEV), rays_d.to(DEV), target.to(DEV), prior.to(DEV))
+    sset = tr.sets[tr.cur]
+    tr._set_hyper(); tr._march(sset); tr._forward_backward(sset)
+    assert int(sset.counter[0].item()) == res["total_samples"] > 1000
+    torch.testing.assert_close(tr.depth.cpu(), res["depth"].detach(), rtol=5e-3, atol=5e-3)
+    assert abs(tr.loss.item() - loss_ref.item()) < 3e-3 * abs(loss_ref.item()), (tr.loss.item(), loss_ref.item())
+    rep = _grad_report((tr.g_xyz, tr.g_rgb), ref, ref.n_mlp, ref.layout["offsets"], unscale=1.0 / tr.loss_scale)
+    print("\n[C4 depth-prior step] " + " ".join(f"{k}=({v[0]:.1e},{v[1]:.1e})" for k, v in rep.items()))
+    for k, (mx, l2, frac) in rep.items():
+        assert (mx <= 5e-3) if k.startswith("W") else (l2 <= 2e-2 and mx <= 1e-1), (k, mx, l2)
+    # and the step trains: graph replay, loss goes down
+    tr2 = NGPTrainer(NGP(scale, log2_T=15).to(DEV), n_rays=n, use_graph=True, samples_per_ray=200,
+                     grid_update_interval=10 ** 9, lambda_depth=lam)
+    tr2.model.density_bitfield.copy_(ref.density_bitfield); tr2.step_count = 1
+    tgt = syn.shade(rays_o, rays_d, scale).to(DEV)
+    ls = [float(tr2.step(rays_o.to(DEV), rays_d.to(DEV), tgt, prior_disp=prior.to(DEV)).item()) for _ in range(25)]
+    assert ls[-1] < 0.7 * ls[0], ls
