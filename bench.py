@@ -212,7 +212,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- kernel table
 # algorithmic bytes per unit and the roofline that bounds each kernel
-def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16):
+def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16, fused_scatter):
     s, r, a = n_samples, n_rays, n_alive
     gather = "l2" if table_in_l2 else "hbm"                   # 21.8 MiB fp16 table is L2-resident, 185 MiB (T=2^22) is not
     wire = (world - 1) * ((2 if grad16 else 4) + 2)           # NVLink bytes per owned parameter: W-1 gradient reads + W-1 fp16 stores
@@ -227,7 +227,8 @@ def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16):
         # the tensor roofline; their algorithmic traffic is enc 64 + dirs 12 + sigma 4 + rgb 12 + h 32 = 124 B/sample
         # forward, enc 64 + h 32 + dirs 12 + rgb 12 + dL 16 + index 4 in and dL/denc 64 out = 204 B/alive sample backward
         "b2n_field_mlp_fw": ("hbm", 124 * s),
-        "b2n_field_mlp_bw": ("hbm", 204 * a),
+        # (+ 1100 - 64 B/alive sample when the hash-grid scatter is fused in: the dL/denc store becomes the table reds)
+        "b2n_field_mlp_bw": ("l2" if (fused_scatter and table_in_l2) else "hbm", (204 + (1036 if fused_scatter else 0)) * a),
         "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_composite_loss_fwbw": ("hbm", 40 * s + 76 * r),
         "b2n_composite_train_fw": ("hbm", 24 * s + 48 * r), "b2n_composite_train_bw": ("hbm", 40 * s + 96 * r),
@@ -300,16 +301,18 @@ def api_path_rate(wl, dev, steps=24):
     dd, pp = wl.dirs.to(dev), wl.poses.to(dev)
     g = torch.Generator(device=dev).manual_seed(5)
     kw = {"exp_step_factor": c["esf"]} if c["esf"] else {}
+    # the dataloader's part, done ahead of the timed loop: batch indices and their ground-truth colours on the GPU
+    n_total = 40 + steps
+    img = torch.randint(c["n_img"], (n_total, c["n_rays"]), device=dev, generator=g)
+    pix = torch.randint(c["W"] * c["H"], (n_total, c["n_rays"]), device=dev, generator=g)
+    tgt_all = torch.stack([wl.shade(*syn.get_rays(dd[pix[k]], pp[img[k]]))[0] for k in range(n_total)])
 
     def step(k):
         if k % 16 == 0:
             model.update_density_grid(0.01 * 1024 / 3 ** 0.5, warmup=k < 256)
-        ii = torch.randint(c["n_img"], (c["n_rays"],), device=dev, generator=g)
-        pi = torch.randint(c["W"] * c["H"], (c["n_rays"],), device=dev, generator=g)
-        ro, rd = syn.get_rays(dd[pi], pp[ii])
-        tgt = wl.shade(ro, rd)[0]
+        ro, rd = syn.get_rays(dd[pix[k]], pp[img[k]])           # train.py:150-157
         res = render(model, ro, rd, **kw)
-        loss = sum(v.mean() for v in loss_fn(res, {"rgb": tgt}).values())
+        loss = sum(v.mean() for v in loss_fn(res, {"rgb": tgt_all[k]}).values())
         opt.zero_grad(); loss.backward(); opt.step()
         return loss
 
@@ -325,7 +328,8 @@ def api_path_rate(wl, dev, steps=24):
     return dict(rays_per_s=c["n_rays"] / (ms * 1e-3), ms_per_step=ms, last_loss=float(last.item()),
                 note="render() + NeRFLoss + loss.backward() + FusedAdam.step() (train.py:144-170) through the drop-in "
                      "modules: one fused autograd node (hash gather + tcgen05 field kernels) behind NGP.forward; eager "
-                     "launches, incl. ray generation, ground-truth shading and the grid update every 16 steps")
+                     "launches, incl. get_rays and the grid update every 16 steps; batches (indices + colours) prepared "
+                     "ahead like a DataLoader would")
 
 
 # ---------------------------------------------------------------------------------------------- main arm
@@ -555,7 +559,7 @@ def main():
         gather_loads_per_s = gatherbench(16 << 20, 64)       # 16 MiB: about the fp16 table (21.8 MiB), L2-resident
 
         table_in_l2 = cfg["log2_T"] <= 20
-        costs = kernel_costs(N_RAYS, samples, alive, tr.shard, table_in_l2, world, tr.grad_fp16)
+        costs = kernel_costs(N_RAYS, samples, alive, tr.shard, table_in_l2, world, tr.grad_fp16, tr.hashed and tr.fuse_scatter)
         # the dominant kernel of the step's critical path (ray generation / AABB / marching of the NEXT batch run on
         # the side stream underneath it and are reported separately in `marcher`)
         side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near", "b2n_rays_from_indices")

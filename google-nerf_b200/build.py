@@ -8,16 +8,18 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
-OBJ_DIR = os.path.join(OUT_DIR, "obj")
-LIB = os.path.join(OUT_DIR, "libb2n.so")
+# tuning experiments: B2N_VARIANT=name B2N_EXTRA_FLAGS="-DAGG_RES_DEF=264" python build.py  ->  lib/libb2n_name.so,
+# loaded by pointing B2N_LIB at it (_lib.py); the product build has neither variable set
+VARIANT = os.environ.get("B2N_VARIANT", "")
+EXTRA = os.environ.get("B2N_EXTRA_FLAGS", "").split() if VARIANT else []
+OBJ_DIR = os.path.join(OUT_DIR, "obj" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(OUT_DIR, "libb2n" + ("_" + VARIANT if VARIANT else "") + ".so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 # bit-exact geometry: one IEEE op per source op, no fused multiply-add (DESIGN.md "Numerics")
 PER_FILE = {"geometry.cu": ["-fmad=false"], "march.cu": ["-fmad=false"]}
-if os.environ.get("B2N_BW_TRACE"):            # debug: phase timestamps in the backward field kernel (scratch/bw_trace.py)
-    PER_FILE["field_tc.cu"] = ["-DB2N_BW_TRACE"]
 
 
 def sources():
@@ -37,7 +39,7 @@ def _compile(src, verbose):
     deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not _stale(obj, deps):
         return obj, ""
-    cmd = ["nvcc", *ARCH, *COMMON, *PER_FILE.get(src, []), "-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = ["nvcc", *ARCH, *COMMON, *PER_FILE.get(src, []), *EXTRA, "-c", os.path.join(CSRC, src), "-o", obj]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src}:\n{p.stdout}\n{p.stderr}")

@@ -12,36 +12,7 @@
 // power-of-two size (mask), dense levels overshoot the size by less than one period (conditional subtract).
 // Algorithmic bytes per sample: 12 in + 16 levels x 8 corners x 4 B gathered + 64 out = 588 B.
 #include "common.cuh"
-
-struct GridLevels {
-    int n_levels;
-    float scale[B2N_MAX_LEVELS];
-    uint32_t resolution[B2N_MAX_LEVELS];
-    uint32_t size[B2N_MAX_LEVELS];
-    uint32_t offset[B2N_MAX_LEVELS];
-    uint8_t mode[B2N_MAX_LEVELS];       // 0 dense (index < 2 * size), 1 hashed with a power-of-two size, 2 generic
-    float x_offset, x_scale;
-};
-
-static int to_levels(const b2n_grid_layout *l, GridLevels &g) {
-    B2N_CHECK_ARG(l != nullptr && l->n_features == 2 && l->n_levels >= 1 && l->n_levels <= B2N_MAX_LEVELS,
-                  "hash grid needs n_features == 2 and 1..32 levels");
-    g.n_levels = l->n_levels;
-    g.x_offset = l->x_offset; g.x_scale = l->x_scale;
-    for (int i = 0; i < l->n_levels; ++i) {
-        g.scale[i] = l->scale[i]; g.resolution[i] = l->resolution[i];
-        g.size[i] = l->size[i]; g.offset[i] = l->offset[i];
-        // the stride walk of grid_index on the host: does this level fall through to the hash?
-        const uint32_t res = l->resolution[i], size = l->size[i];
-        uint32_t stride = 1;
-        for (int d = 0; d < 3; ++d)
-            if (stride <= size) stride *= res;
-        const bool hashed = size < stride, pow2 = size && (size & (size - 1)) == 0;
-        const bool dense_ok = !hashed && res >= 2 && (uint64_t)res * res * res <= size;   // index <= res+res^2+res^3 < 2*size
-        g.mode[i] = hashed ? (pow2 ? 1 : 2) : (dense_ok ? 0 : 2);
-    }
-    return 0;
-}
+#include "hashgrid.cuh"
 
 extern "C" int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashmap_size, int base_resolution,
                                    double per_level_scale, b2n_grid_layout *layout) {
@@ -70,18 +41,6 @@ extern "C" int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashma
     return 0;
 }
 
-// entry index of one corner (tiny-cuda-nn grid_index: dense x + y*res + z*res^2 while it fits, otherwise the
-// coherent prime hash), all in wrapping uint32 arithmetic
-__device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size) {
-    uint32_t stride = 1, index = 0;
-    // unrolled over the 3 dims with the early exit of the reference loop
-    if (stride <= size) { index += x * stride; stride *= res; }
-    if (stride <= size) { index += y * stride; stride *= res; }
-    if (stride <= size) { index += z * stride; stride *= res; }
-    if (size < stride) index = x ^ (y * 2654435761u) ^ (z * 805459861u);
-    return index % size;
-}
-
 // Lane mapping of the forward kernel: TWO lanes per sample, lane parity = x-corner (x0 or x0+1); each lane
 // handles the four (y,z) corners of its x.  Entries of x-neighbours are adjacent (dense levels) or, with the
 // coherent prime hash, differ only in their low bits, so the two lanes of a pair hit the same 128-byte line and a
@@ -99,20 +58,6 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t x, uint32_t y, uint32_t 
 #ifndef HG_BW_CTAS
 #define HG_BW_CTAS 16
 #endif
-// the same index without the division (mode from to_levels)
-__device__ __forceinline__ uint32_t grid_index_m(uint32_t x, uint32_t y, uint32_t z, uint32_t res, uint32_t size, int mode) {
-    if (mode == 1) return (x ^ (y * 2654435761u) ^ (z * 805459861u)) & (size - 1);
-    if (mode == 0) {
-        uint32_t index = x + (y + z * res) * res;
-        if (index >= size) {                          // only the x/y/z = res boundary corners; positions inside the box
-            index -= size;                            // overshoot by less than one period
-            if (index >= size) index %= size;         // out-of-box positions stay in bounds like the generic form
-        }
-        return index;
-    }
-    return grid_index(x, y, z, res, size);
-}
-
 struct Corner4 {
     uint32_t idx[4];
     float w[4];
@@ -196,45 +141,13 @@ __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restric
     }
 }
 
-struct Corner8 {
-    uint32_t idx[8];
-    float w[8];
-};
-
-__device__ __forceinline__ void level_corners(float px, float py, float pz, float scale, uint32_t res,
-                                              uint32_t size, uint32_t offset, int mode, Corner8 &c) {
-    const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
-    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
-    const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
-    const uint32_t x0 = (uint32_t)gx, y0 = (uint32_t)gy, z0 = (uint32_t)gz;
-    #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const uint32_t x = x0 + (k & 1), y = y0 + ((k >> 1) & 1), z = z0 + ((k >> 2) & 1);
-        float w = 1.0f;
-        w *= (k & 1) ? wx : 1.0f - wx;
-        w *= (k & 2) ? wy : 1.0f - wy;
-        w *= (k & 4) ? wz : 1.0f - wz;
-        c.idx[k] = offset + grid_index_m(x, y, z, res, size, mode);
-        c.w[k] = w;
-    }
-}
-
 __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restrict__ x,
                                                           const __half *__restrict__ dy, int dy_stride,
                                                           const __grid_constant__ GridLevels g, int64_t n,
                                                           const int32_t *__restrict__ n_dev, float grad_scale,
                                                           float2 *__restrict__ grad_table,
                                                           const int32_t *__restrict__ sample_idx) {
-    // Warp-aggregated scatter.  The 32 lanes of a warp hold 32 CONSECUTIVE packed samples, i.e. neighbours on a ray
-    // (0.0017 apart), so on the coarse levels most lanes fall into the same cell and would hit the same 8 table
-    // entries: L2 serialises atomics per address.  For levels whose cells are wide enough (resolution <= AGG_RES)
-    // runs of lanes with the same cell are summed with a segmented shuffle reduction and only the run's head lane
-    // issues the 8 vector reds; fine levels (one sample per cell) go straight to red.global.add.v2.f32.
-#ifndef AGG_RES_DEF
-#define AGG_RES_DEF 128      // measured: 48 / 96 / 160 / 320 / 600 -> 61.9 / 56.6 / 57.9 / 60.2 / 66.5 us
-#endif
-    const uint32_t AGG_RES = AGG_RES_DEF;
-    const uint32_t FULLM = 0xffffffffu;
+    // warp-aggregated scatter: hashgrid.cuh::scatter_level
     n = b2n_eff_n(n, n_dev);
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -248,47 +161,8 @@ __global__ void __launch_bounds__(128) hashgrid_bw_kernel(const float *__restric
         const __half2 *row = reinterpret_cast<const __half2 *>(dy + ii * dy_stride);
         #pragma unroll 1
         for (int l = 0; l < g.n_levels; ++l) {
-            float2 gr = __half22float2(__ldg(row + l));
-            gr.x = live ? gr.x * grad_scale : 0.f;
-            gr.y = live ? gr.y * grad_scale : 0.f;
-            const uint32_t res = g.resolution[l];
-            Corner8 c;
-            level_corners(px, py, pz, g.scale[l], res, g.size[l], g.offset[l], g.mode[l], c);
-            if (res > AGG_RES) {
-                if (gr.x != 0.0f || gr.y != 0.0f) {
-                    #pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        atomicAdd(grad_table + c.idx[k], make_float2(gr.x * c.w[k], gr.y * c.w[k]));
-                }
-                continue;
-            }
-            // cell key: the integer lattice position (10 bits per axis is enough for res <= 320)
-            const float s = g.scale[l];
-            const uint32_t kx = (uint32_t)floorf(fmaf(s, px, 0.5f)), ky = (uint32_t)floorf(fmaf(s, py, 0.5f)),
-                           kz = (uint32_t)floorf(fmaf(s, pz, 0.5f));
-            const uint32_t key = live ? (kx | (ky << 10) | (kz << 20)) : (0xC0000000u | (uint32_t)lane);
-            const uint32_t prev = __shfl_up_sync(FULLM, key, 1);
-            const bool head = (lane == 0) || (key != prev);
-            const uint32_t heads = __ballot_sync(FULLM, head);
-            const uint32_t above = (lane == 31) ? 0u : (heads & ~((2u << lane) - 1u));   // heads at positions > lane
-            const int seg_end = above ? (__ffs(above) - 2) : 31;
-            float vx[8], vy[8];
-            #pragma unroll
-            for (int k = 0; k < 8; ++k) { vx[k] = gr.x * c.w[k]; vy[k] = gr.y * c.w[k]; }
-            #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const bool take = lane + d <= seg_end;
-                #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const float ox = __shfl_down_sync(FULLM, vx[k], d), oy = __shfl_down_sync(FULLM, vy[k], d);
-                    if (take) { vx[k] += ox; vy[k] += oy; }
-                }
-            }
-            if (head && live) {
-                #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (vx[k] != 0.0f || vy[k] != 0.0f) atomicAdd(grad_table + c.idx[k], make_float2(vx[k], vy[k]));
-            }
+            const float2 gr = __half22float2(__ldg(row + l));
+            scatter_level(px, py, pz, gr.x * grad_scale, gr.y * grad_scale, l, g, grad_table, live, lane);
         }
     }
 }

@@ -15,6 +15,7 @@
 // Backward: the three hidden activations are RECOMPUTED on the tensor cores from enc / [SH | h] (20 kFLOP per sample
 // on a pipe that idles) instead of being written by the forward pass and read back (416 B per sample each way).
 #include "common.cuh"
+#include "hashgrid.cuh"
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -435,7 +436,8 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) field_mlp_bw_kernel(
     const float *__restrict__ dirs, const __half *__restrict__ image, int64_t n, const int32_t *__restrict__ n_dev,
     const float *__restrict__ rgbs, const __half *__restrict__ h_in, float grad_scale, __half *__restrict__ dL_denc,
     float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w, const int32_t *__restrict__ sample_idx,
-    int serialize, int32_t *__restrict__ found_inf) {
+    int serialize, int32_t *__restrict__ found_inf, const float *__restrict__ xyz,
+    const __grid_constant__ GridLevels gl, float2 *__restrict__ grad_table) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     using SM = FieldBwSmem<K1, GROUPS>;
     using I = Img<K1>;
@@ -622,16 +624,43 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) field_mlp_bw_kernel(
         relu_bw_epilogue(tmem_work, Y, G, tid);                              // g1 = . * (hid_s > 0)
         GROUP_STEP_SYNC();
         // ---- step E: layer 1 (K1 -> 64)
+        const bool want_genc = (dL_denc != nullptr) || (grad_table != nullptr);
         if (tid == 0) {
             issue_lock(lock);
             issue_wgrad(tmem + TM_DW1, g_a, enc_a, K1);                       // dW1[out][in] += g1^T . enc
-            if (dL_denc != nullptr) issue_dgrad(tm_d0, g_a, w_addr + I::W1 * 2, 32, 64);   // g_enc = g1 . W1
+            if (want_genc) issue_dgrad(tm_d0, g_a, w_addr + I::W1 * 2, 32, 64);   // g_enc = g1 . W1
             mma_commit(bar);
             issue_unlock(lock);
         }
+        float px = 0.f, py = 0.f, pz = 0.f;
+        if (grad_table != nullptr && live) {      // the sample's position, in flight while the MMAs run
+            px = (__ldg(xyz + 3 * my_s) - gl.x_offset) * gl.x_scale;
+            py = (__ldg(xyz + 3 * my_s + 1) - gl.x_offset) * gl.x_scale;
+            pz = (__ldg(xyz + 3 * my_s + 2) - gl.x_offset) * gl.x_scale;
+        }
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        if (dL_denc != nullptr) {
+        if (grad_table != nullptr) {
+            // Fused hash-grid backward: this thread's dL/denc row (16 levels x 2 features, fp32 straight from TMEM -- no
+            // fp16 rounding, no dL/denc round trip through memory, no second kernel) is scattered into the gradient
+            // table while the other groups of the CTA run their MMA chains.  The row is parked in the thread's own row
+            // of the G tile (its readers, the step-E MMAs, are done) to keep the register footprint of the loop small.
+            {
+                float v[32];
+                tmem_ld32(tmem_work, v);
+                #pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    bad |= !(fabsf(v[4 * c]) <= 3.0e38f) || !(fabsf(v[4 * c + 1]) <= 3.0e38f) ||
+                           !(fabsf(v[4 * c + 2]) <= 3.0e38f) || !(fabsf(v[4 * c + 3]) <= 3.0e38f);
+                    *reinterpret_cast<float4 *>(G + act_off(tid, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
+            }
+            #pragma unroll 1
+            for (int l = 0; l < gl.n_levels; ++l) {
+                const float2 gr = *reinterpret_cast<const float2 *>(G + act_off(tid, l >> 1) + (l & 1) * 8);
+                scatter_level(px, py, pz, gr.x * grad_scale, gr.y * grad_scale, l, gl, grad_table, live, lane);
+            }
+        } else if (dL_denc != nullptr) {
             // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
             float v[32];
             tmem_ld32(tmem_work, v);
@@ -688,33 +717,43 @@ template <int K1, int GROUPS>
 static void launch_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
                       const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs, const b2n_half *h,
                       float grad_scale, b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w,
-                      const int32_t *sample_idx, int serialize, int32_t *found_inf, void *stream) {
+                      const int32_t *sample_idx, int serialize, int32_t *found_inf, const float *xyz,
+                      const GridLevels &gl, float *grad_table, void *stream) {
     const int smem = (int)sizeof(FieldBwSmem<K1, GROUPS>) + 256;
     cudaFuncSetAttribute(field_mlp_bw_kernel<K1, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int64_t n_tiles = (n + 127) / 128;
     field_mlp_bw_kernel<K1, GROUPS><<<b2n_grid((n_tiles + GROUPS - 1) / GROUPS, 1), 128 * GROUPS, smem, (cudaStream_t)stream>>>(
         dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)h,
-        grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w, sample_idx, serialize, found_inf);
+        grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl,
+        (float2 *)grad_table);
 }
 
 extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, int k1,
                                 const float *dirs, const b2n_half *image, int64_t n, const int32_t *n_dev,
                                 const float *rgbs, const b2n_half *h, float grad_scale, b2n_half *dL_denc,
                                 float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx, int serialize,
-                                int32_t *found_inf, void *stream) {
+                                int32_t *found_inf, const float *xyz, const b2n_grid_layout *layout,
+                                float *grad_table, void *stream) {
     B2N_CHECK_ARG(k1 == 32 || k1 == 80, "first-layer width must be 32 (HashGrid) or 80 (Frequency-12)");
     B2N_CHECK_ARG(dL_dsigmas && dL_drgbs && enc && dirs && image && rgbs && h && grad_sigma_w && grad_rgb_w,
                   "gradients in, enc, dirs, weights, rgbs, h and the weight-gradient outputs are required");
     B2N_CHECK_ARG(k1 == 32 || dL_denc == nullptr, "dL/denc exists for the HashGrid configuration only");
     B2N_CHECK_ARG(((uintptr_t)enc & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)dL_denc & 15) == 0,
                   "enc / h / dL_denc must be 16-byte aligned");
+    GridLevels gl = {};
+    if (grad_table != nullptr) {
+        B2N_CHECK_ARG(k1 == 32 && xyz != nullptr && layout != nullptr && dL_denc == nullptr,
+                      "the fused table scatter needs the HashGrid width, xyz and the layout, and replaces dL_denc");
+        if (to_levels(layout, gl)) return 1;
+        B2N_CHECK_ARG(gl.n_levels == 16 && ((uintptr_t)grad_table & 15) == 0, "16 levels x 2 features, 16-byte aligned table");
+    }
     if (n <= 0) return 0;
     if (k1 == 32)
         launch_bw<32, 4>(dL_dsigmas, dL_drgbs, enc, dirs, image, n, n_dev, rgbs, h, grad_scale, dL_denc, grad_sigma_w,
-                         grad_rgb_w, sample_idx, serialize, found_inf, stream);
+                         grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl, grad_table, stream);
     else
         launch_bw<80, 2>(dL_dsigmas, dL_drgbs, enc, dirs, image, n, n_dev, rgbs, h, grad_scale, dL_denc, grad_sigma_w,
-                         grad_rgb_w, sample_idx, serialize, found_inf, stream);
+                         grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl, grad_table, stream);
     B2N_LAUNCH_CHECK();
     return 0;
 }

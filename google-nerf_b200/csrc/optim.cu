@@ -8,7 +8,7 @@
 #define FULL 0xffffffffu
 
 // ------------------------------------------------------------------------------------------------ Adam
-// Per parameter: read p, g, m, v (16 B), write p, m, v (12 B), zero g (4 B), write fp16 copy (2 B) = 34 B.
+// Per parameter: read p, g, m, v (16 B), write p, m, v (12 B), zero g (4 B, optional), write fp16 copy (2 B) = 34 B.
 // hyper (b2n_hyper, optional): learning rate, step count and the loss-scaler state live on the device so that a captured
 // graph replays with fresh values.  found_inf != 0 (a backward kernel saw a gradient leave the fp16 range) turns the
 // step into "clear the gradient, keep everything else" -- what torch.cuda.amp.GradScaler does for the reference's
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float
                                                    float4 *__restrict__ m, float4 *__restrict__ v,
                                                    __half2 *__restrict__ h, int64_t n4, float lr, float b1,
                                                    float b2, float eps, float inv_scale, int step,
-                                                   const b2n_hyper *__restrict__ hyper) {
+                                                   const b2n_hyper *__restrict__ hyper, int zero_grad) {
     bool skip = false;
     if (hyper != nullptr) {
         lr = hyper->lr;
@@ -27,7 +27,10 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float
     }
     const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
-        if (skip) { g[i] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+        if (skip) {
+            if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
         float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
         float *P = &pp.x, *G = &gg.x, *M = &mm.x, *V = &vv.x;
         #pragma unroll
@@ -38,7 +41,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float
             P[k] -= lr * (M[k] / c1) / (sqrtf(V[k] / c2) + eps);
         }
         p[i] = pp; m[i] = mm; v[i] = vv;
-        g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zero_grad) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (h != nullptr) {
             h[2 * i] = __floats2half2_rn(pp.x, pp.y);
             h[2 * i + 1] = __floats2half2_rn(pp.z, pp.w);
@@ -48,7 +51,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float4 *__restrict__ p, float
 
 extern "C" int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
                              int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale,
-                             int step, const b2n_hyper *hyper_dev, void *stream) {
+                             int step, const b2n_hyper *hyper_dev, int zero_grad, void *stream) {
     B2N_CHECK_ARG(n % 4 == 0, "parameter count must be a multiple of 4");
     B2N_CHECK_ARG(step >= 1 || hyper_dev != nullptr, "step is 1-based");
     if (n == 0) return 0;
@@ -57,7 +60,7 @@ extern "C" int b2n_adam_step(float *param, float *grad, float *exp_avg, float *e
 #endif
     b2n_launch(adam_kernel, b2n_grid(b2n_blocks(n / 4, 256), ADAM_CTAS), 256, (cudaStream_t)stream,
                (float4 *)param, (float4 *)grad, (float4 *)exp_avg, (float4 *)exp_avg_sq, (__half2 *)half_copy, n / 4,
-               lr, beta1, beta2, eps, inv_scale, step, hyper_dev);
+               lr, beta1, beta2, eps, inv_scale, step, hyper_dev, zero_grad);
     B2N_LAUNCH_CHECK();
     return 0;
 }

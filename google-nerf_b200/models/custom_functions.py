@@ -31,16 +31,49 @@ class RayMarcher(torch.autograd.Function):
     """-> rays_a (N_rays,3) [ray_idx, start_idx, N_samples], xyzs, dirs (N,3), deltas, ts (N), total_samples.
 
     ``RayMarcher.noise`` may be set to a (N_rays) tensor to fix the per-ray jitter (parity tests share it with
-    the oracle); otherwise it is drawn with torch.rand_like as at custom_functions.py:84."""
+    the oracle); otherwise it is drawn with torch.rand_like as at custom_functions.py:84.
+
+    ``RayMarcher.sync_free`` (default True): the reference reads the sample count back to the host to size its outputs
+    (custom_functions.py:92-97), which stalls the host once per step.  Here the first call does the same; later calls
+    size the buffers from the previous step's count with 4x headroom (capped at N_rays * max_samples, the reference's
+    own allocation), keep the count on the device -- it travels to the field kernels as the ``_b2n_n_dev`` attribute of
+    ``xyzs`` -- and return ``total_samples`` as a device scalar.  Rows past the count are never read.  The count of a
+    step is checked one step later; a step whose samples did not fit is truncated ray-wise by the marcher and reported
+    with a warning (it takes a 4x jump of the sample count between two consecutive steps)."""
     noise = None
+    sync_free = True
+    _state = {}
 
     @staticmethod
     @_fwd32
     def forward(ctx, rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, grid_size,
                 max_samples):
         noise = RayMarcher.noise if RayMarcher.noise is not None else torch.rand_like(rays_o[:, 0])
-        rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(
-            rays_o, rays_d, hits_t, density_bitfield, cascades, scale, exp_step_factor, noise, grid_size, max_samples)
+        args = (rays_o.contiguous(), rays_d.contiguous(), hits_t.contiguous(), density_bitfield, cascades, scale,
+                exp_step_factor, noise, grid_size, max_samples)
+        n = rays_o.shape[0]
+        st = RayMarcher._state.setdefault((rays_o.device, n), {"last": None, "pending": False})
+        if st["pending"] and st["event"].query():
+            st["pending"] = False
+            st["last"] = int(st["host"][3])
+            if int(st["host"][2]):
+                import warnings
+                warnings.warn("RayMarcher: a step produced more than 4x the samples of the step before; its rays were "
+                              "truncated to the buffer (set RayMarcher.sync_free = False for exact sizing)")
+        if not RayMarcher.sync_free or st["last"] is None or n == 0:
+            rays_a, xyzs, dirs, deltas, ts, counter = vren.raymarching_train(*args)
+            st["last"] = int(xyzs.shape[0])
+        else:
+            cap = min(n * int(max_samples), max(4 * st["last"], 16 * n))
+            rays_a, counter, ws = vren.raymarching_train_count(*args, capacity=cap)
+            xyzs, dirs, deltas, ts = vren.raymarching_train_write(*args, rays_a, cap, ws)
+            xyzs._b2n_n_dev = counter                       # device-side sample count for the field kernels
+            if not st["pending"]:
+                if "host" not in st:
+                    st["host"], st["event"] = torch.zeros(4, dtype=torch.int32).pin_memory(), torch.cuda.Event()
+                st["host"].copy_(counter, non_blocking=True)
+                st["event"].record()
+                st["pending"] = True
         total_samples = counter[0]
         ctx.save_for_backward(rays_a, ts)
         return rays_a, xyzs, dirs, deltas, ts, total_samples

@@ -35,15 +35,17 @@ class _FieldFn(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, d, xyz_params, rgb_params, model):
         L.require_cuda(x, d, xyz_params, rgb_params)
+        # a sync-free RayMarcher hands over buffers sized with headroom and the true sample count on the device
+        n_dev = getattr(x, "_b2n_n_dev", None)
         x, d = x.contiguous(), d.contiguous()
         p16, image = model._fused_state(x.device)
         n, dev = x.shape[0], x.device
-        enc = model._encode(x, p16)
+        enc = model._encode(x, p16, n_dev=n_dev)
         sigmas = torch.empty(n, device=dev); rgbs = torch.empty(n, 3, device=dev)
         h = torch.empty(n, 16, dtype=torch.float16, device=dev)
-        L.call("b2n_field_mlp_fw", L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, None, L.ptr(sigmas), L.ptr(rgbs),
-               L.ptr(h))
-        ctx.model = model
+        L.call("b2n_field_mlp_fw", L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, L.ptr(n_dev), L.ptr(sigmas),
+               L.ptr(rgbs), L.ptr(h))
+        ctx.model, ctx.n_dev = model, n_dev
         ctx.save_for_backward(x, d, enc, h, rgbs, image)
         return sigmas, rgbs.to(torch.float16)
 
@@ -61,10 +63,12 @@ class _FieldFn(torch.autograd.Function):
         hashed = model.encoding == "HashGrid"
         denc = torch.empty(n, 32, dtype=torch.float16, device=dev) if hashed else None
         found = torch.zeros(1, dtype=torch.int32, device=dev)
-        L.call("b2n_field_mlp_bw", L.ptr(ds), L.ptr(dc), L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, None,
-               L.ptr(rgbs), L.ptr(h), 1.0 / S, L.ptr(denc), L.ptr(g_xyz), L.ptr(g_rgb), None, 0, L.ptr(found))
+        nd = L.ptr(ctx.n_dev)
+        L.call("b2n_field_mlp_bw", L.ptr(ds), L.ptr(dc), L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, nd,
+               L.ptr(rgbs), L.ptr(h), 1.0 / S, L.ptr(denc), L.ptr(g_xyz), L.ptr(g_rgb), None, 0, L.ptr(found),
+               None, None, None)
         if hashed:
-            L.call("b2n_hashgrid_bw", L.ptr(x), L.ptr(denc), 32, model._layout, n, None, 1.0 / S,
+            L.call("b2n_hashgrid_bw", L.ptr(x), L.ptr(denc), 32, model._layout, n, nd, 1.0 / S,
                    L.ptr(g_xyz[xe.mlp.n_params:]), None)
         g_rgb[:1] += torch.where(found > 0, float("inf"), 0.0)
         return None, None, g_xyz, g_rgb, None

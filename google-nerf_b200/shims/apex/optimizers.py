@@ -1,6 +1,6 @@
 """apex.optimizers.FusedAdam as used at ngp_pl/train.py:112 (`FusedAdam(net_params, lr, eps=1e-15)`): Adam with bias
-correction and no weight decay, one fused b2n_adam_step launch per parameter tensor (CUDA fp32 tensors whose size
-is a multiple of 4; anything else falls through to the same formula in torch ops)."""
+correction and no weight decay, one fused b2n_adam_step launch per parameter tensor.  Parameters must be CUDA fp32
+tensors (apex's own requirement); there is no CPU path."""
 import torch
 
 from google_nerf_b200 import _lib as L
@@ -41,15 +41,20 @@ class FusedAdam(torch.optim.Optimizer):
                     st["exp_avg_sq"] = torch.zeros_like(p, dtype=torch.float32)
                 st["step"] += 1
                 g = p.grad
-                if p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.numel() % 4 == 0:
-                    g = g.to(torch.float32).contiguous().clone()      # the kernel zeroes the gradient buffer it is given
-                    L.call("b2n_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), None,
-                           p.numel(), float(group["lr"]), float(b1), float(b2), float(group["eps"]), 1.0, st["step"], None)
-                    _bump_version(p)      # the kernel wrote through the raw pointer: consumers that cache derived data
-                                          # by (pointer, version) -- the tinycudann modules' fp16 copy -- must see a change
-                else:
-                    m, v = st["exp_avg"], st["exp_avg_sq"]
-                    m.mul_(b1).add_(g, alpha=1 - b1); v.mul_(b2).addcmul_(g, g, value=1 - b2)
+                if not (p.is_cuda and p.dtype == torch.float32 and p.is_contiguous()):
+                    raise RuntimeError("FusedAdam: parameters must be contiguous CUDA fp32 tensors (no CPU fallback)")
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = g.to(torch.float32).contiguous()
+                n4 = p.numel() // 4 * 4
+                if n4:
+                    L.call("b2n_adam_step", L.ptr(p), L.ptr(g), L.ptr(st["exp_avg"]), L.ptr(st["exp_avg_sq"]), None, n4,
+                           float(group["lr"]), float(b1), float(b2), float(group["eps"]), 1.0, st["step"], None, 0)
+                if n4 < p.numel():                        # a tail shorter than one 16-byte vector: same formula, torch ops on the GPU
+                    sl = slice(n4, p.numel())
+                    pf, gf, m, v = p.view(-1)[sl], g.view(-1)[sl], st["exp_avg"].view(-1)[sl], st["exp_avg_sq"].view(-1)[sl]
+                    m.mul_(b1).add_(gf, alpha=1 - b1); v.mul_(b2).addcmul_(gf, gf, value=1 - b2)
                     c1, c2 = 1 - b1 ** st["step"], 1 - b2 ** st["step"]
-                    p.sub_(group["lr"] * (m / c1) / ((v / c2).sqrt() + group["eps"]))
+                    pf.sub_(group["lr"] * (m / c1) / ((v / c2).sqrt() + group["eps"]))
+                _bump_version(p)          # the kernel wrote through the raw pointer: consumers that cache derived data
+                                          # by (pointer, version) -- the tinycudann modules' fp16 copy -- must see a change
         return loss

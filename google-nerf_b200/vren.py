@@ -153,8 +153,9 @@ def composite_train_bw(dL_dopacity, dL_ddepth, dL_ddepth_sq, dL_drgb, sigmas, rg
     rays_a = _prep(rays_a, torch.int64)
     outs = [_prep(v) for v in (opacity, depth, depth_sq, rgb)]
     N, dev = sigmas.shape[0], sigmas.device
-    dL_dsigmas = torch.zeros(N, dtype=_f32, device=dev)
-    dL_drgbs = torch.zeros(N, 3, dtype=_f32, device=dev)
+    # the kernel writes every sample a ray owns (zeros after an early stop); rows no ray owns are never read downstream
+    dL_dsigmas = torch.empty(N, dtype=_f32, device=dev)
+    dL_drgbs = torch.empty(N, 3, dtype=_f32, device=dev)
     L.call("b2n_composite_train_bw", *[L.ptr(v) for v in g], L.ptr(sigmas), L.ptr(rgbs), L.ptr(deltas), L.ptr(ts),
            L.ptr(rays_a), *[L.ptr(v) for v in outs], float(T_threshold), rays_a.shape[0], L.ptr(dL_dsigmas),
            L.ptr(dL_drgbs), None, None)

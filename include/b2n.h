@@ -245,12 +245,17 @@ B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, con
  * n_dev count list entries and row i of dL_denc belongs to sample sample_idx[i].
  * serialize != 0: MMA issue of the CTA's tile groups goes through a shared-memory lock (validation of the default
  * lock-free accumulation).  found_inf (may be NULL): set to 1 when a gradient left the fp16 range (inf / NaN), the
- * GradScaler signal of the reference's precision=16 training (train.py:265). */
+ * GradScaler signal of the reference's precision=16 training (train.py:265).
+ * Fused hash-grid backward (k1 = 32): with grad_table != NULL (and dL_denc == NULL) every sample's dL/denc row is
+ * scattered straight into the fp32 table gradient (the same warp-aggregated red.global.add as b2n_hashgrid_bw, from the
+ * fp32 accumulator, times grad_scale) inside this kernel; xyz (n_alloc,3) are the sample positions the encoding was
+ * evaluated at and layout its b2n_grid_layout (with the same x_offset / x_scale as the forward gather). */
 B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, int k1,
                              const float *dirs, const b2n_half *image, int64_t n, const int32_t *n_dev,
                              const float *rgbs, const b2n_half *h, float grad_scale, b2n_half *dL_denc,
                              float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx, int serialize,
-                             int32_t *found_inf, void *stream);
+                             int32_t *found_inf, const float *xyz, const b2n_grid_layout *layout,
+                             float *grad_table, void *stream);
 
 /* ---------------------------------------------------------------- multi-GPU: NVLink peer memory ------ */
 /* Data-parallel training (ngp_pl/train.py:197-208: DDPPlugin -> one NCCL gradient all-reduce per step, every rank
@@ -289,13 +294,14 @@ B2N_API int b2n_grad_pack_half(float *grad, b2n_half *grad16, int64_t lo, int64_
 
 /* ---------------------------------------------------------------- optimiser / grid maintenance ------- */
 /* apex FusedAdam step (train.py:112: lr, eps=1e-15, betas (0.9,0.999), bias-corrected, no weight decay)
- * over one flat fp32 parameter; grad is multiplied by inv_scale, then ZEROED; half_copy (may be NULL)
+ * over one flat fp32 parameter; grad is multiplied by inv_scale and, with zero_grad != 0, then ZEROED (the fused
+ * trainer accumulates into it again next step; apex leaves it alone: zero_grad = 0); half_copy (may be NULL)
  * receives the fp16 copy of the updated parameter.  hyper_dev (may be NULL): device b2n_hyper that overrides
  * `lr` / `step` (effective step = step - skipped), divides inv_scale by its loss_scale, and turns the call into
  * "clear the gradient only" while found_inf is set. */
 B2N_API int b2n_adam_step(float *param, float *grad, float *exp_avg, float *exp_avg_sq, b2n_half *half_copy,
                   int64_t n, float lr, float beta1, float beta2, float eps, float inv_scale, int step,
-                  const b2n_hyper *hyper_dev, void *stream);
+                  const b2n_hyper *hyper_dev, int zero_grad, void *stream);
 /* GradScaler bookkeeping after the optimiser step: found_inf (OR-ed with the blocks in hyper_ptrs, a HOST array of
  * `world` device pointers, or NULL) halves loss_scale and counts a skipped step; otherwise growth_interval clean
  * steps in a row double it.  found_inf is left for the caller to clear. */

@@ -516,12 +516,18 @@ def test_c4_depth_prior_training_step_matches_oracle(built_lib):
         ref.xyz_params[ref.n_mlp:] = (torch.rand(ref.layout["n_params"], generator=g) * 2 - 1) * 0.5
     ref.density_bitfield = syn.bitfield_from_grid(syn.density_grid(scale, 1))
     res = O.render(ref, rays_o, rays_d.clone(), noise=noise)
-    # prior = the oracle's own depth under a random affine map of the disparity + noise, missing on some rays
+    # prior = the analytic scene's true disparity under a random affine map + noise (what a monocular depth network
+    # delivers), missing where the ray hits nothing and on every 13th ray.  The random-init field renders
+    # depths unrelated to it, so the residuals are O(1) and the gradient is well conditioned.  (A prior built from the
+    # model's OWN depth makes the normalised residuals ~0.05, and a 1e-3 rounding difference of the rendered depth then
+    # moves the gradient by several percent -- in the oracle just as much as here.)
     with torch.no_grad():
-        disp = 1.0 / res["depth"].clamp(min=1e-3)
+        t_hit = syn._shade_prims(rays_o / scale, rays_d / scale, syn._SPHERES, [syn._BOX], 1.0)[1]
+        disp = torch.where(torch.isfinite(t_hit), 1.0 / t_hit.clamp(min=1e-3), torch.zeros(n))
         prior = (0.7 * disp + 0.2 + 0.02 * torch.randn(n, generator=g)).clamp(min=1e-3)
-        prior[res["depth"] <= 1e-6] = 0.0
+        prior[disp <= 0] = 0.0
         prior[::13] = 0.0
+        assert int((prior > 0).sum()) > 300
     loss_ref = O.nerf_loss(res, target) + O.depth_prior_loss(res, prior, lam)
     loss_ref.backward()
     model = NGP(scale, log2_T=15).to(DEV)
@@ -539,7 +545,7 @@ def test_c4_depth_prior_training_step_matches_oracle(built_lib):
     rep = _grad_report((tr.g_xyz, tr.g_rgb), ref, ref.n_mlp, ref.layout["offsets"], unscale=1.0 / tr.loss_scale)
     print("\n[C4 depth-prior step] " + " ".join(f"{k}=({v[0]:.1e},{v[1]:.1e})" for k, v in rep.items()))
     for k, (mx, l2, frac) in rep.items():
-        assert (mx <= 5e-3) if k.startswith("W") else (l2 <= 2e-2 and mx <= 1e-1), (k, mx, l2)
+        assert (mx <= 5e-3) if k.startswith("W") else (l2 <= 1e-2 and mx <= 6e-2), (k, mx, l2)
     # and the step trains: graph replay, loss goes down
     tr2 = NGPTrainer(NGP(scale, log2_T=15).to(DEV), n_rays=n, use_graph=True, samples_per_ray=200,
                      grid_update_interval=10 ** 9, lambda_depth=lam)

@@ -420,7 +420,7 @@ def test_adam_matches_reference_formula(mods):
         pr.grad = gr.clone(); opt.step()
         gd = (gr * 128).to(DEV)
         L.call("b2n_adam_step", L.ptr(p), L.ptr(gd), L.ptr(m), L.ptr(v), L.ptr(h), n, 1e-2, 0.9, 0.999, 1e-15,
-               1.0 / 128, step, None)
+               1.0 / 128, step, None, 1)
         assert float(gd.abs().max()) == 0.0                      # gradient buffer is zeroed by the step
         torch.testing.assert_close(p.cpu(), pr.detach(), rtol=1e-5, atol=1e-6)
         assert torch.equal(h.cpu(), p.cpu().half())

@@ -82,7 +82,7 @@ def test_adam_step_peer_world_1_equals_adam_step(block, half):
     p1, m1, v1 = p0.clone(), m0.clone(), v0.clone()
     h1 = torch.empty(n, dtype=torch.float16, device=DEV)
     L.call("b2n_adam_step", L.ptr(p1), L.ptr(g_seen), L.ptr(m1), L.ptr(v1), L.ptr(h1), n, 1e-2, 0.9, 0.999, 1e-15,
-           1.0 / 128, 7, None)
+           1.0 / 128, 7, None, 1)
     # fused path, shard = the middle half of the vector
     first, cnt = n // 4, n // 2
     p2, m2, v2 = p0[first:first + cnt].clone(), m0[first:first + cnt].clone(), v0[first:first + cnt].clone()
@@ -113,16 +113,16 @@ def test_adam_step_peer_world_1_equals_adam_step(block, half):
            1e-15, 1.0, 0, L.ptr(hyper), hyp, None)
     assert torch.equal(p3, p2) and torch.equal(m3, m2)               # skipped
     p4, m4, v4, g4 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
-    L.call("b2n_adam_step", L.ptr(p4), L.ptr(g4), L.ptr(m4), L.ptr(v4), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper))
+    L.call("b2n_adam_step", L.ptr(p4), L.ptr(g4), L.ptr(m4), L.ptr(v4), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper), 1)
     assert torch.equal(p4, p1) and torch.equal(m4, m1) and float(g4.abs().max()) == 0.0   # skipped, gradient cleared
     L.call("b2n_scaler_update", L.ptr(hyper), hyp, 1)
     assert hyper.tolist()[2:6] == [1, 1, f2i(64.0), 0]               # found_inf left for the caller, skipped, scale / 2
     hyper[2] = 0
     # clean step: effective step = step - skipped = 6, gradients divided by the device loss scale (64)
     p5, m5, v5, g5 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
-    L.call("b2n_adam_step", L.ptr(p5), L.ptr(g5), L.ptr(m5), L.ptr(v5), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper))
+    L.call("b2n_adam_step", L.ptr(p5), L.ptr(g5), L.ptr(m5), L.ptr(v5), None, n, 0.0, 0.9, 0.999, 1e-15, 1.0, 0, L.ptr(hyper), 1)
     p6, m6, v6, g6 = p1.clone(), m1.clone(), v1.clone(), grad.clone()
-    L.call("b2n_adam_step", L.ptr(p6), L.ptr(g6), L.ptr(m6), L.ptr(v6), None, n, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 64, 6, None)
+    L.call("b2n_adam_step", L.ptr(p6), L.ptr(g6), L.ptr(m6), L.ptr(v6), None, n, 1e-2, 0.9, 0.999, 1e-15, 1.0 / 64, 6, None, 1)
     assert torch.equal(p5, p6) and torch.equal(v5, v6)
     L.call("b2n_scaler_update", L.ptr(hyper), None, 1)
     assert hyper.tolist()[2:6] == [0, 1, f2i(64.0), 0]               # growth_interval 0: the scale never grows
