@@ -165,12 +165,19 @@ __global__ void __launch_bounds__(256) adam_peer_kernel(float4 *__restrict__ p, 
     // a timed-out barrier (sticky error word) means some peer's gradients are incomplete: leave everything untouched
     if (barrier_state != nullptr && barrier_state[1] != 0u) return;
     if (hyper != nullptr) {
+        // GradScaler semantics: any rank's overflow skips the step.  ONE thread per CTA looks at the peers' flags (a
+        // volatile load per thread would put more sectors on NVLink than the gradients themselves).
+        __shared__ int s_bad;
+        if (threadIdx.x == 0) {
+            int bad = hyper->found_inf;
+            for (int r = 0; r < world; ++r)
+                if (hy.p[r] != nullptr) bad |= reinterpret_cast<const volatile b2n_hyper *>(hy.p[r])->found_inf;
+            s_bad = bad;
+        }
+        __syncthreads();
+        if (s_bad) return;                                   // (the gradient vectors are cleared by the caller's memset)
         lr = hyper->lr;
         step = hyper->step - hyper->skipped;
-        int bad = hyper->found_inf;                          // GradScaler semantics: any rank's overflow skips the step
-        for (int r = 0; r < world; ++r)
-            if (hy.p[r] != nullptr) bad |= reinterpret_cast<const volatile b2n_hyper *>(hy.p[r])->found_inf;
-        if (bad) return;                                     // (the gradient vectors are cleared by the caller's memset)
         if (hyper->loss_scale > 0.f) inv_scale /= hyper->loss_scale;
     }
     const float c1 = 1.0f - powf(b1, (float)step), c2 = 1.0f - powf(b2, (float)step);
