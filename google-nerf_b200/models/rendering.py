@@ -15,6 +15,13 @@ def render(model, rays_o, rays_d, **kwargs):
     """rays_o, rays_d (N_rays,3) -> dict.  AABB-clip, clamp the near hit to NEAR_DISTANCE, then train- or
     test-time rendering (rendering.py:26-39)."""
     rays_o = rays_o.contiguous(); rays_d = rays_d.contiguous()
+    if not kwargs.get("test_time", False) and _train_graph_ok(model, rays_o, rays_d, kwargs):
+        # training with this repo's NGP: the whole of render() is ONE autograd node replaying two CUDA graphs
+        # (`graph=False` or RayMarcher.sync_free = False select the launch-by-launch form below)
+        results = _render_train_graph(model, rays_o, rays_d, **kwargs)
+        if kwargs.get("to_cpu", False):
+            results = {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in results.items()}
+        return results
     _, hits_t, _ = RayAABBIntersector.apply(rays_o, rays_d, model.center, model.half_size, 1)
     if hits_t.is_cuda:       # hits_t[(t1 >= 0) & (t1 < NEAR), 0, 0] = NEAR (rendering.py:29) without the boolean-mask sync
         from .. import _lib as L
@@ -173,16 +180,224 @@ class _DeviceLoop:
         return {"opacity": self.opacity.clone(), "depth": self.depth.clone(), "rgb": rgb, "total_samples": total}
 
 
+class _TrainGraph:
+    """The training-time render of rendering.py:117-166 for the autograd API as TWO CUDA-graph replays over static
+    buffers: forward = march (count + write) -> encode -> fused field kernel -> compositing, backward = compositing
+    backward (+ alive list) -> fused field backward -> hash-grid scatter.  The per-step host work of the reference call
+    path (train.py:144-170) drops from ~40 eager launches to two replays; counts stay on the device.  Buffers are sized
+    from the sample count with headroom and grown when a step did not fit (that step's rays are truncated ray-wise by
+    the marcher, reported once, like NGPTrainer)."""
+
+    @classmethod
+    def get(cls, model, n_rays, esf, T_threshold):
+        pool = model.__dict__.setdefault("_train_graphs", {})
+        key = (n_rays, float(esf), float(T_threshold))
+        st = pool.get(key)
+        if st is None:
+            st = pool[key] = cls(model, n_rays, float(esf), float(T_threshold))
+        return st
+
+    def __init__(self, model, n, esf, T_threshold):
+        self.model, self.n, self.esf, self.T = model, n, esf, T_threshold
+        self.dev = model.center.device
+        self.cap = max(128 * n, 4096)
+        self.serial = 0
+        self.host = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.event, self.pending, self.warned = torch.cuda.Event(), False, False
+        self._alloc()
+
+    def _alloc(self):
+        n, cap, dev, m = self.n, self.cap, self.dev, self.model
+        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        self.rays_o, self.rays_d, self.hits, self.noise = e(n, 3), e(n, 3), e(n, 1, 2), e(n)
+        self.hits_cnt, self.hits_idx = e(n, dt=torch.int32), e(n, 1, dt=torch.int64)
+        self.march_ws, self.rays_a = e(n, 64, dt=torch.int32), e(n, 3, dt=torch.int64)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)
+        self.xyzs, self.dirs, self.deltas, self.ts = e(cap, 3), e(cap, 3), e(cap), e(cap)
+        self.enc, self.h = e(cap, m.k1, dt=torch.float16), e(cap, 16, dt=torch.float16)
+        self.sigmas, self.rgbs = e(cap), e(cap, 3)
+        # per-ray outputs side by side (one clone hands them to autograd): opacity | depth | depth_sq | blended rgb
+        self.out = e(6 * n)
+        self.opacity, self.depth, self.depth_sq = self.out[:n], self.out[n:2 * n], self.out[2 * n:3 * n]
+        self.rgb_out = self.out[3 * n:].view(n, 3)
+        self.rgb = e(n, 3)                                    # composited colour before the background blend
+        self.gin = e(6 * n)                                   # incoming gradients, same packing
+        self.gO, self.gD, self.gD2 = self.gin[:n], self.gin[n:2 * n], self.gin[2 * n:3 * n]
+        self.gRGB = self.gin[3 * n:].view(n, 3)
+        self.bg = 1.0 if self.esf == 0 else 0.0               # rendering.py:108-111: white for synthetic scenes, else black
+        self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
+        self.alive_idx, self.alive_cnt = e(cap, dt=torch.int32), torch.zeros(1, dtype=torch.int32, device=dev)
+        self.din_enc = e(cap, 32, dt=torch.float16) if m.encoding == "HashGrid" else None
+        self.g_xyz = torch.zeros(m.xyz_encoder.params.numel(), device=dev)
+        self.g_rgb = torch.zeros(m.rgb_net.params.numel(), device=dev)
+        self.found = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.graphs, self.graph_key = {}, None
+
+    # ---------------------------------------------------------------- kernels (recorded into the graphs)
+    def _fw(self, fixed_noise):
+        from .. import _lib as L
+        m, P, call, n, cap = self.model, L.ptr, L.call, self.n, self.cap
+        p16, image = m._fused_state(self.dev)
+        if not fixed_noise:
+            self.noise.uniform_()
+        call("b2n_ray_aabb_intersect", P(self.rays_o), P(self.rays_d), P(m.center), P(m.half_size), n, 1, 1,
+             P(self.hits_cnt), P(self.hits), P(self.hits_idx))
+        call("b2n_clamp_near", P(self.hits), n, NEAR_DISTANCE)
+        march = (P(self.rays_o), P(self.rays_d), P(self.hits), P(m.density_bitfield), m.cascades, float(m.scale),
+                 self.esf, P(self.noise), m.grid_size, MAX_SAMPLES, n)
+        call("b2n_raymarching_train_count", *march, cap, P(self.rays_a), P(self.counter), P(self.march_ws))
+        call("b2n_raymarching_train_write", *march, P(self.rays_a), P(self.xyzs), P(self.dirs), P(self.deltas),
+             P(self.ts), P(self.march_ws))
+        m._encode(self.xyzs, p16, out=self.enc, n_dev=self.counter)
+        call("b2n_field_mlp_fw", P(self.enc), m.k1, P(self.dirs), P(image), cap, P(self.counter), P(self.sigmas),
+             P(self.rgbs), P(self.h))
+        call("b2n_composite_train_fw", P(self.sigmas), P(self.rgbs), P(self.deltas), P(self.ts), P(self.rays_a),
+             self.T, n, P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb))
+        torch.add(self.rgb, (1 - self.opacity)[:, None], alpha=self.bg, out=self.rgb_out)      # rendering.py:163-164
+
+    def _bw(self):
+        from .. import _lib as L
+        from .. import tinycudann as tcnn
+        m, P, call, n, cap, S = self.model, L.ptr, L.call, self.n, self.cap, tcnn.LOSS_SCALE
+        p16, image = m._fused_state(self.dev)
+        self.gin.mul_(S)                                       # tcnn's loss scale rides on the per-ray gradients
+        if self.bg:
+            self.gO.sub_(self.gRGB.sum(-1), alpha=self.bg)       # the background blend's share of dL/dopacity
+        call("b2n_composite_train_bw", P(self.gO), P(self.gD), P(self.gD2), P(self.gRGB), P(self.sigmas), P(self.rgbs),
+             P(self.deltas), P(self.ts), P(self.rays_a), P(self.opacity), P(self.depth), P(self.depth_sq), P(self.rgb),
+             self.T, n, P(self.dL_dsigmas), P(self.dL_drgbs), P(self.alive_idx), P(self.alive_cnt))
+        self.g_xyz.zero_(); self.g_rgb.zero_(); self.found.zero_()
+        call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), m.k1, P(self.dirs), P(image), cap,
+             P(self.alive_cnt), P(self.rgbs), P(self.h), 1.0 / S, P(self.din_enc), P(self.g_xyz), P(self.g_rgb),
+             P(self.alive_idx), 0, P(self.found), None, None, None)
+        if self.din_enc is not None:
+            call("b2n_hashgrid_bw", P(self.xyzs), P(self.din_enc), 32, m._layout, cap, P(self.alive_cnt), 1.0 / S,
+                 P(self.g_xyz[m.xyz_encoder.mlp.n_params:]), P(self.alive_idx))
+        # an fp16 overflow on the way surfaces as inf in the returned gradient (what a GradScaler keys on)
+        self.g_rgb[:1] += torch.where(self.found > 0, float("inf"), 0.0)
+
+    def _replay(self, name, fn):
+        p16, image = self.model._fused_state(self.dev)        # refreshes the fp16 copies / weight image IN PLACE (eager)
+        key = (p16.data_ptr(), image.data_ptr(), self.model.density_bitfield.data_ptr())
+        if key != self.graph_key:
+            self.graphs, self.graph_key = {}, key
+        g = self.graphs.get(name)
+        if g is None:
+            side = torch.cuda.Stream(device=self.dev)         # eager warm-up, then capture
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fn()
+            torch.cuda.current_stream().wait_stream(side)     # (this eager pass IS this call's execution)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[name] = g
+        else:
+            g.replay()
+
+    def _size_from_first_batch(self, fixed_noise):
+        """One exact count pass (and the only host synchronisation) before the first step: a fresh occupancy grid is
+        fully occupied, so the first batches are the largest ones (hundreds of samples per ray)."""
+        from .. import _lib as L
+        m, P, n = self.model, L.ptr, self.n
+        if not fixed_noise:
+            self.noise.uniform_()
+        L.call("b2n_ray_aabb_intersect", P(self.rays_o), P(self.rays_d), P(m.center), P(m.half_size), n, 1, 1,
+               P(self.hits_cnt), P(self.hits), P(self.hits_idx))
+        L.call("b2n_clamp_near", P(self.hits), n, NEAR_DISTANCE)
+        L.call("b2n_raymarching_train_count", P(self.rays_o), P(self.rays_d), P(self.hits), P(m.density_bitfield),
+               m.cascades, float(m.scale), self.esf, P(self.noise), m.grid_size, MAX_SAMPLES, n, -1, P(self.rays_a),
+               P(self.counter), P(self.march_ws))
+        total = int(self.counter[0].item())
+        if total * 1.25 > self.cap:
+            ro, rd, nz = self.rays_o, self.rays_d, self.noise
+            self.cap = int(total * 1.25)
+            self._alloc()
+            self.rays_o.copy_(ro); self.rays_d.copy_(rd); self.noise.copy_(nz)
+
+    # ---------------------------------------------------------------- the two halves
+    def forward(self, rays_o, rays_d, fixed_noise):
+        if self.pending and self.event.query():
+            self.pending = False
+            if int(self.host[2]):                             # the step before last did not fit: grow for the next ones
+                if not self.warned:
+                    import warnings
+                    warnings.warn("render(): a training batch produced more samples than the buffers held; its rays were "
+                                  "truncated for that step and the buffers have been enlarged")
+                    self.warned = True
+                self.cap = int(max(self.cap * 1.5, int(self.host[3]) * 1.25))
+                self._alloc()
+        self.rays_o.copy_(rays_o); self.rays_d.copy_(rays_d)
+        if fixed_noise is not None:
+            self.noise.copy_(fixed_noise)
+        if self.serial == 0:
+            self._size_from_first_batch(fixed_noise is not None)
+        self._replay(("fw", fixed_noise is not None), lambda: self._fw(fixed_noise is not None))
+        if not self.pending:
+            self.host.copy_(self.counter, non_blocking=True); self.event.record(); self.pending = True
+        self.serial += 1
+        return self.serial
+
+    def backward(self, g_out):
+        self.gin.copy_(g_out)
+        self._replay("bw", self._bw)
+        return self.g_xyz.clone(), self.g_rgb.clone()
+
+
+class _TrainRenderFn(torch.autograd.Function):
+    """render() at training time (rendering.py:12-39 + 117-166: AABB clip, near clamp, march, field, compositing,
+    background blend) as one autograd node over _TrainGraph.  Returns the packed per-ray outputs
+    [opacity | depth | depth_sq | rgb] (6 * N_rays) and the sample count."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, rays_o, rays_d, xyz_params, rgb_params, model, esf, T_threshold):
+        st = _TrainGraph.get(model, rays_o.shape[0], esf, T_threshold)
+        ctx.st = st
+        ctx.serial = st.forward(rays_o, rays_d, RayMarcher.noise)
+        total = st.counter[0].clone()
+        ctx.mark_non_differentiable(total)
+        return st.out.clone(), total
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g_out, _):
+        st = ctx.st
+        if st.serial != ctx.serial:
+            raise RuntimeError("render() ran again on this model before the previous result's backward pass; its "
+                               "activations live in reused buffers -- call render(..., graph=False) for that pattern")
+        g_xyz, g_rgb = st.backward(g_out)
+        return None, None, g_xyz, g_rgb, None, None, None
+
+
+def _train_graph_ok(model, rays_o, rays_d, kwargs):
+    xe = getattr(model, "xyz_encoder", None)
+    return (kwargs.get("graph", True) and RayMarcher.sync_free and hasattr(model, "_fused_state") and rays_o.is_cuda
+            and torch.is_grad_enabled() and not rays_o.requires_grad and not rays_d.requires_grad and rays_o.shape[0] > 0
+            and (xe.params.requires_grad or model.rgb_net.params.requires_grad)
+            and not torch.cuda.is_current_stream_capturing())
+
+
+def _render_train_graph(model, rays_o, rays_d, **kwargs):
+    n = rays_o.shape[0]
+    out, total_samples = _TrainRenderFn.apply(rays_o, rays_d, model.xyz_encoder.params, model.rgb_net.params, model,
+                                              kwargs.get("exp_step_factor", 0.), kwargs.get("T_threshold", 1e-4))
+    return {"total_samples": total_samples, "opacity": out[:n], "depth": out[n:2 * n], "depth_sq": out[2 * n:3 * n],
+            "rgb": out[3 * n:].view(n, 3)}
+
+
 def _render_rays_train(model, rays_o, rays_d, hits_t, **kwargs):
-    """march -> field -> composite under autocast (rendering.py:117-166)."""
+    """march -> field -> composite under autocast (rendering.py:117-166), one autograd node per reference Function
+    (RayMarcher, the fused field node behind NGP.forward, VolumeRenderer); differentiates w.r.t. the rays as well.
+    render() takes the graph-replayed single-node form (_TrainRenderFn) instead whenever it applies."""
     exp_step_factor = kwargs.get("exp_step_factor", 0.)
+    T_threshold = kwargs.get("T_threshold", 1e-4)
     with torch.autocast("cuda", dtype=torch.float16):
         rays_a, xyzs, dirs, deltas, ts, total_samples = RayMarcher.apply(
             rays_o, rays_d, hits_t[:, 0], model.density_bitfield, model.cascades, model.scale, exp_step_factor,
             model.grid_size, MAX_SAMPLES)
         sigmas, rgbs = model(xyzs, dirs)
-        opacity, depth, depth_sq, rgb = VolumeRenderer.apply(sigmas, rgbs.contiguous(), deltas, ts, rays_a,
-                                                             kwargs.get("T_threshold", 1e-4))
+        opacity, depth, depth_sq, rgb = VolumeRenderer.apply(sigmas, rgbs.contiguous(), deltas, ts, rays_a, T_threshold)
         rgb = rgb + _background(exp_step_factor, rays_o.device) * (1 - opacity)[:, None]
     return {"total_samples": total_samples, "opacity": opacity, "depth": depth, "depth_sq": depth_sq, "rgb": rgb}
 

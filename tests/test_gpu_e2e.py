@@ -255,3 +255,36 @@ def test_trainer_unbounded_config_matches_oracle_step(built_lib):
     for got, want, name in ((tr.g_rgb, ref.rgb_params.grad, "rgb_net"), (tr.g_xyz, ref.xyz_params.grad, "xyz_encoder")):
         sc = want.abs().max().item()
         assert (got.cpu() - want).abs().max().item() <= 1e-2 * sc, name
+
+
+@pytest.mark.parametrize("esf", [0.0, 1.0 / 256])
+def test_render_graph_form_equals_launch_by_launch(pair, esf):
+    """render() at training time: the single-node form (two CUDA-graph replays: AABB, march, field, compositing, blend
+    forward; compositing / field / scatter backward) gives the results and parameter gradients of the launch-by-launch
+    form with one autograd node per reference Function -- on the first call (capture) and on replays with new rays."""
+    from google_nerf_b200.models.rendering import render
+    from google_nerf_b200.models.custom_functions import RayMarcher
+    _, model, s = pair
+    g = torch.Generator().manual_seed(4)
+    model.zero_grad()
+    try:
+        for lo in (0, 256, 0):                                    # third pass: a replay on the first rays again
+            ro, rd = s["rays_o"][lo:lo + 512].to(DEV), s["rays_d"][lo:lo + 512].to(DEV)
+            RayMarcher.noise = s["noise"][lo:lo + 512].to(DEV)
+            w = [torch.rand(512, generator=g).to(DEV) for _ in range(3)] + [torch.rand(512, 3, generator=g).to(DEV)]
+            out = {}
+            for graph in (False, True):
+                res = render(model, ro, rd.clone(), exp_step_factor=esf, graph=graph)
+                loss = sum((res[k] * wk).sum() for k, wk in zip(("opacity", "depth", "depth_sq", "rgb"), w))
+                model.zero_grad()
+                (loss * 64.0).backward()
+                out[graph] = (res, model.xyz_encoder.params.grad.clone(), model.rgb_net.params.grad.clone())
+            a, b = out[False], out[True]
+            assert int(a[0]["total_samples"]) == int(b[0]["total_samples"]) > 0
+            for k in ("opacity", "depth", "depth_sq", "rgb"):
+                torch.testing.assert_close(b[0][k], a[0][k].float(), rtol=1e-6, atol=1e-6)
+            for ga, gb in zip(a[1:], b[1:]):
+                assert (ga - gb).abs().max().item() <= 2e-4 * ga.abs().max().item()   # atomics order only
+    finally:
+        RayMarcher.noise = None
+        model.zero_grad()
