@@ -212,7 +212,7 @@ class ClockSampler:
 
 # ---------------------------------------------------------------------------------------------- kernel table
 # algorithmic bytes per unit and the roofline that bounds each kernel
-def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16, fused_scatter):
+def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16):
     s, r, a = n_samples, n_rays, n_alive
     gather = "l2" if table_in_l2 else "hbm"                   # 21.8 MiB fp16 table is L2-resident, 185 MiB (T=2^22) is not
     wire = (world - 1) * ((2 if grad16 else 4) + 2)           # NVLink bytes per owned parameter: W-1 gradient reads + W-1 fp16 stores
@@ -227,8 +227,7 @@ def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16, 
         # the tensor roofline; their algorithmic traffic is enc 64 + dirs 12 + sigma 4 + rgb 12 + h 32 = 124 B/sample
         # forward, enc 64 + h 32 + dirs 12 + rgb 12 + dL 16 + index 4 in and dL/denc 64 out = 204 B/alive sample backward
         "b2n_field_mlp_fw": ("hbm", 124 * s),
-        # (+ 1100 - 64 B/alive sample when the hash-grid scatter is fused in: the dL/denc store becomes the table reds)
-        "b2n_field_mlp_bw": ("l2" if (fused_scatter and table_in_l2) else "hbm", (204 + (1036 if fused_scatter else 0)) * a),
+        "b2n_field_mlp_bw": ("hbm", 204 * a),
         "b2n_field_pack_weights": ("hbm", 40960),
         "b2n_composite_loss_fwbw": ("hbm", 40 * s + 76 * r),
         "b2n_composite_train_fw": ("hbm", 24 * s + 48 * r), "b2n_composite_train_bw": ("hbm", 40 * s + 96 * r),
@@ -559,7 +558,7 @@ def main():
         gather_loads_per_s = gatherbench(16 << 20, 64)       # 16 MiB: about the fp16 table (21.8 MiB), L2-resident
 
         table_in_l2 = cfg["log2_T"] <= 20
-        costs = kernel_costs(N_RAYS, samples, alive, tr.shard, table_in_l2, world, tr.grad_fp16, tr.hashed and tr.fuse_scatter)
+        costs = kernel_costs(N_RAYS, samples, alive, tr.shard, table_in_l2, world, tr.grad_fp16)
         # the dominant kernel of the step's critical path (ray generation / AABB / marching of the NEXT batch run on
         # the side stream underneath it and are reported separately in `marcher`)
         side = ("b2n_raymarching", "b2n_ray_aabb", "b2n_clamp_near", "b2n_rays_from_indices")

@@ -66,9 +66,9 @@ _SIGS = {
     "b2n_sh4_fw": [_P, _I, _L, _P, _P, _I, _P],
     "b2n_mlp_fw": [_P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _P],
     "b2n_mlp_bw": [_P, _P, _I, _I, _P, _I, _I, _L, _P, _P, _P, _F, _P, _P, _P],
-    "b2n_field_pack_weights": [_P, _P, _P, _I, _P],
+    "b2n_field_pack_weights": [_P, _P, _P, _I, _P, _P],
     "b2n_field_mlp_fw": [_P, _I, _P, _P, _L, _P, _P, _P, _P, _P],
-    "b2n_field_mlp_bw": [_P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P, C.POINTER(GridLayout), _P, _P],
+    "b2n_field_mlp_bw": [_P, _P, _P, _I, _P, _P, _L, _P, _P, _P, _F, _P, _P, _P, _P, _I, _P, _P],
     "b2n_adam_step": [_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _I, _P, _I, _P],
     "b2n_cast_half": [_P, _P, _L, _P],
     "b2n_grid_cell_positions": [_P, _P, _L, _I, _F, _F, _F, _I, _P, _P],

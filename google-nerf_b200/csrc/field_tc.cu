@@ -15,7 +15,6 @@
 // Backward: the three hidden activations are RECOMPUTED on the tensor cores from enc / [SH | h] (20 kFLOP per sample
 // on a pipe that idles) instead of being written by the forward pass and read back (416 B per sample each way).
 #include "common.cuh"
-#include "hashgrid.cuh"
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -29,7 +28,19 @@ struct Img {
 
 __global__ void __launch_bounds__(256) field_pack_weights_kernel(const __half *__restrict__ sigma_w,
                                                                  const __half *__restrict__ rgb_w,
-                                                                 __half *__restrict__ image, int k1) {
+                                                                 __half *__restrict__ image, int k1, b2n_hyper *hyper) {
+    // single-GPU trainer: the loss-scaler bookkeeping that follows the optimiser step (b2n_scaler_update) rides along,
+    // including the clearing of found_inf -- two launches less per step
+    if (hyper != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (hyper->found_inf) {
+            hyper->skipped += 1; hyper->good_steps = 0;
+            hyper->loss_scale = fmaxf(hyper->loss_scale * 0.5f, 1.0f);
+        } else if (hyper->growth_interval > 0 && ++hyper->good_steps >= hyper->growth_interval) {
+            hyper->good_steps = 0;
+            hyper->loss_scale = fminf(hyper->loss_scale * 2.0f, 65536.0f);
+        }
+        hyper->found_inf = 0;
+    }
     // flat row-major (out,in) matrices -> canonical K-major no-swizzle images
     const int w2 = 64 * k1, w3 = w2 + 1024, w4 = w3 + 2048, w5 = w4 + 4096, total = w5 + 1024;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
@@ -47,10 +58,10 @@ __global__ void __launch_bounds__(256) field_pack_weights_kernel(const __half *_
 extern "C" int b2n_field_image_halves(int k1) { return (k1 == 32 || k1 == 80) ? 64 * k1 + 8192 : -1; }
 
 extern "C" int b2n_field_pack_weights(const b2n_half *sigma_w, const b2n_half *rgb_w, b2n_half *image, int k1,
-                                      void *stream) {
+                                      b2n_hyper *scaler_update, void *stream) {
     B2N_CHECK_ARG(k1 == 32 || k1 == 80, "first-layer width must be 32 (HashGrid) or 80 (Frequency-12)");
     field_pack_weights_kernel<<<14, 256, 0, (cudaStream_t)stream>>>((const __half *)sigma_w, (const __half *)rgb_w,
-                                                                    (__half *)image, k1);
+                                                                    (__half *)image, k1, scaler_update);
     B2N_LAUNCH_CHECK();
     return 0;
 }
@@ -436,8 +447,7 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) field_mlp_bw_kernel(
     const float *__restrict__ dirs, const __half *__restrict__ image, int64_t n, const int32_t *__restrict__ n_dev,
     const float *__restrict__ rgbs, const __half *__restrict__ h_in, float grad_scale, __half *__restrict__ dL_denc,
     float *__restrict__ grad_sigma_w, float *__restrict__ grad_rgb_w, const int32_t *__restrict__ sample_idx,
-    int serialize, int32_t *__restrict__ found_inf, const float *__restrict__ xyz,
-    const __grid_constant__ GridLevels gl, float2 *__restrict__ grad_table) {
+    int serialize, int32_t *__restrict__ found_inf) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     using SM = FieldBwSmem<K1, GROUPS>;
     using I = Img<K1>;
@@ -495,41 +505,54 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) field_mlp_bw_kernel(
     if (grp) __nanosleep(grp * BW_SKEW_NS);
 
     const int64_t tile_stride = (int64_t)gridDim.x * GROUPS;
-    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + grp; tile < n_tiles; tile += tile_stride) {
-        const int64_t row0 = tile * 128, row = row0 + tid, rows_valid = n - row0;
-        const bool live = row < n;
+    // Per-tile inputs are fetched ONE TILE AHEAD (during step E of the tile before): [SH | h] -> X[0:32) (cp.async for
+    // h, registers for SH), the packed g5 = dL/drgb * sigmoid'(rgb) and dL/dsigma in registers -- the L2 latency of
+    // these loads is off the tile's dependent chain.
+    int64_t nx_s = 0;
+    uint32_t nx_g5a = 0u, nx_g5b = 0u;
+    float nx_dsig = 0.f;
+    bool nx_live = false;
+    auto prefetch = [&](int64_t t) {
+        const int64_t r = t * 128 + tid;
+        nx_live = (t < n_tiles) && (r < n);
         // Row r of a tile is sample IDX[r]: the identity, or an entry of the compacted alive list (sample_idx).
-        const int64_t my_s = live ? (sample_idx ? (int64_t)__ldg(sample_idx + row) : row) : 0;
-        IDX[tid] = (int32_t)my_s;
-        // ---- prologue: [SH | h] -> X[0:32), g5 = dL/drgb * sigmoid'(rgb) -> G[0:16)
-        cp_async16(X + act_off(tid, 2), h_in + my_s * 16, live);
-        cp_async16(X + act_off(tid, 3), h_in + my_s * 16 + 8, live);
+        nx_s = nx_live ? (sample_idx ? (int64_t)__ldg(sample_idx + r) : r) : 0;
+        cp_async16(X + act_off(tid, 2), h_in + nx_s * 16, nx_live);
+        cp_async16(X + act_off(tid, 3), h_in + nx_s * 16 + 8, nx_live);
         cp_async_commit();
-        if (K1 != 32) {       // the dedicated encoded tile can be fetched right away (after IDX is visible)
+        sh_to_tile(dirs, nx_s, nx_live, X, tid);
+        float g5[8];
+        #pragma unroll
+        for (int i = 0; i < 8; ++i) g5[i] = 0.f;
+        nx_dsig = 0.f;
+        if (nx_live) {
+            #pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float y = __ldg(rgbs + 3 * nx_s + c);
+                g5[c] = __ldg(dL_drgbs + 3 * nx_s + c) * y * (1.0f - y);
+            }
+            nx_dsig = __ldg(dL_dsigmas + nx_s);
+        }
+        const uint4 p0 = pack8(g5);
+        const __half2 *ph = reinterpret_cast<const __half2 *>(&p0);
+        bad |= __hisinf(ph[0].x) || __hisnan(ph[0].x) || __hisinf(ph[0].y) || __hisnan(ph[0].y) ||
+               __hisinf(ph[1].x) || __hisnan(ph[1].x);
+        nx_g5a = p0.x; nx_g5b = p0.y;
+    };
+    if ((int64_t)blockIdx.x * GROUPS + grp < n_tiles) prefetch((int64_t)blockIdx.x * GROUPS + grp);
+    for (int64_t tile = (int64_t)blockIdx.x * GROUPS + grp; tile < n_tiles; tile += tile_stride) {
+        const int64_t row0 = tile * 128, rows_valid = n - row0;
+        const bool live = nx_live;
+        const int64_t my_s = nx_s;
+        const float dsig = nx_dsig;
+        IDX[tid] = (int32_t)my_s;
+        // ---- prologue: [SH | h] is already in X[0:32) (or in flight); g5 -> G[0:16)
+        *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = make_uint4(nx_g5a, nx_g5b, 0u, 0u);
+        *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = make_uint4(0, 0, 0, 0);
+        if (K1 != 32) {       // the dedicated encoded tile is fetched here (after IDX is visible)
             group_sync(grp);
             tile_gather_async<K1 / 8>(ENC, enc, IDX, rows_valid, tid);
             cp_async_commit();
-        }
-        sh_to_tile(dirs, my_s, live, X, tid);
-        float dsig = 0.f;
-        {
-            float g5[16];
-            #pragma unroll
-            for (int i = 0; i < 16; ++i) g5[i] = 0.f;
-            if (live) {
-                #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float y = __ldg(rgbs + 3 * my_s + c);
-                    g5[c] = __ldg(dL_drgbs + 3 * my_s + c) * y * (1.0f - y);
-                }
-                dsig = __ldg(dL_dsigmas + my_s);
-            }
-            const uint4 p0 = pack8(g5);
-            const __half2 *ph = reinterpret_cast<const __half2 *>(&p0);
-            bad |= __hisinf(ph[0].x) || __hisnan(ph[0].x) || __hisinf(ph[0].y) || __hisnan(ph[0].y) ||
-                   __hisinf(ph[1].x) || __hisnan(ph[1].x);
-            *reinterpret_cast<uint4 *>(G + act_off(tid, 0)) = p0;
-            *reinterpret_cast<uint4 *>(G + act_off(tid, 1)) = make_uint4(0, 0, 0, 0);
         }
         if (K1 == 32) cp_async_wait_all(); else asm volatile("cp.async.wait_group 1;" ::: "memory");   // h has landed
         GROUP_STEP_SYNC();
@@ -624,43 +647,17 @@ __global__ void __launch_bounds__(128 * GROUPS, 1) field_mlp_bw_kernel(
         relu_bw_epilogue(tmem_work, Y, G, tid);                              // g1 = . * (hid_s > 0)
         GROUP_STEP_SYNC();
         // ---- step E: layer 1 (K1 -> 64)
-        const bool want_genc = (dL_denc != nullptr) || (grad_table != nullptr);
         if (tid == 0) {
             issue_lock(lock);
             issue_wgrad(tmem + TM_DW1, g_a, enc_a, K1);                       // dW1[out][in] += g1^T . enc
-            if (want_genc) issue_dgrad(tm_d0, g_a, w_addr + I::W1 * 2, 32, 64);   // g_enc = g1 . W1
+            if (dL_denc != nullptr) issue_dgrad(tm_d0, g_a, w_addr + I::W1 * 2, 32, 64);   // g_enc = g1 . W1
             mma_commit(bar);
             issue_unlock(lock);
         }
-        float px = 0.f, py = 0.f, pz = 0.f;
-        if (grad_table != nullptr && live) {      // the sample's position, in flight while the MMAs run
-            px = (__ldg(xyz + 3 * my_s) - gl.x_offset) * gl.x_scale;
-            py = (__ldg(xyz + 3 * my_s + 1) - gl.x_offset) * gl.x_scale;
-            pz = (__ldg(xyz + 3 * my_s + 2) - gl.x_offset) * gl.x_scale;
-        }
+        prefetch(tile + tile_stride);             // X[0:32) is free since step C: the next tile's [SH | h], g5, dL/dsigma
         mbar_wait(bar, phase); phase ^= 1;
         fence_after_sync();
-        if (grad_table != nullptr) {
-            // Fused hash-grid backward: this thread's dL/denc row (16 levels x 2 features, fp32 straight from TMEM -- no
-            // fp16 rounding, no dL/denc round trip through memory, no second kernel) is scattered into the gradient
-            // table while the other groups of the CTA run their MMA chains.  The row is parked in the thread's own row
-            // of the G tile (its readers, the step-E MMAs, are done) to keep the register footprint of the loop small.
-            {
-                float v[32];
-                tmem_ld32(tmem_work, v);
-                #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    bad |= !(fabsf(v[4 * c]) <= 3.0e38f) || !(fabsf(v[4 * c + 1]) <= 3.0e38f) ||
-                           !(fabsf(v[4 * c + 2]) <= 3.0e38f) || !(fabsf(v[4 * c + 3]) <= 3.0e38f);
-                    *reinterpret_cast<float4 *>(G + act_off(tid, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-                }
-            }
-            #pragma unroll 1
-            for (int l = 0; l < gl.n_levels; ++l) {
-                const float2 gr = *reinterpret_cast<const float2 *>(G + act_off(tid, l >> 1) + (l & 1) * 8);
-                scatter_level(px, py, pz, gr.x * grad_scale, gr.y * grad_scale, l, gl, grad_table, live, lane);
-            }
-        } else if (dL_denc != nullptr) {
+        if (dL_denc != nullptr) {
             // dL/denc: own row -> G tile (its readers, the step-E MMAs, are done), then one coalesced copy to global
             float v[32];
             tmem_ld32(tmem_work, v);
@@ -717,43 +714,33 @@ template <int K1, int GROUPS>
 static void launch_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, const float *dirs,
                       const b2n_half *image, int64_t n, const int32_t *n_dev, const float *rgbs, const b2n_half *h,
                       float grad_scale, b2n_half *dL_denc, float *grad_sigma_w, float *grad_rgb_w,
-                      const int32_t *sample_idx, int serialize, int32_t *found_inf, const float *xyz,
-                      const GridLevels &gl, float *grad_table, void *stream) {
+                      const int32_t *sample_idx, int serialize, int32_t *found_inf, void *stream) {
     const int smem = (int)sizeof(FieldBwSmem<K1, GROUPS>) + 256;
     cudaFuncSetAttribute(field_mlp_bw_kernel<K1, GROUPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     const int64_t n_tiles = (n + 127) / 128;
     field_mlp_bw_kernel<K1, GROUPS><<<b2n_grid((n_tiles + GROUPS - 1) / GROUPS, 1), 128 * GROUPS, smem, (cudaStream_t)stream>>>(
         dL_dsigmas, dL_drgbs, (const __half *)enc, dirs, (const __half *)image, n, n_dev, rgbs, (const __half *)h,
-        grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl,
-        (float2 *)grad_table);
+        grad_scale, (__half *)dL_denc, grad_sigma_w, grad_rgb_w, sample_idx, serialize, found_inf);
 }
 
 extern "C" int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, int k1,
                                 const float *dirs, const b2n_half *image, int64_t n, const int32_t *n_dev,
                                 const float *rgbs, const b2n_half *h, float grad_scale, b2n_half *dL_denc,
                                 float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx, int serialize,
-                                int32_t *found_inf, const float *xyz, const b2n_grid_layout *layout,
-                                float *grad_table, void *stream) {
+                                int32_t *found_inf, void *stream) {
     B2N_CHECK_ARG(k1 == 32 || k1 == 80, "first-layer width must be 32 (HashGrid) or 80 (Frequency-12)");
     B2N_CHECK_ARG(dL_dsigmas && dL_drgbs && enc && dirs && image && rgbs && h && grad_sigma_w && grad_rgb_w,
                   "gradients in, enc, dirs, weights, rgbs, h and the weight-gradient outputs are required");
     B2N_CHECK_ARG(k1 == 32 || dL_denc == nullptr, "dL/denc exists for the HashGrid configuration only");
     B2N_CHECK_ARG(((uintptr_t)enc & 15) == 0 && ((uintptr_t)h & 15) == 0 && ((uintptr_t)dL_denc & 15) == 0,
                   "enc / h / dL_denc must be 16-byte aligned");
-    GridLevels gl = {};
-    if (grad_table != nullptr) {
-        B2N_CHECK_ARG(k1 == 32 && xyz != nullptr && layout != nullptr && dL_denc == nullptr,
-                      "the fused table scatter needs the HashGrid width, xyz and the layout, and replaces dL_denc");
-        if (to_levels(layout, gl)) return 1;
-        B2N_CHECK_ARG(gl.n_levels == 16 && ((uintptr_t)grad_table & 15) == 0, "16 levels x 2 features, 16-byte aligned table");
-    }
     if (n <= 0) return 0;
     if (k1 == 32)
         launch_bw<32, 4>(dL_dsigmas, dL_drgbs, enc, dirs, image, n, n_dev, rgbs, h, grad_scale, dL_denc, grad_sigma_w,
-                         grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl, grad_table, stream);
+                         grad_rgb_w, sample_idx, serialize, found_inf, stream);
     else
         launch_bw<80, 2>(dL_dsigmas, dL_drgbs, enc, dirs, image, n, n_dev, rgbs, h, grad_scale, dL_denc, grad_sigma_w,
-                         grad_rgb_w, sample_idx, serialize, found_inf, xyz, gl, grad_table, stream);
+                         grad_rgb_w, sample_idx, serialize, found_inf, stream);
     B2N_LAUNCH_CHECK();
     return 0;
 }

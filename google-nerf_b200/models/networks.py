@@ -65,8 +65,7 @@ class _FieldFn(torch.autograd.Function):
         found = torch.zeros(1, dtype=torch.int32, device=dev)
         nd = L.ptr(ctx.n_dev)
         L.call("b2n_field_mlp_bw", L.ptr(ds), L.ptr(dc), L.ptr(enc), model.k1, L.ptr(d), L.ptr(image), n, nd,
-               L.ptr(rgbs), L.ptr(h), 1.0 / S, L.ptr(denc), L.ptr(g_xyz), L.ptr(g_rgb), None, 0, L.ptr(found),
-               None, None, None)
+               L.ptr(rgbs), L.ptr(h), 1.0 / S, L.ptr(denc), L.ptr(g_xyz), L.ptr(g_rgb), None, 0, L.ptr(found))
         if hashed:
             L.call("b2n_hashgrid_bw", L.ptr(x), L.ptr(denc), 32, model._layout, n, nd, 1.0 / S,
                    L.ptr(g_xyz[xe.mlp.n_params:]), None)
@@ -153,7 +152,7 @@ class NGP(nn.Module):
             self._layout.x_scale = 1.0 / (2.0 * float(self.scale))
         key = (xe._p16_key, rn._p16_key, p16.data_ptr(), r16.data_ptr())
         if self._image_key != key:
-            L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image), self.k1)
+            L.call("b2n_field_pack_weights", L.ptr(p16), L.ptr(r16), L.ptr(self._image), self.k1, None)
             self._image_key = key
         return p16, self._image
 

@@ -269,7 +269,7 @@ class _TrainGraph:
         self.g_xyz.zero_(); self.g_rgb.zero_(); self.found.zero_()
         call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), m.k1, P(self.dirs), P(image), cap,
              P(self.alive_cnt), P(self.rgbs), P(self.h), 1.0 / S, P(self.din_enc), P(self.g_xyz), P(self.g_rgb),
-             P(self.alive_idx), 0, P(self.found), None, None, None)
+             P(self.alive_idx), 0, P(self.found))
         if self.din_enc is not None:
             call("b2n_hashgrid_bw", P(self.xyzs), P(self.din_enc), 32, m._layout, cap, P(self.alive_cnt), 1.0 / S,
                  P(self.g_xyz[m.xyz_encoder.mlp.n_params:]), P(self.alive_idx))

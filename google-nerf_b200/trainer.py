@@ -66,10 +66,6 @@ class NGPTrainer:
         self.k1 = model.k1
         self.erode, self.serialize_mma = bool(erode), int(bool(serialize_mma))
         self.lambda_depth = float(lambda_depth)
-        # table-gradient scatter inside the backward field kernel (b2n_field_mlp_bw's grad_table): measured 349 us against
-        # 89 + 103 us for the two separate launches -- 512 threads per SM in the middle of a dependent MMA chain cannot
-        # keep the L2 atomic path as busy as 2048 free-running ones -- so the separate b2n_hashgrid_bw launch is the default
-        self.fuse_scatter = os.environ.get("B2N_FUSE_SCATTER", "0") == "1"
         self.dev = model.center.device
         if self.dev.type != "cuda":
             raise RuntimeError("NGPTrainer needs the model on a CUDA device (no CPU fallback)")
@@ -202,7 +198,7 @@ class NGPTrainer:
         self._scalars = torch.zeros(4, dtype=torch.int32, device=dev)
         self.alive_cnt, self.loss = self._scalars[0:1], self._scalars[1:2].view(_f32)
         self.dL_dsigmas, self.dL_drgbs = e(cap), e(cap, 3)
-        self.din_enc = e(cap, 32, dt=_f16) if (self.hashed and not self.fuse_scatter) else None
+        self.din_enc = e(cap, 32, dt=_f16) if self.hashed else None
         self.alive_idx = e(cap, dt=torch.int32)
         self.last_counter = self.sets[0].counter
         self.graphs = {}
@@ -266,13 +262,10 @@ class NGPTrainer:
         # field backward (gradients carry the loss scale; parameter gradients are unscaled inside Adam)
         # only the samples composited before each ray's early stop carry gradient: the two heavy backward kernels
         # run over that compacted list (alive_cnt is a device-side count)
-        # HashGrid: the table-gradient scatter runs inside the backward field kernel (no dL/denc buffer, no second launch)
-        fused = self.hashed and self.fuse_scatter
         call("b2n_field_mlp_bw", P(self.dL_dsigmas), P(self.dL_drgbs), P(self.enc), self.k1, P(s.dirs), P(self.w_image),
-             cap, P(self.alive_cnt), P(self.rgbs), P(self.h), 1.0, None if fused else P(self.din_enc), P(self.g_xyz),
-             P(self.g_rgb), P(self.alive_idx), self.serialize_mma, P(self.hyper[2:]),
-             P(s.xyzs) if fused else None, self.layout if fused else None, P(self.g_xyz[self.n_mlp:]) if fused else None)
-        if self.hashed and not fused:
+             cap, P(self.alive_cnt), P(self.rgbs), P(self.h), 1.0, P(self.din_enc), P(self.g_xyz), P(self.g_rgb),
+             P(self.alive_idx), self.serialize_mma, P(self.hyper[2:]))
+        if self.hashed:
             call("b2n_hashgrid_bw", P(s.xyzs), P(self.din_enc), 32, self.layout, cap, P(self.alive_cnt), 1.0,
                  P(self.g_xyz[self.n_mlp:]), P(self.alive_idx))
 
@@ -289,11 +282,11 @@ class NGPTrainer:
         b1, b2 = self.betas
         call("b2n_adam_step", P(self.p_shard), P(self.g_shard), P(self.m), P(self.v), P(self.h_shard), self.shard,
              self.lr, b1, b2, self.eps, inv, 1, P(self.hyper), 1)
-        call("b2n_scaler_update", P(self.hyper), None, 1)
-        self.hyper[2:3].zero_()                              # found_inf consumed
         if self.world == 1:
-            self._pack_weights()
+            self._pack_weights(scaler=True)                  # + loss-scaler bookkeeping, found_inf consumed
         else:
+            call("b2n_scaler_update", P(self.hyper), None, 1)
+            self.hyper[2:3].zero_()                          # found_inf consumed
             self.g_all.zero_()                               # Adam only zeroed this rank's (reduced) shard
 
     def _gather_params(self):
@@ -325,9 +318,10 @@ class NGPTrainer:
             self.g_all.zero_()
         self._pack_weights()
 
-    def _pack_weights(self):
+    def _pack_weights(self, scaler=False):
         """fp16 MLP weights -> UMMA canonical shared-memory image for the fused field kernels."""
-        L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image), self.k1)
+        L.call("b2n_field_pack_weights", L.ptr(self.h_xyz), L.ptr(self.h_rgb), L.ptr(self.w_image), self.k1,
+               L.ptr(self.hyper) if scaler else None)
 
     def _train(self, p):
         """Forward, backward and the optimiser on sample set p (world > 1: with the gradient reduce-scatter and the

@@ -6,6 +6,26 @@ asked for) and any `val_lpips*` entries.  `NGP.state_dict()` of this package has
 """
 import torch
 
+# Flat-parameter layouts of the tinycudann modules (checkpoint key `xyz_encoder.params` / `rgb_net.params`).  This
+# package's own layout ("b2n", documented in tinycudann.py): network weights first, layer by layer, each a row-major
+# (out, in) matrix with the input width padded to a multiple of 16 and the output layer padded to 16 rows, then the hash
+# table level by level (2 features per entry).  Upstream tiny-cuda-nn is not in the reference tree (.gitignore:25), so
+# its layout cannot be verified here; from its published sources it is the same ordering (FullyFusedMLP row-major
+# weight matrices, NetworkWithInputEncoding = network parameters followed by encoding parameters), hence "tcnn" is
+# registered as the identity.  A checkpoint from a build that differs registers its own pair of converters here.
+PARAM_LAYOUTS = {"b2n": (lambda name, p: p, lambda name, p: p), "tcnn": (lambda name, p: p, lambda name, p: p)}
+
+
+def register_param_layout(name, to_b2n, from_b2n):
+    """to_b2n(key, flat_params) / from_b2n(key, flat_params): convert one flat `*.params` tensor of a checkpoint."""
+    PARAM_LAYOUTS[name] = (to_b2n, from_b2n)
+
+
+def convert_param_layout(state, layout, to_b2n=True):
+    fn = PARAM_LAYOUTS[layout][0 if to_b2n else 1]
+    return {k: (fn(k, v) if (k == "params" or k.endswith(".params")) else v) for k, v in state.items()}
+
+
 _TRAIN_ONLY = ("directions", "model.density_grid", "model.grid_coords")
 
 
@@ -23,11 +43,12 @@ def extract_model_state_dict(ckpt_path, model_name="model", prefixes_to_ignore=(
     return out
 
 
-def load_ckpt(model, ckpt_path, model_name="model", prefixes_to_ignore=()):
+def load_ckpt(model, ckpt_path, model_name="model", prefixes_to_ignore=(), param_layout="b2n"):
+    """utils.py:19-25; param_layout names the flat-parameter layout the checkpoint was written with (PARAM_LAYOUTS)."""
     if not ckpt_path:
         return
     state = model.state_dict()
-    state.update(extract_model_state_dict(ckpt_path, model_name, prefixes_to_ignore))
+    state.update(convert_param_layout(extract_model_state_dict(ckpt_path, model_name, prefixes_to_ignore), param_layout))
     model.load_state_dict(state)
 
 

@@ -228,13 +228,14 @@ B2N_API int b2n_mlp_bw(const b2n_half *dL_dout, const b2n_half *in, int in_strid
  * k1 = 32: the HashGrid configuration (networks.py:39-47, enc = b2n_hashgrid_fw output);
  * k1 = 80: the Frequency-12 configuration this fork has active (networks.py:49-53, enc = b2n_frequency_fw output).
  * image: the two FullyFusedMLP weight sets (sigma: 64*k1 + 1024 halves, rgb: 7168 halves, flat row-major (out,in))
- * repacked by b2n_field_pack_weights into b2n_field_image_halves(k1) halves.
+ * repacked by b2n_field_pack_weights into b2n_field_image_halves(k1) halves (scaler_update, may be NULL: a single-GPU
+ * trainer's b2n_hyper; the launch then also does what b2n_scaler_update does and clears found_inf).
  * enc (n,k1) fp16, dirs (n,3) fp32 raw directions -> sigmas (n) fp32 (may be NULL), rgbs (n,3) fp32 (fp16-rounded),
  * h (n,16) fp16 (may be NULL; the one activation the backward pass wants saved).  rgbs == NULL selects the
  * density-only form (NGP.density, models/networks.py:87-100): the chain stops after h, dirs is not read. */
 B2N_API int b2n_field_image_halves(int k1);
 B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights, const b2n_half *rgb_weights, b2n_half *image, int k1,
-                                   void *stream);
+                                   b2n_hyper *scaler_update, void *stream);
 B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, const b2n_half *image, int64_t n,
                              const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *h, void *stream);
 /* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale); the hidden
@@ -245,17 +246,12 @@ B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, con
  * n_dev count list entries and row i of dL_denc belongs to sample sample_idx[i].
  * serialize != 0: MMA issue of the CTA's tile groups goes through a shared-memory lock (validation of the default
  * lock-free accumulation).  found_inf (may be NULL): set to 1 when a gradient left the fp16 range (inf / NaN), the
- * GradScaler signal of the reference's precision=16 training (train.py:265).
- * Fused hash-grid backward (k1 = 32): with grad_table != NULL (and dL_denc == NULL) every sample's dL/denc row is
- * scattered straight into the fp32 table gradient (the same warp-aggregated red.global.add as b2n_hashgrid_bw, from the
- * fp32 accumulator, times grad_scale) inside this kernel; xyz (n_alloc,3) are the sample positions the encoding was
- * evaluated at and layout its b2n_grid_layout (with the same x_offset / x_scale as the forward gather). */
+ * GradScaler signal of the reference's precision=16 training (train.py:265). */
 B2N_API int b2n_field_mlp_bw(const float *dL_dsigmas, const float *dL_drgbs, const b2n_half *enc, int k1,
                              const float *dirs, const b2n_half *image, int64_t n, const int32_t *n_dev,
                              const float *rgbs, const b2n_half *h, float grad_scale, b2n_half *dL_denc,
                              float *grad_sigma_w, float *grad_rgb_w, const int32_t *sample_idx, int serialize,
-                             int32_t *found_inf, const float *xyz, const b2n_grid_layout *layout,
-                             float *grad_table, void *stream);
+                             int32_t *found_inf, void *stream);
 
 /* ---------------------------------------------------------------- multi-GPU: NVLink peer memory ------ */
 /* Data-parallel training (ngp_pl/train.py:197-208: DDPPlugin -> one NCCL gradient all-reduce per step, every rank

@@ -40,11 +40,7 @@ calls = {
     "hashgrid_fw": lambda: L.call("b2n_hashgrid_fw", P(s.xyzs), P(tr.h_xyz[tr.n_mlp:]), tr.layout, cap, P(nd), P(tr.enc), 32),
     "field_mlp_fw": lambda: L.call("b2n_field_mlp_fw", P(tr.enc), 32, P(s.dirs), P(tr.w_image), cap, P(nd), P(tr.sigmas), P(tr.rgbs), P(tr.h)),
     "field_mlp_bw": lambda: L.call("b2n_field_mlp_bw", P(tr.dL_dsigmas), P(tr.dL_drgbs), P(tr.enc), 32, P(s.dirs), P(tr.w_image), cap,
-                                   P(tr.alive_cnt), P(tr.rgbs), P(tr.h), 1.0, P(din_enc), P(tr.g_xyz), P(tr.g_rgb), P(tr.alive_idx), 0, None,
-                                   None, None, None),
-    "field_mlp_bw_fused": lambda: L.call("b2n_field_mlp_bw", P(tr.dL_dsigmas), P(tr.dL_drgbs), P(tr.enc), 32, P(s.dirs), P(tr.w_image), cap,
-                                   P(tr.alive_cnt), P(tr.rgbs), P(tr.h), 1.0, None, P(tr.g_xyz), P(tr.g_rgb), P(tr.alive_idx), 0, None,
-                                   P(s.xyzs), tr.layout, P(tr.g_xyz[tr.n_mlp:])),
+                                   P(tr.alive_cnt), P(tr.rgbs), P(tr.h), 1.0, P(din_enc), P(tr.g_xyz), P(tr.g_rgb), P(tr.alive_idx), 0, None),
     "hashgrid_bw": lambda: L.call("b2n_hashgrid_bw", P(s.xyzs), P(din_enc), 32, tr.layout, cap, P(tr.alive_cnt), 1.0,
                                   P(tr.g_xyz[tr.n_mlp:]), P(tr.alive_idx)),
 }

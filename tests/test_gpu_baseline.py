@@ -341,7 +341,7 @@ def test_graph_replayed_grid_update_sees_current_weights(built_lib):
         assert m._image.data_ptr() == image_ptr == tr.w_image.data_ptr()
         # the image the graphs read is the pack of the current fp16 weights
         fresh = torch.empty_like(tr.w_image)
-        built_lib.call("b2n_field_pack_weights", built_lib.ptr(tr.h_xyz), built_lib.ptr(tr.h_rgb), built_lib.ptr(fresh), 32)
+        built_lib.call("b2n_field_pack_weights", built_lib.ptr(tr.h_xyz), built_lib.ptr(tr.h_rgb), built_lib.ptr(fresh), 32, None)
         assert torch.equal(fresh, tr.w_image)
         grids[use_graph], bits[use_graph] = m.density_grid.clone(), m.density_bitfield.clone()
     a, b = grids[False], grids[True]

@@ -35,7 +35,7 @@ class _Dev:
         n = self.n
         self.ws, self.wr = ps.float().to(DEV).half(), pr.float().to(DEV).half()
         self.image = torch.empty(64 * k1 + 8192, dtype=torch.float16, device=DEV)
-        L.call("b2n_field_pack_weights", L.ptr(self.ws), L.ptr(self.wr), L.ptr(self.image), k1)
+        L.call("b2n_field_pack_weights", L.ptr(self.ws), L.ptr(self.wr), L.ptr(self.image), k1, None)
         self.enc, self.dirs = enc.to(DEV).contiguous(), dirs.to(DEV).contiguous()
         self.sig = torch.empty(n, device=DEV); self.rgb = torch.empty(n, 3, device=DEV)
         self.h = torch.empty(n, 16, dtype=torch.float16, device=DEV)
@@ -53,19 +53,8 @@ class _Dev:
         found = torch.zeros(1, dtype=torch.int32, device=DEV)
         L.call("b2n_field_mlp_bw", L.ptr(dsig), L.ptr(drgb), L.ptr(self.enc), k1, L.ptr(self.dirs), L.ptr(self.image), n,
                L.ptr(n_dev), L.ptr(self.rgb), L.ptr(self.h), 1.0, L.ptr(denc), L.ptr(gs), L.ptr(gr), L.ptr(idx),
-               serialize, L.ptr(found), None, None, None)
+               serialize, L.ptr(found))
         return denc, gs, gr, int(found.item())
-
-    def backward_fused_scatter(self, dsig, drgb, xyz, layout, n_table, n=None, n_dev=None, idx=None):
-        """The same launch with the hash-grid scatter fused in: -> table gradient, weight gradients."""
-        L = self.L
-        n = self.n if n is None else n
-        gs = torch.zeros(64 * 32 + 1024, device=DEV); gr = torch.zeros(7168, device=DEV)
-        gt = torch.zeros(n_table, device=DEV); found = torch.zeros(1, dtype=torch.int32, device=DEV)
-        L.call("b2n_field_mlp_bw", L.ptr(dsig), L.ptr(drgb), L.ptr(self.enc), 32, L.ptr(self.dirs), L.ptr(self.image), n,
-               L.ptr(n_dev), L.ptr(self.rgb), L.ptr(self.h), 1.0, None, L.ptr(gs), L.ptr(gr), L.ptr(idx), 0,
-               L.ptr(found), L.ptr(xyz), layout, L.ptr(gt))
-        return gt, gs, gr, int(found.item())
 
 
 @pytest.mark.parametrize("k1", [32, 80])
@@ -136,45 +125,6 @@ def test_field_tc_backward(built_lib, n, k1):
     if k1 == 32:
         torch.testing.assert_close(denc2[:idx.numel()].float(), denc_f[idx.long()].float(), rtol=1e-2,
                                    atol=1e-3 * denc_f.abs().max().item())
-
-
-@pytest.mark.parametrize("log2_T", [19, 14])
-def test_field_tc_backward_fused_scatter(built_lib, log2_T):
-    """The table-gradient scatter fused into the backward field kernel == dL/denc written out + b2n_hashgrid_bw (up to
-    the fp16 rounding of dL/denc that the fused form skips), also through a compacted sample list; weight gradients are
-    unaffected."""
-    import numpy as np
-    from google_nerf_b200 import tinycudann as tc
-    L = built_lib
-    n = 20000
-    T, s_shapes, r_shapes, ps, pr, enc, dirs, g = _setup(n, 7)
-    lay = tc.hashgrid_layout(16, 2, log2_T, 16, np.exp(np.log(2048 * 0.5 / 16) / 15))
-    # samples along rays, like the trainer's packed lists (exercises the run aggregation on the coarse levels)
-    o = torch.rand(n // 50, 1, 3, generator=g) * 0.6 + 0.2
-    xyz = (o + torch.linspace(0, 0.08, 50)[None, :, None] * torch.randn(n // 50, 1, 3, generator=g)).reshape(-1, 3).clamp(0, 1)
-    d = _Dev(L, ps, pr, enc, dirs, 32)
-    d.forward()
-    dsig, drgb = torch.randn(n, generator=g).to(DEV) * 4, torch.randn(n, 3, generator=g).to(DEV) * 4
-    xyz_d = xyz.to(DEV).contiguous()
-    denc, gs, gr, _ = d.backward(dsig, drgb)
-    ref_t = torch.zeros(lay.n_params, device=DEV)
-    tc.hashgrid_bw(xyz_d, denc, lay, ref_t, 1.0)
-    gt, gs2, gr2, found = d.backward_fused_scatter(dsig, drgb, xyz_d, lay, lay.n_params)
-    assert found == 0
-    assert (gs2 - gs).abs().max().item() <= 1e-4 * gs.abs().max().item()
-    assert (gr2 - gr).abs().max().item() <= 1e-4 * gr.abs().max().item()
-    for l in range(16):
-        lo, hi = 2 * lay.offset[l], 2 * lay.offset[l + 1]
-        sc = ref_t[lo:hi].abs().max().item()
-        assert (gt[lo:hi] - ref_t[lo:hi]).abs().max().item() <= 2e-3 * sc, l     # fp16 rounding of dL/denc in the reference
-    # compacted list + device-side count
-    keep = torch.rand(n, generator=g) < 0.5
-    idx = torch.nonzero(keep)[:, 0].to(torch.int32).to(DEV)
-    cnt = torch.tensor([idx.numel(), 0, 0, 0], dtype=torch.int32, device=DEV)
-    dsig_m, drgb_m = dsig * keep.to(DEV), drgb * keep.to(DEV)[:, None]
-    gt_full, *_ = d.backward_fused_scatter(dsig_m, drgb_m, xyz_d, lay, lay.n_params)
-    gt_c, *_ = d.backward_fused_scatter(dsig_m, drgb_m, xyz_d, lay, lay.n_params, n_dev=cnt, idx=idx)
-    assert (gt_c - gt_full).abs().max().item() <= 1e-4 * gt_full.abs().max().item()
 
 
 def test_field_tc_backward_reports_overflow(built_lib):

@@ -76,3 +76,50 @@ def test_segment_csr_shim_matches_per_ray_sums():
     want_o = torch.stack([d_xyz[s:s + c].sum(0) for s, c in zip(start.tolist(), counts.tolist())])
     ptr = torch.cat([rays_a[:, 1], rays_a[-1:, 1] + rays_a[-1:, 2]])           # the reference's CSR pointer
     torch.testing.assert_close(segment_csr(d_xyz, ptr), want_o)
+
+
+def test_leres_prior_and_scannet_shaped_dataset(tmp_path):
+    """f3: the LeReS `*-depth_raw.png` encoding (test_scannet.py:85) round-trips, and a ScanNet-shaped directory written
+    from the analytic room is read back with the reference dataset's attributes, normalisation and batch format."""
+    import numpy as np
+    from google_nerf_b200 import priors, synthetic as syn
+    depth = np.random.default_rng(0).random((48, 64)) * 3 + 0.5
+    depth[0, :5] = 0.0
+    p = str(tmp_path / "a-depth_raw.png")
+    priors.write_leres_prior(p, depth)
+    rel = priors.read_leres_prior(p, as_disparity=False)
+    assert rel.shape == (48, 64) and abs(float(rel.max()) - 1.0) < 1e-4
+    np.testing.assert_allclose(rel.numpy(), depth / depth.max(), atol=1.0 / 60000 + 1e-7)
+    disp = priors.read_leres_prior(p)
+    assert float(disp[0, 0]) == 0.0 and abs(float(disp[5, 5]) - depth.max() / depth[5, 5]) < 2e-3 * depth.max() / depth[5, 5]
+    root = str(tmp_path / "scene0000_00")
+    poses = priors.write_scannet_dataset(root, n_views=9, test_skip=4)
+    ds = priors.ScanNetShapedDataset(root, "train", downsample=624 / 640, test_skip=4, scale=1.0)
+    assert ds.img_wh == (624, 468) and ds.K.shape == (3, 3) and ds.directions.shape == (624 * 468, 3)
+    assert ds.poses.shape == (7, 3, 4) and ds.rays.shape == (7, 624 * 468, 3) and ds.priors.shape == (7, 624 * 468)
+    torch.testing.assert_close(ds.poses[0, :, 3], poses[0, :, 3] / 2.0, rtol=1e-5, atol=1e-6)   # (x - shift) / (2 scale)
+    ds.batch_size = 512
+    b = ds[0]
+    assert set(b) == {"rgb", "img_idxs", "pix_idxs", "disp"} and b["rgb"].shape == (512, 3) and b["disp"].shape == (512,)
+    assert len(ds) == 1000 and float(b["disp"].min()) >= 0.0
+    # the prior of a view is an affine image of its true depth: the SSI loss against the true disparity is ~0
+    from google_nerf_b200.losses import shiftscale_inv_depthloss
+    test = priors.ScanNetShapedDataset(root, "test", downsample=1.0, test_skip=4)
+    ro, rd = syn.get_rays(syn.directions(640, 480, test.K), poses[3])
+    t = syn.scene_shade(ro, rd, syn.ROOM)[1]
+    rel_depth = 1.0 / test.priors[0]                                  # back from disparity
+    assert float(shiftscale_inv_depthloss(rel_depth, t).mean()) < 1e-3
+
+
+def test_param_layout_hook(tmp_path):
+    from google_nerf_b200 import utils
+    lin = torch.nn.Linear(2, 2)
+    lin.params = torch.nn.Parameter(torch.arange(6.0))
+    path = str(tmp_path / "c.ckpt")
+    torch.save({"state_dict": {"model.params": torch.arange(6.0).flip(0), "model.weight": lin.weight.detach(),
+                               "model.bias": lin.bias.detach()}}, path)
+    utils.register_param_layout("flipped", lambda k, p: p.flip(0), lambda k, p: p.flip(0))
+    utils.load_ckpt(lin, path, param_layout="flipped")
+    assert torch.equal(lin.params.detach(), torch.arange(6.0))
+    utils.load_ckpt(lin, path, param_layout="tcnn")                   # identity
+    assert torch.equal(lin.params.detach(), torch.arange(6.0).flip(0))
