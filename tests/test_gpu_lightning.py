@@ -108,3 +108,79 @@ def test_lightning_stand_in_trains_ngp(built_lib, tmp_path):
     load_ckpt(fresh, path)
     torch.testing.assert_close(fresh.xyz_encoder.params, system.model.xyz_encoder.params)
     assert torch.equal(fresh.density_bitfield, system.model.density_bitfield)
+
+
+def test_train_mika_step_sequence_matches_oracle(built_lib):
+    """The one-step loop of ngp_pl/train_mika.py:68-173 (the SCADE-style script: no Lightning) spelled with the module
+    names that script imports -- kornia.create_meshgrid3d, apex FusedAdam, torchmetrics PSNR, NGP / render / NeRFLoss --
+    on ScanNet-shaped cameras; its printed loss and PSNR equal the oracle's for the same occupancy bitfield and jitter.
+    (The script itself cannot travel to the GPU box: the reference tree is not there.)"""
+    for p in (ROOT, SHIMS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from apex.optimizers import FusedAdam
+    from kornia.utils.grid import create_meshgrid3d
+    from torch.optim.lr_scheduler import CosineAnnealingLR
+    from torchmetrics import PeakSignalNoiseRatio
+    from google_nerf_b200 import synthetic as syn
+    from google_nerf_b200.losses import NeRFLoss
+    from google_nerf_b200.models.custom_functions import RayMarcher
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.models.rendering import MAX_SAMPLES, render
+    from oracle import ngp_ref as O
+    device, S, batch_size, lr, num_epochs = "cuda", 16, 2048, 1e-2, 30
+    W, H = 624, 468
+    K = syn.intrinsics(W, H, fx=577.87 * 624 / 640); directions = syn.directions(W, H, K).to(device)
+    train_poses = syn.room_poses(18, seed=3).to(device)
+    # ---- train_mika.py:68-76
+    loss_func = NeRFLoss()
+    train_psnr = PeakSignalNoiseRatio(data_range=1)
+    model = NGP(scale=0.5, log2_T=15)
+    G = model.grid_size
+    model.register_buffer("density_grid", torch.zeros(model.cascades, G ** 3))
+    model.register_buffer("grid_coords", create_meshgrid3d(G, G, G, False, dtype=torch.int32).reshape(-1, 3))
+    model.to(device, dtype=torch.float)
+    # ---- :103-121
+    net_opt = FusedAdam(model.parameters(), lr, eps=1e-15)
+    net_sch = CosineAnnealingLR(net_opt, num_epochs, lr / 30)
+    model.mark_invisible_cells(K.to(device), train_poses, (W, H))
+    model.train()
+    g = torch.Generator().manual_seed(0)
+    ii = torch.randint(18, (batch_size,), generator=g); pi = torch.randint(W * H, (batch_size,), generator=g)
+    ro_cpu, rd_cpu = syn.get_rays(directions.cpu()[pi], train_poses.cpu()[ii])
+    batch = {"rgb": syn.scene_shade(ro_cpu, rd_cpu, syn.ROOM)[0].to(device), "img_idxs": ii.to(device), "pix_idxs": pi.to(device)}
+    global_step = 0
+    # ---- :130-167
+    if global_step % S == 0:
+        model.update_density_grid(0.01 * MAX_SAMPLES / 3 ** 0.5, warmup=global_step < 256, erode=False)
+    poses = train_poses[batch["img_idxs"]]
+    rays_o, rays_d = syn.get_rays(directions[batch["pix_idxs"]], poses)
+    noise = torch.rand(batch_size, generator=g)
+    RayMarcher.noise = noise.to(device)
+    try:
+        results = render(model, rays_o, rays_d, test_time=False)
+    finally:
+        RayMarcher.noise = None
+    loss_d = loss_func(results, batch)
+    loss = sum(lo.mean() for lo in loss_d.values())
+    p_before, r_before = model.xyz_encoder.params.detach().clone(), model.rgb_net.params.detach().clone()
+    net_opt.zero_grad()
+    loss.backward()
+    net_opt.step()
+    net_sch.step()
+    with torch.no_grad():
+        psnr = float(train_psnr(results["rgb"], batch["rgb"]))
+    s_per_ray = float(results["total_samples"]) / len(rays_o)
+    # ---- the oracle on the same weights (before the step), bitfield and jitter
+    ref = O.NGPRef(0.5, log2_T=15)
+    with torch.no_grad():
+        ref.xyz_params.copy_(p_before.cpu()); ref.rgb_params.copy_(r_before.cpu())
+    ref.density_bitfield = model.density_bitfield.cpu()
+    res_ref = O.render(ref, ro_cpu, rd_cpu.clone(), noise=noise)
+    loss_ref = O.nerf_loss(res_ref, batch["rgb"].cpu())
+    mse = ((res_ref["rgb"].detach() - batch["rgb"].cpu()) ** 2).mean()
+    psnr_ref = float(-10 * torch.log10(mse))
+    assert int(results["total_samples"]) == res_ref["total_samples"] and s_per_ray > 1
+    assert abs(loss.item() - loss_ref.item()) < 2e-3 * abs(loss_ref.item())
+    assert abs(psnr - psnr_ref) < 0.02
+    assert not torch.equal(p_before, model.xyz_encoder.params.detach()) and net_sch.get_last_lr()[0] < lr
