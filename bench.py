@@ -131,6 +131,8 @@ def cpu_baseline(key, n_rays, steps, warmup):
             times.append(time.perf_counter() - t0)
     sec = float(np.median(times))
     return dict(value=n_rays / sec, unit="rays/s", cores=torch.get_num_threads(), kind="port",
+                protocol="full training steps (forward, backward, Adam) over a bounded ray sample; BASELINE.md section 3 "
+                         "describes a 4096-ray forward render instead -- rays/s of a training step is the metric here",
                 sample=f"{steps} steps x {n_rays} rays of the same workload ({key}; oracle/ngp_ref.py train_step, torch CPU "
                        f"ops; median step {sec:.2f} s; analytic occupancy, random-init weights)"), sec
 
@@ -236,6 +238,18 @@ def kernel_costs(n_rays, n_samples, n_alive, shard, table_in_l2, world, grad16):
         "b2n_adam_step_peer": ("nvlink", wire * shard),
         "b2n_grad_pack_half": ("hbm", 10 * shard * world),
     }
+
+
+def nvlink_counters(index):
+    """Data bytes sent / received over all NVLinks of one GPU so far (`nvidia-smi nvlink -gt d`), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True,
+                             timeout=20).stdout
+        tx = sum(int(l.split(":")[-1].split()[0]) for l in out.splitlines() if "Data Tx" in l)
+        rx = sum(int(l.split(":")[-1].split()[0]) for l in out.splitlines() if "Data Rx" in l)
+        return (tx * 1024, rx * 1024) if (tx or rx) else None
+    except Exception:
+        return None
 
 
 def load_ncu_metrics():
@@ -460,10 +474,12 @@ def main():
     # ---- timed: device-resident inputs
     clocks = ClockSampler(local); clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nv0 = nvlink_counters(local) if (world > 1 and rank == 0) else None
     barrier(); e0.record()
     for _ in range(args.steps):
         dev_step()
     e1.record(); barrier()
+    nv1 = nvlink_counters(local) if nv0 is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     # ---- timed: end to end through the public API with host batches (H2D + loss D2H inside)
     barrier(); t0 = time.perf_counter(); e0.record()
@@ -632,6 +648,9 @@ def main():
                                 if k.startswith(("b2n_peer", "b2n_adam_step", "b2n_grad_pack", "b2n_scaler"))},
                             nvlink_bytes_per_step=wire, nvlink_gbs=wire / t_x / 1e9 if t_x else None,
                             nvlink_peak_gbs=770.0,
+                            nvlink_counters_bytes_per_step=dict(tx=(nv1[0] - nv0[0]) / args.steps, rx=(nv1[1] - nv0[1]) / args.steps,
+                                                                source="nvidia-smi nvlink -gt d around the timed region, rank 0")
+                            if (nv0 and nv1) else None,
                             note="per rank and direction: (W-1) remote gradient reads + (W-1) remote fp16 parameter stores "
                                  "per owned element; the two barrier launches include the wait for the slowest rank")
         cb = None

@@ -35,7 +35,7 @@ s = tr.sets[tr.cur]
 tr.step_count += 1; tr._set_hyper(); tr._march(s); tr._forward_backward(s)      # fills every buffer of the step
 torch.cuda.synchronize()
 P, cap, nd = L.ptr, tr.capacity, s.counter
-din_enc = torch.empty(cap, 32, dtype=torch.float16, device=dev)
+din_enc = tr.din_enc                     # filled by the real step above (zeros would let the scatter skip its reds)
 calls = {
     "hashgrid_fw": lambda: L.call("b2n_hashgrid_fw", P(s.xyzs), P(tr.h_xyz[tr.n_mlp:]), tr.layout, cap, P(nd), P(tr.enc), 32),
     "field_mlp_fw": lambda: L.call("b2n_field_mlp_fw", P(tr.enc), 32, P(s.dirs), P(tr.w_image), cap, P(nd), P(tr.sigmas), P(tr.rgbs), P(tr.h)),

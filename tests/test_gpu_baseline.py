@@ -553,3 +553,43 @@ def test_c4_depth_prior_training_step_matches_oracle(built_lib):
     tgt = syn.shade(rays_o, rays_d, scale).to(DEV)
     ls = [float(tr2.step(rays_o.to(DEV), rays_d.to(DEV), tgt, prior_disp=prior.to(DEV)).item()) for _ in range(25)]
     assert ls[-1] < 0.7 * ls[0], ls
+
+
+def test_trainer_frequency_encoding_matches_oracle_step(built_lib):
+    """The fork's ACTIVE configuration (networks.py:49-53: Frequency-12, 80-wide first layer) through the fused
+    trainer: one step against the oracle, then graph-replayed training reduces the loss."""
+    from google_nerf_b200 import synthetic as syn
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.trainer import NGPTrainer
+    from oracle import ngp_ref as O
+    scale, n = 0.5, 1024
+    s = make_scene(scale, n, seed=17)
+    ref = O.NGPRef(scale, encoding="Frequency", seed=7)
+    ref.density_bitfield = s["bitfield"].clone()
+    g = torch.Generator().manual_seed(2)
+    target = torch.rand(n, 3, generator=g)
+    model = NGP(scale, encoding="Frequency").to(DEV)
+    model.xyz_encoder.params.data.copy_(ref.xyz_params.detach()); model.rgb_net.params.data.copy_(ref.rgb_params.detach())
+    model.density_bitfield.copy_(s["bitfield"])
+    tr = NGPTrainer(model, n_rays=n, use_graph=False, samples_per_ray=200, grid_update_interval=10 ** 9)
+    assert tr.k1 == 80 and not tr.hashed
+    tr.step_count = 1
+    tr.fixed_noise = s["noise"].to(DEV)
+    tr.set_batch(s["rays_o"].to(DEV), s["rays_d"].to(DEV), target.to(DEV))
+    sset = tr.sets[tr.cur]
+    tr._set_hyper(); tr._march(sset); tr._forward_backward(sset)
+    res = O.render(ref, s["rays_o"], s["rays_d"].clone(), noise=s["noise"])
+    loss = O.nerf_loss(res, target)
+    loss.backward()
+    assert int(sset.counter[0].item()) == res["total_samples"] > 1000
+    torch.testing.assert_close(tr.opacity.cpu(), res["opacity"].detach(), rtol=5e-3, atol=5e-3)
+    assert abs(tr.loss.item() - loss.item()) < 2e-3 * abs(loss.item())
+    for got, want, name in ((tr.g_rgb, ref.rgb_params.grad, "rgb_net"), (tr.g_xyz, ref.xyz_params.grad, "xyz_encoder")):
+        sc = want.abs().max().item()
+        err = (got.cpu() / tr.loss_scale - want).abs().max().item()
+        assert err <= 3e-3 * sc, (name, err / sc)
+    tr.use_graph = True
+    ro, rd = s["rays_o"].to(DEV), s["rays_d"].to(DEV)
+    tgt = syn.shade(ro, rd, scale)
+    ls = [float(tr.step(ro, rd, tgt).item()) for _ in range(40)]
+    assert ls[-1] < 0.8 * ls[0], (ls[0], ls[-1])
