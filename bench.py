@@ -622,6 +622,7 @@ def main():
         # ---- hash encode vs its rooflines
         t_fw, t_bw = table.get("b2n_hashgrid_fw", 0) * 1e-3, table.get("b2n_hashgrid_bw", 0) * 1e-3
         req_fw = ncu_per_launch("b2n_hashgrid_fw", "lts_requests_per_unit")
+        req_bw = ncu_per_launch("b2n_hashgrid_bw", "lts_requests_per_unit")
         sec_fw = ncu_per_launch("b2n_hashgrid_fw", "lts_sectors_per_unit")
         probe_req_per_load = ncu["kernels"]["b2n_membench_gather"]["lts_requests_per_unit"] if ncu and \
             "b2n_membench_gather" in ncu.get("kernels", {}) else None
@@ -638,6 +639,9 @@ def main():
             probe_l2_requests_per_s=gather_loads_per_s * probe_req_per_load if probe_req_per_load else None,
             fw_frac_of_request_rate=(req_fw / t_fw) / (gather_loads_per_s * probe_req_per_load)
             if (req_fw and t_fw and probe_req_per_load) else None,
+            bw_l2_requests_per_s=req_bw / t_bw if (req_bw and t_bw) else None,
+            bw_frac_of_request_rate=(req_bw / t_bw) / (gather_loads_per_s * probe_req_per_load)
+            if (req_bw and t_bw and probe_req_per_load) else None,
             note="algorithmic bytes: 588 B/sample fw, 1100 B/sample bw (SURVEY 8d); table %.1f MiB fp16" %
                  (model.xyz_encoder.enc.n_params * 2 / 2 ** 20))
         t_m = (table.get("b2n_raymarching_train_count", 0) + table.get("b2n_raymarching_train_write", 0)) * 1e-3
