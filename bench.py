@@ -668,7 +668,7 @@ def main():
                             nvlink_peak_gbs=770.0,
                             nvlink_counters_bytes_per_step=dict(tx=(nv1[0] - nv0[0]) / args.steps, rx=(nv1[1] - nv0[1]) / args.steps,
                                                                 source="nvidia-smi nvlink -gt d around the timed region, rank 0")
-                            if (nv0 and nv1) else None,
+                            if (nv0 and nv1) else "nvidia-smi nvlink -gt d reports N/A for every link on this pool",
                             note="per rank and direction: (W-1) remote gradient reads + (W-1) remote fp16 parameter stores "
                                  "per owned element; the two barrier launches include the wait for the slowest rank")
         cb = None
