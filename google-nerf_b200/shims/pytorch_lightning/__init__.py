@@ -2,8 +2,11 @@
 LightningModule (save_hyperparameters, log, device, global_step, current_epoch), Trainer.fit with automatic
 optimisation (one training_step + backward + step per optimiser and batch, epoch-interval LR schedulers, fp16
 autocast + GradScaler for precision=16), a validation loop every `check_val_every_n_epoch` epochs, callbacks
-(ModelCheckpoint, TQDMProgressBar) and a scalar logger.  Single process only: the data-parallel path of this
-repository is `NGPTrainer` under torchrun, so `devices > 1` raises.
+(ModelCheckpoint, TQDMProgressBar) and a scalar logger.  `devices > 1` (train.py:260-263: DDPPlugin) is DDP over
+torch.distributed with ONE PROCESS PER GPU started by torchrun (Lightning 1.6 accepts that launch too): parameters and
+buffers are broadcast from rank 0, every rank draws its own batches, gradients are averaged over the ranks before the
+optimiser step, callbacks / logging run on rank 0.  (The fast data-parallel path of this repository is `NGPTrainer`
+under torchrun)
 
 Not a general Lightning replacement -- just enough for the reference's training scripts to run unchanged.
 """
@@ -106,9 +109,8 @@ class Trainer:
     def __init__(self, max_epochs=1, check_val_every_n_epoch=1, callbacks=None, logger=None, accelerator=None,
                  devices=1, strategy=None, num_sanity_val_steps=0, precision=32, enable_model_summary=True,
                  log_every_n_steps=50, limit_train_batches=None, limit_val_batches=None, **kwargs):
-        if isinstance(devices, int) and devices > 1:
-            raise NotImplementedError("this Lightning stand-in is single-process; multi-GPU training is NGPTrainer under "
-                                      "torchrun (see INTEGRATION.md)")
+        self.world = int(devices) if isinstance(devices, int) else 1
+        self.rank = 0
         self.max_epochs, self.check_val = max_epochs, check_val_every_n_epoch
         self.callbacks, self.logger = list(callbacks or []), logger
         self.accelerator, self.precision = accelerator, int(precision) if str(precision).isdigit() else 32
@@ -117,12 +119,47 @@ class Trainer:
         self.global_step = self.current_epoch = 0
         self.model = None
 
+    # ---- DDP over torch.distributed (devices > 1, one process per device under torchrun)
+    @property
+    def is_global_zero(self):
+        return self.rank == 0
+
+    def _init_ddp(self):
+        import torch.distributed as dist
+        if self.world <= 1:
+            return None
+        if "RANK" not in os.environ or int(os.environ.get("WORLD_SIZE", "1")) != self.world:
+            raise RuntimeError(f"devices={self.world}: start one process per device, e.g. `python -m torch.distributed.run "
+                               f"--nproc-per-node {self.world} --master-addr 127.0.0.1 train.py ...` (this stand-in does "
+                               "not spawn the workers itself)")
+        if not dist.is_initialized():
+            dist.init_process_group("nccl" if (self.accelerator == "gpu" and torch.cuda.is_available()) else "gloo")
+        self.rank = dist.get_rank()
+        return dist
+
+    def _sync_module(self, dist, model):
+        for t in list(model.parameters()) + list(model.buffers()):
+            dist.broadcast(t.data, src=0)
+
+    def _average_grads(self, dist, optimizer):
+        for group in optimizer.param_groups:
+            for p in group["params"]:
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad.div_(self.world)
+
     # ---- loops
     def fit(self, model, ckpt_path=None):
         self.model, model.trainer = model, self
-        device = torch.device("cuda") if (self.accelerator == "gpu" and torch.cuda.is_available()) else torch.device("cpu")
+        dist = self._init_ddp()
+        local = int(os.environ.get("LOCAL_RANK", 0)) if dist is not None else 0
+        device = torch.device("cuda", local) if (self.accelerator == "gpu" and torch.cuda.is_available()) else torch.device("cpu")
         if self.accelerator == "gpu" and device.type != "cuda":
             raise RuntimeError("accelerator='gpu' requested but CUDA is not available")
+        if device.type == "cuda":
+            torch.cuda.set_device(device)
+        if dist is not None and not self.is_global_zero:      # rank 0 owns checkpoints, progress and logs
+            self.callbacks, self.logger = [], None
         model.to(device)
         model.setup("fit")
         opt = model.configure_optimizers()
@@ -133,6 +170,8 @@ class Trainer:
             model.load_state_dict(state.get("state_dict", state), strict=False)
             self.current_epoch = int(state.get("epoch", -1)) + 1 if "epoch" in state else 0
             self.global_step = int(state.get("global_step", 0))
+        if dist is not None:
+            self._sync_module(dist, model)                   # every replica starts from rank 0's weights and buffers
         amp = self.precision == 16 and device.type == "cuda"
         scaler = torch.amp.GradScaler("cuda", enabled=amp) if hasattr(torch.amp, "GradScaler") else \
             torch.cuda.amp.GradScaler(enabled=amp)
@@ -160,6 +199,8 @@ class Trainer:
                         loss = loss["loss"]
                     optimizer.zero_grad(set_to_none=True)
                     scaler.scale(loss).backward()
+                    if dist is not None:
+                        self._average_grads(dist, optimizer)  # what DistributedDataParallel's reducer does
                     scaler.step(optimizer)
                     scaler.update()
                 self.global_step += 1

@@ -1,5 +1,6 @@
-"""`DDPPlugin` is only constructed when num_gpus > 1 (train.py:271-272); multi-GPU training in this repository is
-`NGPTrainer` under torchrun, so the stand-in Trainer refuses devices > 1 and this class is a placeholder."""
+"""`DDPPlugin` is only constructed when num_gpus > 1 (train.py:271-272).  The stand-in Trainer implements the DDP
+semantics itself (one process per device under torchrun: broadcast from rank 0, gradient averaging); the plugin object
+only carries its options."""
 
 
 class DDPPlugin:

@@ -63,3 +63,57 @@ def test_shard_bounds_single_process():
     assert D.shard_bounds(10, 3, 0) == (0, 4) and D.shard_bounds(10, 3, 1) == (4, 7) and D.shard_bounds(10, 3, 2) == (7, 10)
     out = D.render_sharded(_fake_render, torch.ones(4, 3), torch.ones(4, 3))
     assert out["rgb"].shape == (4, 3)
+
+
+def _pl_worker(rank, world, port, out_dir):
+    """The Lightning stand-in with devices=2: DDP semantics over gloo (broadcast, own batches, averaged gradients)."""
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "google-nerf_b200", "shims"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    from pytorch_lightning import LightningModule, Trainer
+    from pytorch_lightning.callbacks import ModelCheckpoint
+    from pytorch_lightning.plugins import DDPPlugin
+
+    class Sys(LightningModule):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(100 + rank)                     # replicas start DIFFERENT: the broadcast must fix that
+            self.lin = torch.nn.Linear(4, 1)
+
+        def configure_optimizers(self):
+            return torch.optim.SGD(self.parameters(), lr=0.1)
+
+        def train_dataloader(self):
+            g = torch.Generator().manual_seed(rank)           # every rank draws its own batches
+            return [torch.randn(8, 4, generator=g) for _ in range(5)]
+
+        def training_step(self, batch, batch_idx):
+            return (self.lin(batch) - batch.sum(-1, keepdim=True)).pow(2).mean()
+
+    m = Sys()
+    ck = ModelCheckpoint(dirpath=out_dir, filename="{epoch:d}")
+    Trainer(max_epochs=1, devices=world, strategy=DDPPlugin(find_unused_parameters=False), callbacks=[ck]).fit(m)
+    # reference: the same thing by hand on rank 0's initial weights, gradient = mean over both ranks' batches
+    torch.manual_seed(100)
+    ref = torch.nn.Linear(4, 1)
+    data = [[torch.randn(8, 4, generator=torch.Generator().manual_seed(r)) for _ in range(1)] for r in range(world)]
+    gens = [torch.Generator().manual_seed(r) for r in range(world)]
+    for _ in range(5):
+        ref.zero_grad()
+        for r in range(world):
+            b = torch.randn(8, 4, generator=gens[r])
+            ((ref(b) - b.sum(-1, keepdim=True)).pow(2).mean() / world).backward()
+        with torch.no_grad():
+            for p in ref.parameters():
+                p -= 0.1 * p.grad
+    torch.testing.assert_close(m.lin.weight.detach(), ref.weight.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(m.lin.bias.detach(), ref.bias.detach(), rtol=1e-5, atol=1e-6)
+    assert os.path.exists(os.path.join(out_dir, "epoch=0.ckpt")) or rank != 0
+    dist.barrier()
+    if rank == 1:
+        assert len(os.listdir(out_dir)) == 1                  # only rank 0 wrote a checkpoint
+    dist.destroy_process_group()
+
+
+def test_lightning_stand_in_ddp_world_2_gloo(tmp_path):
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_pl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)

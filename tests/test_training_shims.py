@@ -127,8 +127,9 @@ def test_lightning_fit_loop(shims, tmp_path):
     log = open(os.path.join(tmp_path, "logs", "exp", "metrics.csv")).read()
     assert "train/loss" in log and "test/v,1.0" in log
     assert m.get_progress_bar_dict().keys() >= {"v_num", "train/loss"}
-    with pytest.raises(NotImplementedError):
-        Trainer(devices=2, strategy=DDPPlugin(find_unused_parameters=False))
+    # devices > 1 is DDP with one process per device: outside such a launch fit() says how to start it
+    with pytest.raises(RuntimeError, match="one process per device"):
+        Trainer(devices=2, strategy=DDPPlugin(find_unused_parameters=False)).fit(Toy(argparse.Namespace(lr=0.5)))
 
 
 def test_synthetic_nsvf_dataset_layout(shims, tmp_path):
