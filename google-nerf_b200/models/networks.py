@@ -109,14 +109,16 @@ class NGP(nn.Module):
         self.sigma_act = TruncExp.apply
         # first-layer width of the fused field kernels: 16 levels x 2 features, or Frequency-12 padded to 80
         self.k1 = self.xyz_encoder.mlp.in_width
-        if self.k1 not in (32, 80):
-            raise ValueError("the fused field kernels are built for 16 hash levels x 2 features or Frequency-12")
+        # the fused tcgen05 kernels are built for these two widths (num_levels = 16, the default everywhere in the
+        # reference, and Frequency-12); any other `--num_levels` (train_scannet.py:72, opt.py:51) runs module by module on
+        # the generic kernels of the tinycudann drop-in -- same results, one launch per module
+        self.fused = self.k1 in (32, 80)
         self._image = self._image_key = self._layout = None
 
     # ------------------------------------------------------------------ field
     def density(self, x, return_feat=False):
         """x (N,3) in [-scale, scale] -> sigmas (N) fp32 [, h (N,16) fp16]."""
-        if x.is_cuda and not (torch.is_grad_enabled() and self.xyz_encoder.params.requires_grad):
+        if self.fused and x.is_cuda and not (torch.is_grad_enabled() and self.xyz_encoder.params.requires_grad):
             sigmas, h = self._density_fused(x.contiguous().float(), want_h=return_feat)
             return (sigmas, h) if return_feat else sigmas
         x = (x - self.xyz_min) / (self.xyz_max - self.xyz_min)
@@ -132,6 +134,11 @@ class NGP(nn.Module):
         normalisation happens inside the kernel and d is left as it was."""
         if not x.is_cuda:
             raise RuntimeError("google-nerf_b200 kernels need CUDA tensors (there is no CPU fallback)")
+        if not self.fused:       # networks.py:111-115 verbatim on the drop-in modules
+            sigmas, h = self.density(x, return_feat=True)
+            d = d / torch.norm(d, dim=-1, keepdim=True)
+            d = self.dir_encoder((d + 1) / 2)
+            return sigmas, self.rgb_net(torch.cat([d, h], 1))
         xe, rn = self.xyz_encoder.params, self.rgb_net.params
         if torch.is_grad_enabled() and (xe.requires_grad or rn.requires_grad):
             return _FieldFn.apply(x, d, xe, rn, self)
@@ -306,7 +313,7 @@ class NGP(nn.Module):
             xyz01 = torch.empty(coords.shape[0], 3, device=coords.device)
             L.call("b2n_grid_cell_positions", L.ptr(coords.contiguous()), L.ptr(noise), coords.shape[0], G, float(s),
                    lo, hi, 1, L.ptr(xyz01))
-            sigmas = self._density_fused01(xyz01)
+            sigmas = self._density_fused01(xyz01) if self.fused else torch.exp(self.xyz_encoder(xyz01)[:, 0].float())
             L.call("b2n_grid_scatter", L.ptr(indices.contiguous()), L.ptr(sigmas), indices.shape[0], L.ptr(tmp[c]),
                    tmp.shape[1])
 

@@ -55,7 +55,7 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     hits = hits_t[:, 0]                                   # (N_rays,2) view, advanced in place by the marcher
 
     samples = total_samples = 0
-    fused = hasattr(model, "_forward_fused")            # this repo's NGP (HashGrid or Frequency): fused field kernels
+    fused = getattr(model, "fused", False)              # this repo's NGP (HashGrid L=16 or Frequency): fused field kernels
     if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
         return _DeviceLoop.get(model, N_rays, exp_step_factor, T_threshold).run(rays_o, rays_d, hits)
     alive_indices = torch.arange(N_rays, device=device)
@@ -372,7 +372,7 @@ class _TrainRenderFn(torch.autograd.Function):
 
 def _train_graph_ok(model, rays_o, rays_d, kwargs):
     xe = getattr(model, "xyz_encoder", None)
-    return (kwargs.get("graph", True) and RayMarcher.sync_free and hasattr(model, "_fused_state") and rays_o.is_cuda
+    return (kwargs.get("graph", True) and RayMarcher.sync_free and getattr(model, "fused", False) and rays_o.is_cuda
             and torch.is_grad_enabled() and not rays_o.requires_grad and not rays_d.requires_grad and rays_o.shape[0] > 0
             and (xe.params.requires_grad or model.rgb_net.params.requires_grad)
             and not torch.cuda.is_current_stream_capturing())

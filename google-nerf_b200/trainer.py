@@ -61,6 +61,9 @@ class NGPTrainer:
         gradients dL/denc of an 8192-ray batch (~1e-5) are fp16 subnormals and lose most of their mantissa, at 2^14
         they sit in the normal range with > 2^20 of headroom.  An overflow skips that optimiser step and halves the
         scale like GradScaler; scale_growth_interval > 0 doubles it again after that many clean steps (0: never)."""
+        if not model.fused:
+            raise ValueError("NGPTrainer drives the fused field kernels: 16 hash levels x 2 features, or Frequency-12 "
+                             "(other --num_levels values train through render() + autograd)")
         self.model, self.n_rays = model, n_rays
         self.hashed = model.encoding == "HashGrid"
         self.k1 = model.k1

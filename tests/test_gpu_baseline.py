@@ -593,3 +593,42 @@ def test_trainer_frequency_encoding_matches_oracle_step(built_lib):
     tgt = syn.shade(ro, rd, scale)
     ls = [float(tr.step(ro, rd, tgt).item()) for _ in range(40)]
     assert ls[-1] < 0.8 * ls[0], (ls[0], ls[-1])
+
+
+def test_other_num_levels_runs_module_by_module(built_lib):
+    """train_scannet.py passes --num_levels to NGP (train_scannet.py:72): values other than 16 leave the fused kernels'
+    widths and run through the tinycudann drop-in modules -- render() + backward still match the oracle."""
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.models.rendering import render
+    from google_nerf_b200.models.custom_functions import RayMarcher
+    from oracle import ngp_ref as O
+    s = make_scene(0.5, 512, seed=19)
+    g = torch.Generator().manual_seed(1)
+    ref = O.NGPRef(0.5, num_levels=8, log2_T=15, seed=11)
+    with torch.no_grad():
+        ref.xyz_params[ref.n_mlp:] = (torch.rand(ref.layout["n_params"], generator=g) * 2 - 1) * 0.5
+    ref.density_bitfield = s["bitfield"].clone()
+    model = NGP(0.5, num_levels=8, log2_T=15).to(DEV)
+    assert not model.fused and model.xyz_encoder.params.numel() == ref.xyz_params.numel()
+    model.xyz_encoder.params.data.copy_(ref.xyz_params.detach()); model.rgb_net.params.data.copy_(ref.rgb_params.detach())
+    model.density_bitfield.copy_(s["bitfield"])
+    target = torch.rand(512, 3, generator=g)
+    RayMarcher.noise = s["noise"].to(DEV)
+    try:
+        res = render(model, s["rays_o"].to(DEV), s["rays_d"].to(DEV).clone())
+    finally:
+        RayMarcher.noise = None
+    loss = O.nerf_loss({k: v.float() for k, v in res.items() if torch.is_tensor(v) and v.ndim > 0}, target.to(DEV))
+    (loss * 1024.0).backward()
+    res_ref = O.render(ref, s["rays_o"], s["rays_d"].clone(), noise=s["noise"])
+    loss_ref = O.nerf_loss(res_ref, target)
+    loss_ref.backward()
+    assert int(res["total_samples"]) == res_ref["total_samples"]
+    assert abs(loss.item() - loss_ref.item()) < 3e-3 * abs(loss_ref.item())
+    for got, want in ((model.rgb_net.params.grad, ref.rgb_params.grad), (model.xyz_encoder.params.grad, ref.xyz_params.grad)):
+        assert (got.cpu() / 1024.0 - want).abs().max().item() <= 1e-2 * want.abs().max().item()
+    with torch.no_grad():
+        out = render(model, s["rays_o"][:64].to(DEV), s["rays_d"][:64].to(DEV).clone(), test_time=True)
+    assert torch.isfinite(out["rgb"]).all()
+    model.init_grid_buffers().update_density_grid(5.0, warmup=True)
+    assert float(model.density_grid.max()) > 0

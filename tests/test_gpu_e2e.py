@@ -312,3 +312,27 @@ def test_render_full_frame_device_loop_equals_host_loop(built_lib):
     for k in ("opacity", "depth", "rgb"):
         assert torch.equal(a[k], b[k]), k
     assert float(b["opacity"].max()) > 0.1 and float(b["opacity"].min()) == 0.0      # hit and missed rays both present
+
+
+def test_render_test_time_frequency_encoding(pair):
+    """Test-time render of the fork's active Frequency-12 configuration (device-driven loop on the K1 = 80 kernels)
+    against the oracle's host loop."""
+    from google_nerf_b200.models.networks import NGP
+    from google_nerf_b200.models.rendering import render
+    from oracle import ngp_ref as O
+    _, _, s = pair
+    ref = O.NGPRef(0.5, encoding="Frequency", seed=7)
+    ref.density_bitfield = s["bitfield"].clone()
+    model = NGP(0.5, encoding="Frequency").to(DEV)
+    model.xyz_encoder.params.data.copy_(ref.xyz_params.detach()); model.rgb_net.params.data.copy_(ref.rgb_params.detach())
+    model.density_bitfield.copy_(s["bitfield"])
+    n = 256
+    res_ref = O.render(ref, s["rays_o"][:n], s["rays_d"][:n].clone(), test_time=True, T_threshold=1e-2)
+    res = render(model, s["rays_o"][:n].to(DEV), s["rays_d"][:n].to(DEV).clone(), test_time=True, T_threshold=1e-2)
+    assert abs(int(res["total_samples"]) - res_ref["total_samples"]) <= 0.01 * res_ref["total_samples"] + 2
+    for k in ("opacity", "depth", "rgb"):
+        torch.testing.assert_close(res[k].cpu(), res_ref[k], rtol=1e-2, atol=1e-2, msg=lambda m: f"{k}: {m}")
+    host = render(model, s["rays_o"][:n].to(DEV), s["rays_d"][:n].to(DEV).clone(), test_time=True, T_threshold=1e-2,
+                  device_loop=False)
+    for k in ("opacity", "depth", "rgb"):
+        assert torch.equal(host[k], res[k]), k
