@@ -89,6 +89,11 @@ class NGPTrainer:
         self.directions = self.poses = None
         self.side = torch.cuda.Stream(device=self.dev)
         self._fork = torch.cuda.Event()
+        # Kernel nodes of a captured graph inherit the priority of the stream they were captured on: the training chain
+        # is captured on a high-priority stream, the pre-march of the next batch (which runs underneath it on the side
+        # stream) on a default-priority one, so that the block scheduler serves the chain's CTAs first
+        self._prio = os.environ.get("B2N_PRIO", "1") == "1"
+        self._cap_streams = (torch.cuda.Stream(device=self.dev, priority=-1), torch.cuda.Stream(device=self.dev, priority=0))
         # thread-per-ray count pass for the prefetched batch: fewer issue slots, but a long per-ray latency -- it only
         # pays once a batch has enough rays to fill the machine with threads (measured at 8192 rays: the tail of the
         # longest rays outlasts the training step, 0.47 vs 0.415 ms/step)
@@ -347,11 +352,12 @@ class NGPTrainer:
             return
         g = self.graphs.get(key)
         if g is None:
-            g = self._capture(fn, touches_params=key[0] in ("train", "opt"), touches_grid=key[0].startswith("grid"))
+            g = self._capture(fn, touches_params=key[0] in ("train", "opt"), touches_grid=key[0].startswith("grid"),
+                              low_priority=key[0] == "march")
             self.graphs[key] = g
         g.replay()
 
-    def _capture(self, fn, touches_params, touches_grid=False):
+    def _capture(self, fn, touches_params, touches_grid=False, low_priority=False):
         # one eager warm-up on a side stream, with the optimiser state restored afterwards so that it does not
         # count as a training step; then capture
         state_t = (self.p_pad, self.m, self.v, self.h_all, self.g_all, self.hyper) + \
@@ -372,8 +378,12 @@ class NGPTrainer:
             if not touches_grid:
                 self._pack_weights()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            fn()
+        if self._prio:
+            with torch.cuda.graph(g, stream=self._cap_streams[1 if low_priority else 0]):
+                fn()
+        else:
+            with torch.cuda.graph(g):
+                fn()
         return g
 
     # ------------------------------------------------------------------ public API
