@@ -526,22 +526,30 @@ def main():
     from google_nerf_b200.dist_utils import render_sharded
     render_info = None
     if extras:
-        frames, render_samples = [], 0
-        rkw = dict(test_time=True, T_threshold=1e-2, exp_step_factor=cfg["esf"])
-        with torch.no_grad():
-            for f in range(4):
-                ro, rd = syn.get_rays(dd, pp[f % N_IMG])
-                barrier(); t0 = time.perf_counter()
-                res = render_sharded(lambda o, d, **kw: render(model, o, d, **kw), ro, rd, tile=W_IMG, **rkw)
-                torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
-                if world > 1:
-                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-                frames.append(float(dt.item())); render_samples = int(res["total_samples"])
-        render_info = dict(mrays_per_s=W_IMG * H_IMG / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
-                           rays=W_IMG * H_IMG, samples_per_ray=render_samples / (W_IMG * H_IMG), n_gpus=world,
-                           note="render(test_time=True): the loop of rendering.py:42-114 driven from the device (8 rounds "
-                                "per CUDA-graph replay), T_threshold 1e-2 as in test.ipynb; N > 1: row tiles dealt "
-                                "round-robin to the ranks, max over ranks, all-gather of rgb/depth/opacity included")
+        def frame_rate(**more):
+            frames, samples = [], 0
+            rkw = dict(test_time=True, T_threshold=1e-2, exp_step_factor=cfg["esf"], **more)
+            with torch.no_grad():
+                for f in range(4):
+                    ro, rd = syn.get_rays(dd, pp[f % N_IMG])
+                    barrier(); t0 = time.perf_counter()
+                    res = render_sharded(lambda o, d, **kw: render(model, o, d, **kw), ro, rd, tile=W_IMG, **rkw)
+                    torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
+                    if world > 1:
+                        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                    frames.append(float(dt.item())); samples = int(res["total_samples"])
+            return dict(mrays_per_s=W_IMG * H_IMG / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
+                        samples_per_ray=samples / (W_IMG * H_IMG))
+        whole = getattr(model, "_whole_rays", None)
+        render_info = dict(**frame_rate(whole_rays=True), rays=W_IMG * H_IMG, n_gpus=world, round_loop=frame_rate(whole_rays=False),
+                           note="render(test_time=True), T_threshold 1e-2 as in test.ipynb: whole rays in one persistent "
+                                "kernel (csrc/render_tc.cu; a frame with a ray at the per-call sample budget falls back "
+                                "to the round loop); round_loop = the loop of rendering.py:42-114 driven from the device "
+                                "(whole_rays=False).  N > 1: row tiles dealt round-robin to the ranks, max over ranks, "
+                                "all-gather of rgb/depth/opacity included")
+        whole = getattr(model, "_whole_rays", None)
+        if whole is not None:
+            render_info["fell_back_to_round_loop"] = bool(int(whole.ctl_host[1]) > 0)
     # ---- image quality of what was just trained (sanity of the whole path, not a timed number): PSNR of a training view
     # and of held-out views against the analytic ground truth (T_threshold 1e-4 like validation, train.py:178-183)
     quality = None

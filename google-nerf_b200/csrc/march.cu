@@ -18,60 +18,12 @@
 // O(1); chunks that cross a binade, hit a rounding tie or sit in the geometric part fall back to the serial
 // recurrence.  The count pass records each chunk's emission mask (64 words per ray) so that the write pass
 // replays the ladder without touching the bitfield again.
-#include "common.cuh"
+#include "march.cuh"      // MarchParams, Ray, probe (the loop body, spelled in single IEEE operations), fill_params
 
-#define SQRT3 1.73205080757f
 #define FULL 0xffffffffu
-#define MAX_MIPS 16
 #define WS_WORDS 64          // workspace words per ray: [0] = n_chunks | overflow << 31, [1..63] = chunk masks
 #define MAX_CHUNKS (WS_WORDS - 1)
 #define SERIAL_MIN_RAYS 16384  // test marcher: at or above this many live rays, thread-per-ray; below, warp-per-ray
-
-struct MarchParams {
-    const uint8_t *bitfield;
-    int cascades, grid_size, max_samples;
-    float scale, esf, dt_lo, dt_hi, dt0, g_inv;  // dt0 = calc_dt for esf == 0 (constant step)
-    uint32_t g3;
-    float mip_bound[MAX_MIPS], mip_bound_inv[MAX_MIPS];   // min(2^(mip-1), scale) and its IEEE reciprocal
-};
-
-__device__ __forceinline__ float calc_dt(float t, const MarchParams &p) {
-    return fminf(p.dt_hi, fmaxf(p.dt_lo, t * p.esf));
-}
-
-struct Ray {
-    float ox, oy, oz, dx, dy, dz, ix, iy, iz;
-};
-
-// One DDA loop body at parameter t: occupancy of the cell, the step and (if empty) the skip target.
-__device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &p, float &dt, float &x,
-                                      float &y, float &z, float &t_target) {
-    const float G = (float)p.grid_size;
-    x = r.ox + t * r.dx;
-    y = r.oy + t * r.dy;
-    z = r.oz + t * r.dz;
-    dt = calc_dt(t, p);
-    int mip = 0;
-    if (p.cascades > 1) {
-        int e;
-        frexpf(fmaxf(fabsf(x), fmaxf(fabsf(y), fabsf(z))), &e);
-        mip = min(p.cascades - 1, max(0, e + 1));
-        frexpf(dt * G, &e);
-        mip = max(mip, min(p.cascades - 1, max(0, e)));
-    }
-    const float mip_bound = p.mip_bound[mip];
-    const float mip_bound_inv = p.mip_bound_inv[mip];
-    const int nx = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (x * mip_bound_inv + 1) * G)));
-    const int ny = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (y * mip_bound_inv + 1) * G)));
-    const int nz = __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, 0.5f * (z * mip_bound_inv + 1) * G)));
-    const uint32_t idx = (uint32_t)mip * p.g3 + b2n_morton3D(nx, ny, nz);
-    const bool occ = (__ldg(p.bitfield + (idx >> 3)) >> (idx & 7)) & 1;
-    const float tx = (((nx + 0.5f + 0.5f * copysignf(1.0f, r.dx)) * p.g_inv * 2 - 1) * mip_bound - x) * r.ix;
-    const float ty = (((ny + 0.5f + 0.5f * copysignf(1.0f, r.dy)) * p.g_inv * 2 - 1) * mip_bound - y) * r.iy;
-    const float tz = (((nz + 0.5f + 0.5f * copysignf(1.0f, r.dz)) * p.g_inv * 2 - 1) * mip_bound - z) * r.iz;
-    t_target = t + fmaxf(0.0f, fminf(tx, fminf(ty, tz)));
-    return occ;
-}
 
 // 32 rungs of the ladder starting at t_base: lane j gets f^j(t_base), t_next = f^32(t_base).
 template <bool ESF_ZERO>
@@ -232,14 +184,6 @@ __device__ __forceinline__ void replay_ray(const Ray &r, float t_start, int n_ch
     }
 }
 
-__device__ __forceinline__ Ray load_ray(const float *rays_o, const float *rays_d, int64_t r) {
-    Ray q;
-    q.ox = __ldg(rays_o + 3 * r); q.oy = __ldg(rays_o + 3 * r + 1); q.oz = __ldg(rays_o + 3 * r + 2);
-    q.dx = __ldg(rays_d + 3 * r); q.dy = __ldg(rays_d + 3 * r + 1); q.dz = __ldg(rays_d + 3 * r + 2);
-    q.ix = 1.0f / q.dx; q.iy = 1.0f / q.dy; q.iz = 1.0f / q.dz;
-    return q;
-}
-
 // ------------------------------------------------------------------------------------------------ train
 // WRITE=false: count pass (rays_a[r] = [r, -, N]); WRITE=true: write pass using rays_a[r] = [r, start, N].
 template <bool ESF_ZERO, bool WRITE>
@@ -386,25 +330,6 @@ __global__ void __launch_bounds__(1024) march_scan_kernel(int64_t *rays_a, int64
         counter[2] = any_over;
         counter[3] = (int32_t)total;
     }
-}
-
-static int fill_params(MarchParams &p, const uint8_t *bitfield, int cascades, float scale, float esf,
-                       int grid_size, int max_samples) {
-    B2N_CHECK_ARG(cascades >= 1 && cascades <= MAX_MIPS && grid_size >= 1 && grid_size <= 1024 && max_samples >= 1,
-                  "bad marcher config");
-    p.bitfield = bitfield; p.cascades = cascades; p.grid_size = grid_size; p.max_samples = max_samples;
-    p.scale = scale; p.esf = esf;
-    p.dt_lo = SQRT3 / max_samples;
-    p.dt_hi = SQRT3 * 2 * scale / grid_size;
-    p.dt0 = fminf(p.dt_hi, fmaxf(p.dt_lo, 0.0f));
-    p.g_inv = 1.0f / grid_size;
-    p.g3 = (uint32_t)grid_size * grid_size * grid_size;
-    for (int m = 0; m < MAX_MIPS; ++m) {
-        const float b = fminf(scalbnf(1.0f, m - 1), scale);   // host fp32 = IEEE, same values as the device would compute
-        p.mip_bound[m] = b;
-        p.mip_bound_inv[m] = 1.0f / b;
-    }
-    return 0;
 }
 
 static inline unsigned march_grid(int64_t n_warps, int per_sm = 8) { return b2n_grid((n_warps + 7) / 8, per_sm); }

@@ -71,8 +71,8 @@ def _partition(n, world, rank, tile, device):
         sels = [(owners == r).nonzero(as_tuple=True)[0] for r in range(world)]
         counts = [int(x.numel()) for x in sels]
         longest = max(counts)
-        # row j of rank r's padded part lands at ray sels[r][j]; padding rows are dropped
-        src = torch.cat([r * longest + torch.arange(c, device=device) for r, c in enumerate(counts)])
+        # row j of rank r's padded part (longest rows + one row of bookkeeping) lands at ray sels[r][j]
+        src = torch.cat([r * (longest + 1) + torch.arange(c, device=device) for r, c in enumerate(counts)])
         dst = torch.cat(sels)
         part = dict(sel=sels[rank], counts=counts, longest=longest, src=src, dst=dst)
         if len(_PARTITIONS) > 16:
@@ -96,14 +96,18 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
     part = _partition(n, world, rank, tile, rays_o.device)
     sel = part["sel"]
     res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **kwargs)
-    # one (longest, 5) fp32 block per rank: rgb | depth | opacity
-    mine = torch.zeros(part["longest"], 5, dtype=torch.float32, device=rays_o.device)
+    # one (longest + 1, 5) fp32 block per rank: rgb | depth | opacity, and in the last row the rank's sample count as
+    # three exact 16-bit digits -- ONE collective per frame
+    L1 = part["longest"] + 1
+    mine = torch.zeros(L1, 5, dtype=torch.float32, device=rays_o.device)
     c = sel.numel()
     mine[:c, 0:3] = res["rgb"]; mine[:c, 3] = res["depth"]; mine[:c, 4] = res["opacity"]
-    gathered = torch.empty(world * part["longest"], 5, dtype=torch.float32, device=rays_o.device)
+    cnt = int(res["total_samples"])
+    mine[L1 - 1].copy_(torch.tensor([cnt & 0xffff, (cnt >> 16) & 0xffff, cnt >> 32, 0, 0], dtype=torch.float32))
+    gathered = torch.empty(world * L1, 5, dtype=torch.float32, device=rays_o.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
     full = torch.empty(n, 5, dtype=torch.float32, device=rays_o.device)
     full[part["dst"]] = gathered[part["src"]]
-    ts = torch.as_tensor(res["total_samples"], device=rays_o.device, dtype=torch.int64).reshape(1).clone()
-    dist.all_reduce(ts, group=group)
-    return {"rgb": full[:, 0:3], "depth": full[:, 3], "opacity": full[:, 4], "total_samples": int(ts.item())}
+    digits = gathered.view(world, L1, 5)[:, L1 - 1, :3].to(torch.int64).sum(0).cpu()
+    total = int(digits[0]) + (int(digits[1]) << 16) + (int(digits[2]) << 32)
+    return {"rgb": full[:, 0:3], "depth": full[:, 3], "opacity": full[:, 4], "total_samples": total}

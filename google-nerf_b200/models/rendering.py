@@ -9,6 +9,7 @@ from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
 
 MAX_SAMPLES = 1024
 NEAR_DISTANCE = 0.05
+WHOLE_RAYS = False      # default of render(test_time=True, whole_rays=...): one persistent kernel per call (render_tc.cu)
 
 
 def render(model, rays_o, rays_d, **kwargs):
@@ -57,6 +58,10 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     samples = total_samples = 0
     fused = getattr(model, "fused", False)              # this repo's NGP (HashGrid L=16 or Frequency): fused field kernels
     if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
+        if kwargs.get("whole_rays", WHOLE_RAYS) and _WholeRays.supports(model):
+            res = _WholeRays.get(model, N_rays).run(rays_o, rays_d, hits, exp_step_factor, T_threshold)
+            if res is not None:                           # None: a ray met the per-call sample budget -> round loop
+                return res
         return _DeviceLoop.get(model, N_rays, exp_step_factor, T_threshold).run(rays_o, rays_d, hits)
     alive_indices = torch.arange(N_rays, device=device)
     min_samples = 1 if exp_step_factor == 0 else 4
@@ -91,6 +96,51 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 
     rgb = rgb + _background(exp_step_factor, device) * (1 - opacity)[:, None]
     return {"opacity": opacity, "depth": depth, "rgb": rgb, "total_samples": total_samples}
+
+
+class _WholeRays:
+    """Test-time rendering with ONE launch per call (csrc/render_tc.cu): every ray runs the per-ray arithmetic of
+    rendering.py:64-102 -- march, field, compositing -- start to finish inside a persistent kernel; rays are independent
+    at test time, the reference's rounds only batch them.  HashGrid field (k1 = 32).  The one thing a ray cannot know
+    without the rounds is the per-call sample budget (`samples < MAX_SAMPLES`, rendering.py:66): the kernel counts
+    rays that reach MAX_SAMPLES alive and `run` then returns None so that the caller renders that frame with the round
+    loop (a box of scale 0.5 cannot get there: sqrt(3) / dt = 1024).  `whole_rays=False` selects the round loop."""
+
+    @staticmethod
+    def supports(model):
+        return getattr(model, "encoding", None) == "HashGrid" and model.k1 == 32
+
+    @classmethod
+    def get(cls, model, n_rays):
+        st = getattr(model, "_whole_rays", None)
+        if st is None or st.n != n_rays or st.dev != model.center.device:
+            st = cls(model, n_rays)
+            model._whole_rays = st
+        return st
+
+    def __init__(self, model, n):
+        self.model, self.n, self.dev = model, n, model.center.device
+        self.ctl = torch.zeros(8, dtype=torch.int32, device=self.dev)
+        self.ctl_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+
+    def run(self, rays_o, rays_d, hits, esf, T_threshold, ray_samples=None):
+        from .. import _lib as L
+        m, P, n, dev = self.model, L.ptr, self.n, self.dev
+        p16, image = m._fused_state(dev)
+        rays_o, rays_d, hits = rays_o.contiguous().float(), rays_d.contiguous().float(), hits.contiguous().float()
+        opacity, depth, rgb = (torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, 3, device=dev))
+        L.call("b2n_render_rays", P(rays_o), P(rays_d), P(hits), n, P(m.density_bitfield), m.cascades, float(m.scale),
+               float(esf), m.grid_size, MAX_SAMPLES, m._layout, P(p16[m.xyz_encoder.mlp.n_params:]), P(image),
+               float(T_threshold), P(opacity), P(depth), P(rgb), P(self.ctl), P(ray_samples))
+        self.ctl_host.copy_(self.ctl, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        c = self.ctl_host
+        self.rounds = int(c[4])
+        if int(c[1]) > 0:
+            return None
+        total = (int(c[3]) << 32) | (int(c[2]) & 0xffffffff)
+        rgb = rgb + _background(esf, dev) * (1 - opacity)[:, None]
+        return {"opacity": opacity, "depth": depth, "rgb": rgb, "total_samples": total}
 
 
 class _DeviceLoop:

@@ -238,6 +238,24 @@ B2N_API int b2n_field_pack_weights(const b2n_half *sigma_weights, const b2n_half
                                    b2n_hyper *scaler_update, void *stream);
 B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, const b2n_half *image, int64_t n,
                              const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *h, void *stream);
+
+/* Whole rays in ONE persistent kernel: the test-time loop of models/rendering.py:42-114 for the 16-level HashGrid field
+ * (k1 = 32) without rounds, launches or intermediate arrays.  A CTA owns 128 ray slots; per round it marches
+ * (the reference's serial DDA loop), gathers the hash grid, runs the five layers on tcgen05 and composites, rays take
+ * their next samples as soon as their own previous ones are composited and new rays come from a global queue.
+ * rays_o / rays_d (n,3), hits_t (n,2) = [t_near, t_far] (read only), layout / table / image as for b2n_hashgrid_fw /
+ * b2n_field_mlp_fw.  opacity (n), depth (n), rgb (n,3) are written once per ray (no background blend).
+ * ctl: 8 x i32 on the device, 8-byte aligned, zeroed by the call: [1] rays that reached max_samples while alive (the
+ * reference's per-call sample budget would have cut them at a schedule-dependent point: the caller re-renders such a
+ * frame with the round loop), [2..3] u64 samples marched, [4] rounds of the longest CTA.  ray_samples (n) i32, may be
+ * NULL: samples marched per ray.  Per-ray arithmetic (positions, encoding, MLP, compositing order) is that of the
+ * round loop; rounds start at different samples, so T is re-derived from the opacity at different points: results
+ * agree to fp32 rounding (1e-5), not bit for bit. */
+B2N_API int b2n_render_rays(const float *rays_o, const float *rays_d, const float *hits_t, int64_t n_rays,
+                            const uint8_t *density_bitfield, int cascades, float scale, float exp_step_factor,
+                            int grid_size, int max_samples, const b2n_grid_layout *layout, const b2n_half *table,
+                            const b2n_half *image, float T_threshold, float *opacity, float *depth, float *rgb,
+                            int32_t *ctl, int32_t *ray_samples, void *stream);
 /* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale); the hidden
  * activations are recomputed from enc / dirs / h (the forward pass saves nothing else).  Writes dL_denc (n,32) fp16
  * for b2n_hashgrid_bw (k1 = 32; NULL to skip, must be NULL for k1 = 80) and accumulates (+=) grad_sigma_w
