@@ -35,7 +35,8 @@ _SIGS = {
     "b2n_ray_sphere_intersect": [_P, _P, _P, _P, _L, _L, _I, _P, _P, _P, _P],
     "b2n_clamp_near": [_P, _L, _F, _P],
     "b2n_render_schedule": [_P, _L, _I, _I, _P],
-    "b2n_render_rays": [_P, _P, _P, _L, _P, _I, _F, _F, _I, _I, C.POINTER(GridLayout), _P, _P, _F, _P, _P, _P, _P, _P, _P],
+    "b2n_render_rays": [_P, _P, _P, _L, _P, _I, _F, _F, _I, _I, C.POINTER(GridLayout), _P, _P, _F, _F, _P, _P, _P, _I, _P, _P, _P,
+                        _P, _P],
     "b2n_raymarching_test_dev": [_P, _P, _P, _P, _P, _I, _F, _F, _I, _I, _L, _P, _P, _P, _P, _P, _P, _P],
     "b2n_composite_test_fw_dev": [_P, _P, _P, _P, _P, _P, _F, _P, _L, _P, _P, _P, _P, _P],
     "b2n_peer_alloc": [_L, C.POINTER(C.c_void_p), _P],

@@ -61,33 +61,6 @@ extern "C" int b2n_hashgrid_layout(int n_levels, int n_features, int log2_hashma
 #ifndef B2N_BW_PASS_BYTES
 #define B2N_BW_PASS_BYTES (72ull << 20)      // gradient bytes one level-major scatter pass may keep resident in the 126 MB L2
 #endif
-struct Corner4 {
-    uint32_t idx[4];
-    float w[4];
-    uint32_t key;     // packed integer lattice position of the cell (for run detection in the backward pass)
-};
-
-__device__ __forceinline__ void level_corners4(float px, float py, float pz, float scale, uint32_t res, uint32_t size,
-                                               uint32_t offset, int mode, int cx, Corner4 &c) {
-    const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
-    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
-    const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
-    const uint32_t x0 = (uint32_t)gx, y0 = (uint32_t)gy, z0 = (uint32_t)gz;
-    c.key = x0 | (y0 << 10) | (z0 << 20);
-    const uint32_t x = x0 + (uint32_t)cx;
-    const float wxc = cx ? wx : 1.0f - wx;
-    #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const uint32_t y = y0 + (k & 1), z = z0 + ((k >> 1) & 1);
-        float w = 1.0f;
-        w *= wxc;                                  // same product order as the 8-corner form: ((1*wx)*wy)*wz
-        w *= (k & 1) ? wy : 1.0f - wy;
-        w *= (k & 2) ? wz : 1.0f - wz;
-        c.idx[k] = offset + grid_index_m(x, y, z, res, size, mode);
-        c.w[k] = w;
-    }
-}
-
 __global__ void __launch_bounds__(128) hashgrid_fw_kernel(const float *__restrict__ x,
                                                           const __half2 *__restrict__ table,
                                                           const __grid_constant__ GridLevels g, int64_t n,

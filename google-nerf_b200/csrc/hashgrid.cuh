@@ -82,6 +82,35 @@ __device__ __forceinline__ void level_corners(float px, float py, float pz, floa
     }
 }
 
+// Half a cell: the four (y, z) corners at x0 + cx.  Two adjacent lanes (cx = lane & 1) share a sample, so their
+// gathers fall into one sector; the halves are combined with one xor-shuffle (hashgrid_fw_kernel, render_tc.cu).
+struct Corner4 {
+    uint32_t idx[4];
+    float w[4];
+    uint32_t key;     // packed integer lattice position of the cell (for run detection in the backward pass)
+};
+
+__device__ __forceinline__ void level_corners4(float px, float py, float pz, float scale, uint32_t res, uint32_t size,
+                                               uint32_t offset, int mode, int cx, Corner4 &c) {
+    const float fx = fmaf(scale, px, 0.5f), fy = fmaf(scale, py, 0.5f), fz = fmaf(scale, pz, 0.5f);
+    const float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    const float wx = fx - gx, wy = fy - gy, wz = fz - gz;
+    const uint32_t x0 = (uint32_t)gx, y0 = (uint32_t)gy, z0 = (uint32_t)gz;
+    c.key = x0 | (y0 << 10) | (z0 << 20);
+    const uint32_t x = x0 + (uint32_t)cx;
+    const float wxc = cx ? wx : 1.0f - wx;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t y = y0 + (k & 1), z = z0 + ((k >> 1) & 1);
+        float w = 1.0f;
+        w *= wxc;                                  // same product order as the 8-corner form: ((1*wx)*wy)*wz
+        w *= (k & 1) ? wy : 1.0f - wy;
+        w *= (k & 2) ? wz : 1.0f - wz;
+        c.idx[k] = offset + grid_index_m(x, y, z, res, size, mode);
+        c.w[k] = w;
+    }
+}
+
 // The two x-corners of a cell: entries i0 (x0) and i1 (x0 + 1).  Whenever they form an aligned pair {2m, 2m + 1} -- dense
 // levels with an even entry index, hashed levels with an even x0 (the prime of the x axis is 1, so x0 and x0 + 1 then
 // differ in bit 0 only) -- both go out as ONE 16-byte red.global.add.v4.f32: the scatter is bound by the number of L2

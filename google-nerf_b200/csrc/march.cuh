@@ -35,9 +35,11 @@ __device__ __forceinline__ int axis_cell(float x, float bound_inv, float G) {
     return __float2int_rz(fminf(G - 1.0f, fmaxf(0.0f, u)));
 }
 
-// One DDA loop body at parameter t: occupancy of the cell, the step and (if empty) the skip target.
-__device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &p, float &dt, float &x,
-                                      float &y, float &z, float &t_target) {
+// One DDA loop body at parameter t, in two halves so that a caller can put other work between the address and the
+// use of the occupancy byte: probe_cell = position, step, bitfield index of the cell and (for an empty cell) the skip
+// target; cell_occupied = the bit.  probe = both.
+__device__ __forceinline__ uint32_t probe_cell(const Ray &r, float t, const MarchParams &p, float &dt, float &x,
+                                               float &y, float &z, float &t_target) {
     const float G = (float)p.grid_size;
     x = __fadd_rn(r.ox, __fmul_rn(t, r.dx));
     y = __fadd_rn(r.oy, __fmul_rn(t, r.dy));
@@ -54,13 +56,19 @@ __device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &
     const float mip_bound = p.mip_bound[mip];
     const float mip_bound_inv = p.mip_bound_inv[mip];
     const int nx = axis_cell(x, mip_bound_inv, G), ny = axis_cell(y, mip_bound_inv, G), nz = axis_cell(z, mip_bound_inv, G);
-    const uint32_t idx = (uint32_t)mip * p.g3 + b2n_morton3D(nx, ny, nz);
-    const bool occ = (__ldg(p.bitfield + (idx >> 3)) >> (idx & 7)) & 1;
     const float tx = axis_exit(nx, r.dx, r.ix, x, p.g_inv, mip_bound);
     const float ty = axis_exit(ny, r.dy, r.iy, y, p.g_inv, mip_bound);
     const float tz = axis_exit(nz, r.dz, r.iz, z, p.g_inv, mip_bound);
     t_target = __fadd_rn(t, fmaxf(0.0f, fminf(tx, fminf(ty, tz))));
-    return occ;
+    return (uint32_t)mip * p.g3 + b2n_morton3D(nx, ny, nz);
+}
+__device__ __forceinline__ bool cell_occupied(const MarchParams &p, uint32_t idx) {
+    return (__ldg(p.bitfield + (idx >> 3)) >> (idx & 7)) & 1;
+}
+__device__ __forceinline__ bool probe(const Ray &r, float t, const MarchParams &p, float &dt, float &x,
+                                      float &y, float &z, float &t_target) {
+    const uint32_t idx = probe_cell(r, t, p, dt, x, y, z, t_target);
+    return cell_occupied(p, idx);
 }
 
 __device__ __forceinline__ Ray load_ray(const float *rays_o, const float *rays_d, int64_t r) {

@@ -81,6 +81,14 @@ def _partition(n, world, rank, tile, device):
     return part
 
 
+def _takes_kwargs(fn):
+    import inspect
+    try:
+        return any(p.kind == p.VAR_KEYWORD for p in inspect.signature(fn).parameters.values())
+    except (TypeError, ValueError):
+        return False
+
+
 def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
     """Tile-sharded test-time render; the (rgb, depth, opacity) parts are gathered with ONE collective and put back in
     ray order.  `render_fn(rays_o, rays_d, **kwargs)` -> dict with those three keys (+ total_samples).
@@ -95,19 +103,27 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
         return render_fn(rays_o, rays_d, **kwargs)
     part = _partition(n, world, rank, tile, rays_o.device)
     sel = part["sel"]
-    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **kwargs)
-    # one (longest + 1, 5) fp32 block per rank: rgb | depth | opacity, and in the last row the rank's sample count as
-    # three exact 16-bit digits -- ONE collective per frame
+    # one (longest + 1, 5) fp32 block per rank: rgb | depth | opacity, and in the last row the rank's totals (samples
+    # marched as three exact 16-bit digits, rays cut at the sample budget) -- ONE collective and one host sync per frame
     L1 = part["longest"] + 1
-    mine = torch.zeros(L1, 5, dtype=torch.float32, device=rays_o.device)
     c = sel.numel()
-    mine[:c, 0:3] = res["rgb"]; mine[:c, 3] = res["depth"]; mine[:c, 4] = res["opacity"]
-    cnt = int(res["total_samples"])
-    mine[L1 - 1].copy_(torch.tensor([cnt & 0xffff, (cnt >> 16) & 0xffff, cnt >> 32, 0, 0], dtype=torch.float32))
+    mine = part.get("mine")
+    if mine is None:
+        mine = part["mine"] = torch.zeros(L1, 5, dtype=torch.float32, device=rays_o.device)
+    # a renderer that can write its pixels and totals straight into the block does (models/rendering.py::_WholeRays)
+    extra = dict(packed_out=mine, tail_out=mine[L1 - 1, :4]) if _takes_kwargs(render_fn) else {}
+    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **extra, **kwargs)
+    if res.get("tail") is None:
+        mine[:c, 0:3] = res["rgb"]; mine[:c, 3] = res["depth"]; mine[:c, 4] = res["opacity"]
+        cnt = int(res["total_samples"])
+        mine[L1 - 1].copy_(torch.tensor([cnt & 0xffff, (cnt >> 16) & 0xffff, cnt >> 32, 0, 0], dtype=torch.float32))
     gathered = torch.empty(world * L1, 5, dtype=torch.float32, device=rays_o.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
     full = torch.empty(n, 5, dtype=torch.float32, device=rays_o.device)
     full[part["dst"]] = gathered[part["src"]]
-    digits = gathered.view(world, L1, 5)[:, L1 - 1, :3].to(torch.int64).sum(0).cpu()
+    digits = gathered.view(world, L1, 5)[:, L1 - 1, :4].to(torch.int64).sum(0).cpu()
+    if int(digits[3]) > 0 and kwargs.get("whole_rays", True):
+        # some rank had a ray at the per-call sample budget: every rank sees that and renders the frame with the round loop
+        return render_sharded(render_fn, rays_o, rays_d, group=group, tile=tile, **{**kwargs, "whole_rays": False})
     total = int(digits[0]) + (int(digits[1]) << 16) + (int(digits[2]) << 32)
     return {"rgb": full[:, 0:3], "depth": full[:, 3], "opacity": full[:, 4], "total_samples": total}

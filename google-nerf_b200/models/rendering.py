@@ -9,7 +9,7 @@ from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
 
 MAX_SAMPLES = 1024
 NEAR_DISTANCE = 0.05
-WHOLE_RAYS = False      # default of render(test_time=True, whole_rays=...): one persistent kernel per call (render_tc.cu)
+WHOLE_RAYS = True       # default of render(test_time=True, whole_rays=...): one persistent kernel per call (render_tc.cu)
 
 
 def render(model, rays_o, rays_d, **kwargs):
@@ -59,7 +59,8 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     fused = getattr(model, "fused", False)              # this repo's NGP (HashGrid L=16 or Frequency): fused field kernels
     if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
         if kwargs.get("whole_rays", WHOLE_RAYS) and _WholeRays.supports(model):
-            res = _WholeRays.get(model, N_rays).run(rays_o, rays_d, hits, exp_step_factor, T_threshold)
+            res = _WholeRays.get(model, N_rays).run(rays_o, rays_d, hits, exp_step_factor, T_threshold,
+                                                    packed_out=kwargs.get("packed_out"), tail_out=kwargs.get("tail_out"))
             if res is not None:                           # None: a ray met the per-call sample budget -> round loop
                 return res
         return _DeviceLoop.get(model, N_rays, exp_step_factor, T_threshold).run(rays_o, rays_d, hits)
@@ -99,12 +100,19 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
 
 
 class _WholeRays:
-    """Test-time rendering with ONE launch per call (csrc/render_tc.cu): every ray runs the per-ray arithmetic of
-    rendering.py:64-102 -- march, field, compositing -- start to finish inside a persistent kernel; rays are independent
-    at test time, the reference's rounds only batch them.  HashGrid field (k1 = 32).  The one thing a ray cannot know
-    without the rounds is the per-call sample budget (`samples < MAX_SAMPLES`, rendering.py:66): the kernel counts
-    rays that reach MAX_SAMPLES alive and `run` then returns None so that the caller renders that frame with the round
-    loop (a box of scale 0.5 cannot get there: sqrt(3) / dt = 1024).  `whole_rays=False` selects the round loop."""
+    """Test-time rendering with ONE persistent kernel per call (csrc/render_tc.cu): every ray runs the per-ray
+    arithmetic of rendering.py:64-102 -- march, field, compositing -- start to finish; rays are independent at test
+    time, the reference's rounds only batch them.  HashGrid field (k1 = 32).  Pixels agree with the round loop to fp32
+    rounding (the transmittance is carried across a ray's rounds instead of being re-derived from the opacity at each
+    round start), do not depend on which rays share a launch (a sharded frame equals the unsharded one bit for bit) and
+    are reproducible.  The one thing a ray cannot know without the rounds is the per-call sample budget
+    (`samples < MAX_SAMPLES`, rendering.py:66): the kernel counts rays that reach MAX_SAMPLES alive and `run` then
+    returns None so that the caller renders that frame with the round loop (a box of scale 0.5 cannot get there:
+    sqrt(3) / dt = 1024).  `total_samples` counts the samples marched under THIS kernel's row schedule (like the
+    reference's it includes samples marched behind a ray's termination point, so it is schedule-dependent).
+    `whole_rays=False` selects the round loop."""
+
+    FIRST_HIT = True      # pre-pass: one thread per ray walks the empty space in front of it (see render_tc.cu)
 
     @staticmethod
     def supports(model):
@@ -122,16 +130,32 @@ class _WholeRays:
         self.model, self.n, self.dev = model, n, model.center.device
         self.ctl = torch.zeros(8, dtype=torch.int32, device=self.dev)
         self.ctl_host = torch.zeros(8, dtype=torch.int32).pin_memory()
+        self.list = torch.empty(max(n, 1), 2, dtype=torch.int32, device=self.dev)   # (ray, t at its first sample)
 
-    def run(self, rays_o, rays_d, hits, esf, T_threshold, ray_samples=None):
+    def run(self, rays_o, rays_d, hits, esf, T_threshold, ray_samples=None, packed_out=None, tail_out=None):
+        """Dense form (packed_out is None): returns the result dict, or None when a ray met the sample budget.
+        Packed form (a rank's part of a sharded frame): pixels go to the rows of packed_out (n.., 5) = rgb | depth |
+        opacity, the call's totals to tail_out (4 floats, see b2n_render_rays); nothing is read back here -- the caller
+        looks at the gathered tails of all ranks once."""
         from .. import _lib as L
         m, P, n, dev = self.model, L.ptr, self.n, self.dev
         p16, image = m._fused_state(dev)
         rays_o, rays_d, hits = rays_o.contiguous().float(), rays_d.contiguous().float(), hits.contiguous().float()
-        opacity, depth, rgb = (torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, 3, device=dev))
+        bg = 1.0 if esf == 0 else 0.0                            # rendering.py:108-111, blended by the kernel
+        if packed_out is None:
+            opacity, depth, rgb = (torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, 3, device=dev))
+            outs, stride, tail = (P(opacity), P(depth), P(rgb)), 0, None
+        else:
+            assert packed_out.dtype == torch.float32 and packed_out.stride() == (5, 1) and packed_out.shape[0] >= n
+            rgb, depth, opacity = packed_out[:n, 0:3], packed_out[:n, 3], packed_out[:n, 4]
+            base = packed_out.data_ptr()
+            outs, stride, tail = (base + 16, base + 12, base), 5, tail_out
         L.call("b2n_render_rays", P(rays_o), P(rays_d), P(hits), n, P(m.density_bitfield), m.cascades, float(m.scale),
                float(esf), m.grid_size, MAX_SAMPLES, m._layout, P(p16[m.xyz_encoder.mlp.n_params:]), P(image),
-               float(T_threshold), P(opacity), P(depth), P(rgb), P(self.ctl), P(ray_samples))
+               float(T_threshold), bg, *outs, stride, P(tail), P(self.ctl), P(ray_samples),
+               P(self.list) if self.FIRST_HIT else None)
+        if packed_out is not None:
+            return {"opacity": opacity, "depth": depth, "rgb": rgb, "total_samples": None, "tail": tail_out}
         self.ctl_host.copy_(self.ctl, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         c = self.ctl_host
@@ -139,7 +163,6 @@ class _WholeRays:
         if int(c[1]) > 0:
             return None
         total = (int(c[3]) << 32) | (int(c[2]) & 0xffffffff)
-        rgb = rgb + _background(esf, dev) * (1 - opacity)[:, None]
         return {"opacity": opacity, "depth": depth, "rgb": rgb, "total_samples": total}
 
 

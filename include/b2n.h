@@ -240,22 +240,33 @@ B2N_API int b2n_field_mlp_fw(const b2n_half *enc, int k1, const float *dirs, con
                              const int32_t *n_dev, float *sigmas, float *rgbs, b2n_half *h, void *stream);
 
 /* Whole rays in ONE persistent kernel: the test-time loop of models/rendering.py:42-114 for the 16-level HashGrid field
- * (k1 = 32) without rounds, launches or intermediate arrays.  A CTA owns 128 ray slots; per round it marches
- * (the reference's serial DDA loop), gathers the hash grid, runs the five layers on tcgen05 and composites, rays take
+ * (k1 = 32) without grid-wide rounds, launches or intermediate arrays.  A CTA owns up to 128 ray slots; per round it
+ * marches (the reference's serial DDA loop), gathers the hash grid, runs the five layers on tcgen05 and composites, rays take
  * their next samples as soon as their own previous ones are composited and new rays come from a global queue.
  * rays_o / rays_d (n,3), hits_t (n,2) = [t_near, t_far] (read only), layout / table / image as for b2n_hashgrid_fw /
- * b2n_field_mlp_fw.  opacity (n), depth (n), rgb (n,3) are written once per ray (no background blend).
+ * b2n_field_mlp_fw.  opacity, depth, rgb are written once per ray: dense arrays (n), (n), (n,3) when out_stride == 0,
+ * otherwise columns of one packed block with out_stride floats per ray (e.g. rgb = base, depth = base + 3, opacity =
+ * base + 4, out_stride = 5: a rank's part of a sharded frame, ready for the all-gather).  background >= 0: rgb +=
+ * background * (1 - opacity) (rendering.py:108-111); < 0: no blend.  tail (4 floats, may be NULL): written by the last
+ * CTA: samples marched as three 16-bit digits and the number of rays cut at the budget (ctl[1]) -- the totals travel
+ * with the pixels, the host needs no separate read-back.
  * ctl: 8 x i32 on the device, 8-byte aligned, zeroed by the call: [1] rays that reached max_samples while alive (the
  * reference's per-call sample budget would have cut them at a schedule-dependent point: the caller re-renders such a
- * frame with the round loop), [2..3] u64 samples marched, [4] rounds of the longest CTA.  ray_samples (n) i32, may be
- * NULL: samples marched per ray.  Per-ray arithmetic (positions, encoding, MLP, compositing order) is that of the
- * round loop; rounds start at different samples, so T is re-derived from the opacity at different points: results
- * agree to fp32 rounding (1e-5), not bit for bit. */
+ * frame with the round loop), [2..3] u64 samples marched, [4] rounds of the longest CTA, [5] rays with at least one
+ * sample.  ray_samples (n) i32, may be NULL: samples marched per ray.  first_hit_list: n x 8 bytes of workspace, may be
+ * NULL: with it a pre-pass (one thread per ray) walks the empty space in front of every ray, writes the pixels of rays
+ * that meet nothing and queues the others at their first sample, so that the persistent kernel never waits on a
+ * new ray's chain of dependent occupancy loads.
+ * Per-ray arithmetic (positions, encoding, MLP, compositing order) is that of the round loop, except that the
+ * transmittance is carried across a ray's rounds (the round loop re-derives it as 1 - opacity at the start of each
+ * round): pixels agree with the round loop to fp32 rounding (1e-5), do not depend on which rays share a launch, and
+ * are reproducible bit for bit. */
 B2N_API int b2n_render_rays(const float *rays_o, const float *rays_d, const float *hits_t, int64_t n_rays,
                             const uint8_t *density_bitfield, int cascades, float scale, float exp_step_factor,
                             int grid_size, int max_samples, const b2n_grid_layout *layout, const b2n_half *table,
-                            const b2n_half *image, float T_threshold, float *opacity, float *depth, float *rgb,
-                            int32_t *ctl, int32_t *ray_samples, void *stream);
+                            const b2n_half *image, float T_threshold, float background, float *opacity, float *depth,
+                            float *rgb, int out_stride, float *tail, int32_t *ctl, int32_t *ray_samples,
+                            void *first_hit_list, void *stream);
 /* Backward of the same chain.  dL_dsigmas (n), dL_drgbs (n,3) fp32 (already multiplied by the loss scale); the hidden
  * activations are recomputed from enc / dirs / h (the forward pass saves nothing else).  Writes dL_denc (n,32) fp16
  * for b2n_hashgrid_bw (k1 = 32; NULL to skip, must be NULL for k1 = 80) and accumulates (+=) grad_sigma_w

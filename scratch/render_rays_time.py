@@ -24,7 +24,9 @@ ro_f, rd_f = syn.get_rays(dd, pp[0])
 rows = torch.arange(800, device=dev)
 share = (rows % 8 == 0).repeat_interleave(800)            # every 8th row: one rank's tiles at N = 8
 for name, ro, rd in (("full", ro_f, rd_f), ("eighth", ro_f[share].contiguous(), rd_f[share].contiguous())):
-    for wr in (False, True):
+    for wr, fh in (((True, True),) if os.environ.get('RR_ONLY') else ((False, True), (True, False), (True, True))):
+        from google_nerf_b200.models.rendering import _WholeRays
+        _WholeRays.FIRST_HIT = fh
         with torch.no_grad():
             for _ in range(3):
                 res = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=wr)
@@ -35,7 +37,25 @@ for name, ro, rd in (("full", ro_f, rd_f), ("eighth", ro_f[share].contiguous(), 
                 e0.record(); res = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=wr); e1.record()
                 torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
         extra = f"rounds {model._whole_rays.rounds}" if wr else f"rounds {int(model._device_loop.ctl_host[5])}"
-        print(f"{name:7s} whole_rays={wr!s:5s} ms {min(ts):.3f} (median {sorted(ts)[4]:.3f})  Mrays/s {len(ro) / min(ts) / 1e3:.1f}  "
+        if wr and fh:
+            import ctypes
+            from google_nerf_b200 import _lib as L
+            lib = ctypes.CDLL(L.LIB_PATH)
+            if hasattr(lib, "b2n_render_profile"):
+                buf = (ctypes.c_ulonglong * 8)()
+                lib.b2n_render_profile(buf, 1)
+                render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=True)
+                lib.b2n_render_profile(buf, 1)
+                tot = sum(buf[:5])
+                extra += "  phases A/B/C/D/E % " + " ".join(f"{100 * buf[i] / tot:.1f}" for i in range(5)) + \
+                         f"  cycles/round {tot / max(buf[5], 1):.0f}  cta-rounds {buf[5]}"
+            from torch.profiler import profile, ProfilerActivity
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=True)
+                torch.cuda.synchronize()
+            extra += "\n      kernels: " + ", ".join(f"{e.key[:28]} {e.device_time_total:.0f}us" for e in
+                                                   sorted(prof.key_averages(), key=lambda e: -e.device_time_total)[:6])
+        print(f"{name:7s} whole_rays={wr!s:5s} first_hit={fh!s:5s} ms {min(ts):.3f} (median {sorted(ts)[4]:.3f})  Mrays/s {len(ro) / min(ts) / 1e3:.1f}  "
               f"samples/ray {res['total_samples'] / len(ro):.2f}  {extra}", flush=True)
     a = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=False)
     b = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=True)

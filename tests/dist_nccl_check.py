@@ -87,6 +87,26 @@ def main():
     seen = (g1 >= 0) & (g2 >= 0)
     agree = ((g1 - g2).abs()[seen].mean() / g1[seen].abs().mean()).item()          # mean deviation / mean density
     assert agree < 0.25 and (g2 > 0).any() and b2.any(), (agree, (g1 - g2).abs()[seen].max().item(), g1[seen].max().item())
+    # sharded test-time render (BASELINE configs[2]): row tiles dealt round-robin / contiguous bands, gathered with one
+    # collective.  The whole-ray kernel's pixels do not depend on which rays share a launch, so the sharded frame equals
+    # the unsharded one bit for bit; the round loop's schedule follows each rank's own live-ray count (rounding level).
+    from google_nerf_b200.dist_utils import render_sharded
+    from google_nerf_b200.models.rendering import render
+    dirs = syn.directions(200, 200, syn.intrinsics(200, 200)).to(dev)
+    fro, frd = syn.get_rays(dirs, syn.hemisphere_poses(3)[1].to(dev))
+    with torch.no_grad():
+        for whole in (True, False):
+            kw = dict(test_time=True, T_threshold=1e-2, whole_rays=whole)
+            full = render(m, fro, frd.clone(), **kw)
+            for tile in (200, None):
+                sh = render_sharded(lambda o, d, **k: render(m, o, d, **k), fro, frd.clone(), tile=tile, **kw)
+                assert sh["total_samples"] > 0 and float(sh["opacity"].max()) > 0.05
+                for key in ("rgb", "depth", "opacity"):
+                    if whole:
+                        assert torch.equal(sh[key], full[key]), (key, tile)
+                    else:
+                        assert float((sh[key] - full[key]).abs().max()) < 5e-2 and \
+                            float(((sh[key] - full[key]).abs() > 1e-4).float().mean()) < 1e-2, (key, tile)
     if rank == 0:
         print("dist_nccl_check ok (comm %s): world" % comm_used, dist.get_world_size(), "final loss", l2[-1], "single-GPU", l1[-1],
               "mean density-grid deviation %.4f" % agree)
