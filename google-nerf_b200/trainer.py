@@ -517,6 +517,11 @@ class NGPTrainer:
         """Collective: release the NVLink peer mappings (comm == "p2p").  Call on every rank when training ends."""
         self.graphs = {}
         if self.peer is not None:
+            # the fp16 working copies the model's fused paths read live in the peer block: hand the model private copies
+            # before the block is freed (render() / density() keep working after training ends)
+            self.h_xyz, self.h_rgb = self.h_xyz.clone(), self.h_rgb.clone()
+            self.sync_model_half()
+            self.model._device_loop = None                   # (graphs captured over the old copies)
             self.peer.close()
             self.peer = None
 
