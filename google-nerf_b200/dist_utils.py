@@ -122,7 +122,7 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
     full = torch.empty(n, 5, dtype=torch.float32, device=rays_o.device)
     full[part["dst"]] = gathered[part["src"]]
     digits = gathered.view(world, L1, 5)[:, L1 - 1, :4].to(torch.int64).sum(0).cpu()
-    if int(digits[3]) > 0 and kwargs.get("whole_rays", True):
+    if int(digits[3]) > 0 and kwargs.get("whole_rays", True) is not False:
         # some rank had a ray at the per-call sample budget: every rank sees that and renders the frame with the round loop
         return render_sharded(render_fn, rays_o, rays_d, group=group, tile=tile, **{**kwargs, "whole_rays": False})
     total = int(digits[0]) + (int(digits[1]) << 16) + (int(digits[2]) << 32)

@@ -9,7 +9,8 @@ from .custom_functions import RayAABBIntersector, RayMarcher, VolumeRenderer
 
 MAX_SAMPLES = 1024
 NEAR_DISTANCE = 0.05
-WHOLE_RAYS = True       # default of render(test_time=True, whole_rays=...): one persistent kernel per call (render_tc.cu)
+WHOLE_RAYS = "auto"     # default of render(test_time=True, whole_rays=...): one persistent kernel per call (render_tc.cu)
+WHOLE_RAYS_MAX_TABLE_BYTES = 96 << 20   # "auto": only while the fp16 hash table stays L2-resident (B200: 126 MB L2)
 
 
 def render(model, rays_o, rays_d, **kwargs):
@@ -58,7 +59,7 @@ def _render_rays_test(model, rays_o, rays_d, hits_t, **kwargs):
     samples = total_samples = 0
     fused = getattr(model, "fused", False)              # this repo's NGP (HashGrid L=16 or Frequency): fused field kernels
     if fused and kwargs.get("device_loop", True) and not torch.cuda.is_current_stream_capturing():
-        if kwargs.get("whole_rays", WHOLE_RAYS) and _WholeRays.supports(model):
+        if _WholeRays.supports(model, kwargs.get("whole_rays", WHOLE_RAYS)):
             res = _WholeRays.get(model, N_rays).run(rays_o, rays_d, hits, exp_step_factor, T_threshold,
                                                     packed_out=kwargs.get("packed_out"), tail_out=kwargs.get("tail_out"))
             if res is not None:                           # None: a ray met the per-call sample budget -> round loop
@@ -115,8 +116,13 @@ class _WholeRays:
     FIRST_HIT = True      # pre-pass: one thread per ray walks the empty space in front of it (see render_tc.cu)
 
     @staticmethod
-    def supports(model):
-        return getattr(model, "encoding", None) == "HashGrid" and model.k1 == 32
+    def supports(model, mode=True):
+        """mode True: the HashGrid field (k1 = 32); "auto": additionally the fp16 table must fit the L2 -- the kernel
+        gathers all 16 levels of a sample at once with 512 threads per SM, which is fine against the L2 but not against
+        HBM (T = 2^22, 185 MB: 75 ms per 1920x1080 frame against 30 ms for the round loop with its level-major gather)."""
+        if not mode or getattr(model, "encoding", None) != "HashGrid" or model.k1 != 32:
+            return False
+        return mode is True or model.xyz_encoder.enc.n_params * 2 <= WHOLE_RAYS_MAX_TABLE_BYTES
 
     @classmethod
     def get(cls, model, n_rays):

@@ -63,7 +63,14 @@ def test_module_contract_on_cpu(built_lib):
     sd = m.state_dict()
     assert sd["xyz_encoder.params"].numel() == 11420064 + 3072 and sd["rgb_net.params"].numel() == 7168
     assert sd["dir_encoder.params"].numel() == 0 and m.cascades == 1 and m.grid_size == 128
-    assert NGP(16.0, log2_T=22).cascades == 6
+    big = NGP(16.0, log2_T=22)
+    assert big.cascades == 6
+    # test-time render path selection (rendering.py::_WholeRays.supports): the persistent whole-ray kernel for the
+    # HashGrid field while its fp16 table fits the L2, the round loop otherwise and for the Frequency encoding
+    from google_nerf_b200.models.rendering import _WholeRays
+    assert _WholeRays.supports(m, "auto") and _WholeRays.supports(m, True) and not _WholeRays.supports(m, False)
+    assert not _WholeRays.supports(big, "auto") and _WholeRays.supports(big, True)
+    assert not _WholeRays.supports(NGP(0.5, encoding="Frequency"), True)
     assert NGP(0.5, encoding="Frequency").xyz_encoder.params.numel() == 80 * 64 + 64 * 16
     # utils.load_ckpt-style round trip (ngp_pl/utils.py:4-25): keys under "model." stripped, then load_state_dict
     ckpt = {"state_dict": {"model." + k: v.clone() for k, v in sd.items()}}
