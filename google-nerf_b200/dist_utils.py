@@ -74,7 +74,11 @@ def _partition(n, world, rank, tile, device):
         # row j of rank r's padded part (longest rows + one row of bookkeeping) lands at ray sels[r][j]
         src = torch.cat([r * (longest + 1) + torch.arange(c, device=device) for r, c in enumerate(counts)])
         dst = torch.cat(sels)
-        part = dict(sel=sels[rank], counts=counts, longest=longest, src=src, dst=dst)
+        # the same as ONE gather: ray i of the frame (and, behind the rays, every rank's bookkeeping row) <- row inv[i]
+        inv = torch.empty(n + world, dtype=torch.int64, device=device)
+        inv[dst] = src
+        inv[n:] = torch.arange(world, device=device) * (longest + 1) + longest
+        part = dict(sel=sels[rank], counts=counts, longest=longest, src=src, dst=dst, inv=inv)
         if len(_PARTITIONS) > 16:
             _PARTITIONS.clear()
         _PARTITIONS[key] = part
@@ -112,16 +116,16 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, tile=None, **kwargs):
         mine = part["mine"] = torch.zeros(L1, 5, dtype=torch.float32, device=rays_o.device)
     # a renderer that can write its pixels and totals straight into the block does (models/rendering.py::_WholeRays)
     extra = dict(packed_out=mine, tail_out=mine[L1 - 1, :4]) if _takes_kwargs(render_fn) else {}
-    res = render_fn(rays_o[sel].contiguous(), rays_d[sel].contiguous(), **extra, **kwargs)
+    res = render_fn(rays_o.index_select(0, sel), rays_d.index_select(0, sel), **extra, **kwargs)
     if res.get("tail") is None:
         mine[:c, 0:3] = res["rgb"]; mine[:c, 3] = res["depth"]; mine[:c, 4] = res["opacity"]
         cnt = int(res["total_samples"])
         mine[L1 - 1].copy_(torch.tensor([cnt & 0xffff, (cnt >> 16) & 0xffff, cnt >> 32, 0, 0], dtype=torch.float32))
     gathered = torch.empty(world * L1, 5, dtype=torch.float32, device=rays_o.device)
     dist.all_gather_into_tensor(gathered, mine, group=group)
-    full = torch.empty(n, 5, dtype=torch.float32, device=rays_o.device)
-    full[part["dst"]] = gathered[part["src"]]
-    digits = gathered.view(world, L1, 5)[:, L1 - 1, :4].to(torch.int64).sum(0).cpu()
+    full = gathered.index_select(0, part["inv"])             # ray order, then the ranks' bookkeeping rows
+    digits = full[n:, :4].cpu().to(torch.int64).sum(0)       # the frame's one host synchronisation
+    full = full[:n]
     if int(digits[3]) > 0 and kwargs.get("whole_rays", True) is not False:
         # some rank had a ray at the per-call sample budget: every rank sees that and renders the frame with the round loop
         return render_sharded(render_fn, rays_o, rays_d, group=group, tile=tile, **{**kwargs, "whole_rays": False})
