@@ -542,14 +542,14 @@ def main():
                         samples_per_ray=samples / (W_IMG * H_IMG))
         whole = getattr(model, "_whole_rays", None)
         render_info = dict(**frame_rate(), rays=W_IMG * H_IMG, n_gpus=world, round_loop=frame_rate(whole_rays=False),
-                           note="render(test_time=True), T_threshold 1e-2 as in test.ipynb: whole rays in one persistent "
-                                "kernel (csrc/render_tc.cu; a frame with a ray at the per-call sample budget falls back "
-                                "to the round loop); round_loop = the loop of rendering.py:42-114 driven from the device "
-                                "(whole_rays=False).  N > 1: row tiles dealt round-robin to the ranks, max over ranks, "
-                                "all-gather of rgb/depth/opacity included")
+                           note="render(test_time=True), T_threshold 1e-2 as in test.ipynb.  Default path: whole rays in "
+                                "one persistent kernel (csrc/render_tc.cu) while the fp16 hash table fits the L2 (c2, "
+                                "c4), else the round loop (c5: both entries are the round loop); round_loop = the loop of "
+                                "rendering.py:42-114 driven from the device (whole_rays=False).  N > 1: row tiles dealt "
+                                "round-robin to the ranks, max over ranks, all-gather of rgb/depth/opacity included")
         whole = getattr(model, "_whole_rays", None)
         render_info["path"] = "whole_rays" if whole is not None else "round_loop"
-        if whole is not None:
+        if whole is not None and world == 1:
             render_info["fell_back_to_round_loop"] = bool(int(whole.ctl_host[1]) > 0)
     # ---- image quality of what was just trained (sanity of the whole path, not a timed number): PSNR of a training view
     # and of held-out views against the analytic ground truth (T_threshold 1e-4 like validation, train.py:178-183)
