@@ -527,21 +527,24 @@ def main():
     render_info = None
     if extras:
         def frame_rate(**more):
+            # 2 warm-up + 5 timed frames of the SAME view (frames of different views differ in cost); the rays exist before
+            # the clock starts; median of the timed frames, max over ranks
             frames, samples = [], 0
             rkw = dict(test_time=True, T_threshold=1e-2, exp_step_factor=cfg["esf"], **more)
             with torch.no_grad():
-                for f in range(4):
-                    ro, rd = syn.get_rays(dd, pp[f % N_IMG])
-                    barrier(); t0 = time.perf_counter()
+                ro, rd = syn.get_rays(dd, pp[0])
+                for f in range(7):
+                    torch.cuda.synchronize(); barrier(); t0 = time.perf_counter()
                     res = render_sharded(lambda o, d, **kw: render(model, o, d, **kw), ro, rd, tile=W_IMG, **rkw)
                     torch.cuda.synchronize(); dt = torch.tensor([time.perf_counter() - t0], device=dev)
                     if world > 1:
                         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
                     frames.append(float(dt.item())); samples = int(res["total_samples"])
-            return dict(mrays_per_s=W_IMG * H_IMG / min(frames[1:]) / 1e6, ms_per_frame=min(frames[1:]) * 1e3,
+            t = sorted(frames[2:])[len(frames[2:]) // 2]
+            return dict(mrays_per_s=W_IMG * H_IMG / t / 1e6, ms_per_frame=t * 1e3, ms_per_frame_min=min(frames[2:]) * 1e3,
                         samples_per_ray=samples / (W_IMG * H_IMG))
-        whole = getattr(model, "_whole_rays", None)
-        render_info = dict(**frame_rate(), rays=W_IMG * H_IMG, n_gpus=world, round_loop=frame_rate(whole_rays=False),
+        fr = frame_rate(); rl = frame_rate(whole_rays=False)
+        render_info = dict(**fr, rays=W_IMG * H_IMG, n_gpus=world, round_loop=rl,
                            note="render(test_time=True), T_threshold 1e-2 as in test.ipynb.  Default path: whole rays in "
                                 "one persistent kernel (csrc/render_tc.cu) while the fp16 hash table fits the L2 (c2, "
                                 "c4), else the round loop (c5: both entries are the round loop); round_loop = the loop of "
