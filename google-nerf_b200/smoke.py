@@ -1,6 +1,7 @@
 """One small invocation of the hot path on the GPU, checked against the oracle (the checker, never the
 thing shipped): a 512-ray training step of the HashGrid NGP -- AABB, marcher, hash encode, MLPs, compositing,
-loss, backward, Adam -- compared with oracle/ngp_ref.py on the same inputs, jitter and weights."""
+loss, backward, Adam -- and a 128-ray test-time render, compared with oracle/ngp_ref.py on the same inputs, jitter and
+weights."""
 import torch
 
 
@@ -25,6 +26,16 @@ def run(device):
     model.xyz_encoder.params.data.copy_(ref.xyz_params.detach())
     model.rgb_net.params.data.copy_(ref.rgb_params.detach())
     model.density_bitfield.copy_(ref.density_bitfield)
+    # test-time render of a few rays: the whole-ray kernel (march + hash grid + tcgen05 field + compositing in one
+    # launch) against the oracle's host loop of rendering.py:42-114
+    from .models.rendering import render
+    m = 128
+    res_t = O.render(ref, rays_o[:m], rays_d[:m].clone(), test_time=True, T_threshold=1e-2)
+    got_t = render(model, rays_o[:m].to(device), rays_d[:m].to(device).clone(), test_time=True, T_threshold=1e-2)
+    assert model._whole_rays.rounds > 0 and got_t["total_samples"] > 0
+    for k in ("opacity", "depth", "rgb"):
+        torch.testing.assert_close(got_t[k].cpu(), res_t[k], rtol=1e-2, atol=1e-2, msg=lambda msg: f"render {k}: {msg}")
+
     tr = NGPTrainer(model, n_rays=n, use_graph=False, samples_per_ray=160, warmup_steps=0, grid_update_interval=10 ** 9)
     tr.step_count = 2                                      # no grid update: the bitfield is the analytic one
     tr.fixed_noise = noise.to(device)
@@ -50,4 +61,5 @@ def run(device):
     tr._optimizer()
     assert float((tr.p_xyz - p_before).abs().max()) > 0
     torch.cuda.synchronize()
-    print(f"smoke ok: {n} rays, {n_samples} samples, loss {loss_gpu:.6f} (oracle {loss.item():.6f})")
+    print(f"smoke ok: {n} rays, {n_samples} samples, loss {loss_gpu:.6f} (oracle {loss.item():.6f}); "
+          f"test-time render of {m} rays: {got_t['total_samples']} samples")
