@@ -1,5 +1,5 @@
 // hashgrid.cuh -- device code of the multiresolution hash grid shared by encoding.cu (stand-alone gather / scatter
-// kernels) and field_tc.cu (scatter fused into the backward field kernel).
+// kernels) and render_tc.cu (the gather inside the whole-ray test-time renderer).
 #pragma once
 #include "common.cuh"
 

@@ -163,6 +163,17 @@ class NGP(nn.Module):
             self._image_key = key
         return p16, self._image
 
+    # render / training-graph states cached on the module (captured CUDA graphs, static buffers, ctypes structures):
+    # rebuilt on demand, never part of a copy or a pickle of the model
+    _TRANSIENT = ("_whole_rays", "_whole_rays_pool", "_device_loop", "_train_graphs", "_image", "_image_key", "_layout")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            if k in state:
+                state[k] = {} if isinstance(state[k], dict) else None
+        return state
+
     def adopt_image(self, image):
         """A trainer that re-packs `image` after every optimiser step hands it over: the model's fused paths (and
         graphs captured over them) read that buffer from now on."""

@@ -138,10 +138,15 @@ class _WholeRays:
 
     @classmethod
     def get(cls, model, n_rays):
-        st = getattr(model, "_whole_rays", None)
-        if st is None or st.n != n_rays or st.dev != model.center.device:
-            st = cls(model, n_rays)
-            model._whole_rays = st
+        """One state (control block, first-hit list, captured graph) per ray count; a few are kept so that a frame
+        rendered in chunks with a shorter last chunk does not rebuild them every call."""
+        pool = model.__dict__.setdefault("_whole_rays_pool", {})
+        st = pool.get(n_rays)
+        if st is None or st.dev != model.center.device:
+            if len(pool) >= 4:
+                pool.pop(next(iter(pool)))
+            st = pool[n_rays] = cls(model, n_rays)
+        model.__dict__["_whole_rays"] = st                   # the state of the last call (tests / bench look at it)
         return st
 
     def __init__(self, model, n):

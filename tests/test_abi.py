@@ -71,6 +71,14 @@ def test_module_contract_on_cpu(built_lib):
     assert _WholeRays.supports(m, "auto") and _WholeRays.supports(m, True) and not _WholeRays.supports(m, False)
     assert not _WholeRays.supports(big, "auto") and _WholeRays.supports(big, True)
     assert not _WholeRays.supports(NGP(0.5, encoding="Frequency"), True)
+    # states cached on the module (captured graphs, ctypes structures) stay out of copies and pickles
+    import copy, io
+    small = NGP(0.5, log2_T=12)
+    small.__dict__["_whole_rays_pool"] = {7: object()}; small.__dict__["_device_loop"] = (lambda: 0)
+    twin = copy.deepcopy(small)
+    assert twin.__dict__["_whole_rays_pool"] == {} and twin.__dict__["_device_loop"] is None
+    assert torch.equal(twin.xyz_encoder.params, small.xyz_encoder.params)
+    torch.save(small, io.BytesIO())
     assert NGP(0.5, encoding="Frequency").xyz_encoder.params.numel() == 80 * 64 + 64 * 16
     # utils.load_ckpt-style round trip (ngp_pl/utils.py:4-25): keys under "model." stripped, then load_state_dict
     ckpt = {"state_dict": {"model." + k: v.clone() for k, v in sd.items()}}
