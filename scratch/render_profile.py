@@ -23,19 +23,19 @@ tr.sync_model()
 ro, rd = syn.get_rays(dd, pp[0])
 with torch.no_grad():
     for _ in range(2):
-        res = render(model, ro, rd, test_time=True, T_threshold=1e-2)
+        res = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=False)
     torch.cuda.synchronize()
     st = model._device_loop
     print("rounds", int(st.ctl_host[5]), "samples", res["total_samples"], "alive left", int(st.ctl_host[4]))
     import time
     ts = []
     for _ in range(6):
-        t0 = time.perf_counter(); res = render(model, ro, rd, test_time=True, T_threshold=1e-2); torch.cuda.synchronize()
+        t0 = time.perf_counter(); res = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=False); torch.cuda.synchronize()
         ts.append((time.perf_counter() - t0) * 1e3)
     print("frame ms", [round(t, 3) for t in ts])
     if os.environ.get("NOPROF"):
         sys.exit(0)
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-        res = render(model, ro, rd, test_time=True, T_threshold=1e-2)
+        res = render(model, ro, rd, test_time=True, T_threshold=1e-2, whole_rays=False)
         torch.cuda.synchronize()
     print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=50))
