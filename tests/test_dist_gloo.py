@@ -36,6 +36,30 @@ def _worker(rank, world, port, n):
             # (sigmoid's vectorised and tail code paths differ in the last ulp, and the subsets change which is used)
             torch.testing.assert_close(out[k], full[k], rtol=1e-6, atol=1e-7, msg=lambda m: f"{k} tile {tile}: {m}")
         assert out["total_samples"] == full["total_samples"]
+    # a renderer that writes pixels and totals straight into the rank's block (what rendering.py::_WholeRays does on the
+    # GPU): no packing on the host, totals from the gathered tails; a rank that reports a ray at the sample budget makes
+    # EVERY rank render the frame again with whole_rays=False
+    calls = []
+
+    def packed_render(ro_, rd_, packed_out=None, tail_out=None, whole_rays=True, cut_on_rank=None, **kw):
+        res = _fake_render(ro_, rd_)
+        if packed_out is None or whole_rays is False:
+            calls.append("generic")
+            return res
+        m = len(ro_)
+        packed_out[:m, 0:3] = res["rgb"]; packed_out[:m, 3] = res["depth"]; packed_out[:m, 4] = res["opacity"]
+        cnt = res["total_samples"]
+        tail_out.copy_(torch.tensor([cnt & 0xffff, (cnt >> 16) & 0xffff, cnt >> 32, 1.0 if cut_on_rank == rank else 0.0]))
+        calls.append("packed")
+        return {"rgb": packed_out[:m, 0:3], "depth": packed_out[:m, 3], "opacity": packed_out[:m, 4],
+                "total_samples": None, "tail": tail_out}
+    for cut, want_calls in ((None, ["packed"]), (1, ["packed", "generic"])):
+        calls.clear()
+        out = D.render_sharded(packed_render, ro, rd, tile=64, cut_on_rank=cut)
+        assert calls == want_calls, (cut, calls)
+        for k in ("rgb", "depth", "opacity"):
+            torch.testing.assert_close(out[k], full[k], rtol=1e-6, atol=1e-7)
+        assert out["total_samples"] == full["total_samples"]
     # bands cover the rays exactly once
     bounds = [D.shard_bounds(n, world, r) for r in range(world)]
     assert bounds[0][0] == 0 and bounds[-1][1] == n and all(bounds[i][1] == bounds[i + 1][0] for i in range(world - 1))
